@@ -1,0 +1,399 @@
+// C-ABI layer: DLPack validation, error classes, and the per-call orchestration of the flow.
+// Reference call graph being replaced: cFlow.call (M:1723-1798), cFlow.log_loss (M:1800-1848),
+// coupling_layer.forward_and_Jacobian / backward (M:1258-1394).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "cnf_internal.h"
+
+using namespace cnf;
+
+namespace {
+
+struct Ten {
+  float* p = nullptr;
+  int ndim = 0;
+  int64_t shape[6] = {0, 0, 0, 0, 0, 0};
+  int64_t numel = 0;
+  int64_t bytes = 0;
+};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[400];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  set_error("%s", buf);
+  return code;
+}
+
+// Borrow a DLPack tensor: fp32 (or raw bytes when `bytes_ok`), current CUDA device, compact, 16B aligned.
+int borrow(const DLManagedTensor* m, const char* name, int ndim, Ten* t, bool bytes_ok = false) {
+  if (!m) return fail(CNF_ERR_ARG, "%s: null tensor", name);
+  const DLTensor& d = m->dl_tensor;
+  if (d.device.device_type != kDLCUDA)
+    return fail(CNF_ERR_DEVICE, "%s: expected a CUDA tensor (DLPack device_type %d)", name, (int)d.device.device_type);
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(CNF_ERR_CUDA, "%s: cudaGetDevice failed", name);
+  if (d.device.device_id != dev)
+    return fail(CNF_ERR_DEVICE, "%s: tensor lives on cuda:%d but the current device is cuda:%d", name,
+                d.device.device_id, dev);
+  const bool f32 = d.dtype.code == kDLFloat && d.dtype.bits == 32 && d.dtype.lanes == 1;
+  if (!f32 && !bytes_ok) return fail(CNF_ERR_DTYPE, "%s: expected float32 (got code %d, %d bits)", name, (int)d.dtype.code, (int)d.dtype.bits);
+  if (ndim >= 0 && d.ndim != ndim) return fail(CNF_ERR_SHAPE, "%s: expected %d dimensions, got %d", name, ndim, d.ndim);
+  if (d.ndim > 6) return fail(CNF_ERR_SHAPE, "%s: too many dimensions", name);
+  t->ndim = d.ndim;
+  t->numel = 1;
+  for (int i = 0; i < d.ndim; ++i) {
+    t->shape[i] = d.shape[i];
+    t->numel *= d.shape[i];
+  }
+  if (d.strides) {
+    int64_t expect = 1;
+    for (int i = d.ndim - 1; i >= 0; --i) {
+      if (d.shape[i] != 1 && d.strides[i] != expect)
+        return fail(CNF_ERR_LAYOUT, "%s: tensor must be compact row-major (NHWC contiguous)", name);
+      expect *= d.shape[i];
+    }
+  }
+  char* p = (char*)d.data + d.byte_offset;
+  if (t->numel && ((uintptr_t)p & 15)) return fail(CNF_ERR_LAYOUT, "%s: data pointer must be 16-byte aligned", name);
+  t->p = (float*)p;
+  t->bytes = t->numel * ((d.dtype.bits * d.dtype.lanes + 7) / 8);
+  return CNF_OK;
+}
+
+int cuda_rc(int e, const char* what) {
+  if (e == 0) return CNF_OK;
+  if (e == (int)cudaErrorInvalidConfiguration)
+    return fail(CNF_ERR_UNSUPPORTED, "%s: shape not supported by the built kernels (%s)", what, cudaGetErrorString((cudaError_t)e));
+  return fail(CNF_ERR_CUDA, "%s: CUDA error %d (%s)", what, e, cudaGetErrorString((cudaError_t)e));
+}
+
+#define TRY(x)              \
+  do {                      \
+    int rc_ = (x);          \
+    if (rc_ != CNF_OK) return rc_; \
+  } while (0)
+
+int check_flow_tensor(const cnf_plan* p, const Ten& t, const char* name) {
+  if (t.shape[1] != p->H || t.shape[2] != p->W || t.shape[3] != p->D)
+    return fail(CNF_ERR_SHAPE, "%s: expected shape [B,%d,%d,%d], got [%lld,%lld,%lld,%lld]", name, p->H, p->W, p->D,
+                (long long)t.shape[0], (long long)t.shape[1], (long long)t.shape[2], (long long)t.shape[3]);
+  return CNF_OK;
+}
+
+int64_t max_coupling_ws(const cnf_plan* p, int64_t B) {
+  int64_t m = 0;
+  for (auto* c : p->couplings) {
+    const int64_t b = coupling_ws_bytes(c, B);
+    if (b > m) m = b;
+  }
+  return m;
+}
+
+// direction +1: all couplings in order, in place on `buf`; -1: reversed with the inverse law.
+int run_flow(const cnf_plan* p, const float* params, float* buf, int B, int direction, double* ldacc, void* ws,
+             void* stream) {
+  const int n = (int)p->couplings.size();
+  for (int s = 0; s < n; ++s) {
+    const int li = direction == 1 ? s : n - 1 - s;
+    const cnf_coupling* c = p->couplings[li];
+    FlowView v = make_view(buf, p->H, p->W, p->D, p->level[li]);
+    const int e = run_coupling(c, params + p->param_off[li], v, c->mask, v, B, direction == 1 ? HEAD_FWD : HEAD_INV,
+                               ldacc, nullptr, nullptr, ws, stream);
+    if (e) return cuda_rc(e, "coupling layer");
+  }
+  return CNF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnf_flow_forward(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params, DLManagedTensor* zy,
+                     DLManagedTensor* logdet, DLManagedTensor* workspace, void* stream) {
+  if (!p) return fail(CNF_ERR_ARG, "null plan");
+  Ten X, P, Z, L, W;
+  TRY(borrow(xy, "xy", 4, &X));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(zy, "zy", 4, &Z));
+  TRY(borrow(logdet, "logdet", 1, &L));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  TRY(check_flow_tensor(p, X, "xy"));
+  TRY(check_flow_tensor(p, Z, "zy"));
+  const int64_t B = X.shape[0];
+  if (Z.shape[0] != B || L.shape[0] != B) return fail(CNF_ERR_SHAPE, "zy/logdet batch size differs from xy (%lld)", (long long)B);
+  if (P.numel < p->param_count) return fail(CNF_ERR_SHAPE, "params: need %lld floats, got %lld", (long long)p->param_count, (long long)P.numel);
+  if (W.bytes < cnf_plan_workspace_bytes(p, B)) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)cnf_plan_workspace_bytes(p, B), (long long)W.bytes);
+  if (B == 0) return CNF_OK;
+  if (X.p != Z.p) TRY(cuda_rc(launch_copy(X.p, Z.p, X.numel, stream), "copy"));
+  double* ldacc = (double*)((char*)W.p + max_coupling_ws(p, B) + 256);
+  TRY(cuda_rc((int)cudaMemsetAsync(ldacc, 0, sizeof(double) * B, (cudaStream_t)stream), "memset"));
+  TRY(run_flow(p, P.p, Z.p, (int)B, 1, ldacc, W.p, stream));
+  return cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream), "logdet");
+}
+
+int cnf_flow_inverse(const cnf_plan* p, const DLManagedTensor* zy, const DLManagedTensor* params, DLManagedTensor* xy,
+                     DLManagedTensor* workspace, void* stream) {
+  if (!p) return fail(CNF_ERR_ARG, "null plan");
+  Ten Z, P, X, W;
+  TRY(borrow(zy, "zy", 4, &Z));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(xy, "xy", 4, &X));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  TRY(check_flow_tensor(p, Z, "zy"));
+  TRY(check_flow_tensor(p, X, "xy"));
+  const int64_t B = Z.shape[0];
+  if (X.shape[0] != B) return fail(CNF_ERR_SHAPE, "xy batch size differs from zy (%lld)", (long long)B);
+  if (P.numel < p->param_count) return fail(CNF_ERR_SHAPE, "params: need %lld floats, got %lld", (long long)p->param_count, (long long)P.numel);
+  if (W.bytes < cnf_plan_workspace_bytes(p, B)) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)cnf_plan_workspace_bytes(p, B), (long long)W.bytes);
+  if (B == 0) return CNF_OK;
+  if (X.p != Z.p) TRY(cuda_rc(launch_copy(Z.p, X.p, Z.numel, stream), "copy"));
+  return run_flow(p, P.p, X.p, (int)B, -1, nullptr, W.p, stream);
+}
+
+int cnf_prior_loss(const DLManagedTensor* zy, const DLManagedTensor* xy, const DLManagedTensor* logdet, int x_d,
+                   double lambda_y, DLManagedTensor* ll_z, DLManagedTensor* ll_y, DLManagedTensor* loss4, void* stream) {
+  Ten Z, X, L, A, Bt, F;
+  TRY(borrow(zy, "zy", 4, &Z));
+  TRY(borrow(xy, "xy", 4, &X));
+  TRY(borrow(logdet, "logdet", 1, &L));
+  TRY(borrow(ll_z, "ll_z", 1, &A));
+  TRY(borrow(ll_y, "ll_y", 1, &Bt));
+  TRY(borrow(loss4, "loss4", 1, &F));
+  for (int i = 0; i < 4; ++i)
+    if (Z.shape[i] != X.shape[i]) return fail(CNF_ERR_SHAPE, "zy and xy must have the same shape");
+  const int64_t B = Z.shape[0];
+  const int D = (int)Z.shape[3];
+  if (x_d < 1 || x_d > D) return fail(CNF_ERR_ARG, "x_d %d out of range for depth %d", x_d, D);
+  if (L.shape[0] != B || A.shape[0] != B || Bt.shape[0] != B || F.shape[0] != 4)
+    return fail(CNF_ERR_SHAPE, "logdet/ll_z/ll_y must be [B] and loss4 [4]");
+  if (B == 0) return fail(CNF_ERR_ARG, "empty batch: the batch means of the loss are undefined");
+  return cuda_rc(launch_prior_loss(Z.p, X.p, L.p, (int)B, Z.shape[1] * Z.shape[2], D, x_d, lambda_y, A.p, Bt.p, F.p, stream), "prior loss");
+}
+
+int cnf_flow_log_loss(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params, DLManagedTensor* zy,
+                      DLManagedTensor* ll_z, DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
+                      DLManagedTensor* workspace, void* stream) {
+  if (!p) return fail(CNF_ERR_ARG, "null plan");
+  Ten X;
+  TRY(borrow(xy, "xy", 4, &X));
+  if (X.shape[0] == 0) return fail(CNF_ERR_ARG, "empty batch: the batch means of the loss are undefined");
+  TRY(cnf_flow_forward(p, xy, params, zy, logdet, workspace, stream));
+  return cnf_prior_loss(zy, xy, logdet, p->x_d, p->lambda_y, ll_z, ll_y, loss4, stream);
+}
+
+static int coupling_common(const cnf_coupling* c, const DLManagedTensor* in, const DLManagedTensor* params,
+                           DLManagedTensor* out, DLManagedTensor* logdet, DLManagedTensor* workspace, void* stream,
+                           int mode) {
+  if (!c) return fail(CNF_ERR_ARG, "null coupling layer");
+  Ten I, P, O, L, W;
+  TRY(borrow(in, "input", 4, &I));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(out, "output", 4, &O));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  if (I.shape[1] != c->H || I.shape[2] != c->W || I.shape[3] != c->D)  // tf.ensure_shape, M:1276 / M:1348
+    return fail(CNF_ERR_SHAPE, "input: expected shape [B,%d,%d,%d], got [%lld,%lld,%lld,%lld]", c->H, c->W, c->D,
+                (long long)I.shape[0], (long long)I.shape[1], (long long)I.shape[2], (long long)I.shape[3]);
+  for (int i = 0; i < 4; ++i)
+    if (O.shape[i] != I.shape[i]) return fail(CNF_ERR_SHAPE, "output must have the input's shape");
+  if (O.p == I.p) return fail(CNF_ERR_ARG, "output must not alias input");
+  const int64_t B = I.shape[0];
+  if (P.numel < 2 * c->net_stride) return fail(CNF_ERR_SHAPE, "params: need %lld floats, got %lld", (long long)(2 * c->net_stride), (long long)P.numel);
+  if (W.bytes < cnf_coupling_workspace_bytes(c, B)) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)cnf_coupling_workspace_bytes(c, B), (long long)W.bytes);
+  double* ldacc = nullptr;
+  if (mode == HEAD_FWD) {
+    TRY(borrow(logdet, "logdet", 1, &L));
+    if (L.shape[0] != B) return fail(CNF_ERR_SHAPE, "logdet must be [B]");
+    ldacc = (double*)((char*)W.p + coupling_ws_bytes(c, B) + 256);
+  }
+  if (B == 0) return CNF_OK;
+  TRY(cuda_rc(launch_copy(I.p, O.p, I.numel, stream), "copy"));
+  if (ldacc) TRY(cuda_rc((int)cudaMemsetAsync(ldacc, 0, sizeof(double) * B, (cudaStream_t)stream), "memset"));
+  FlowView v = make_view(O.p, c->H, c->W, c->D, 0);
+  TRY(cuda_rc(run_coupling(c, P.p, v, c->mask, v, (int)B, mode, ldacc, nullptr, nullptr, W.p, stream), "coupling layer"));
+  if (ldacc) return cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream), "logdet");
+  return CNF_OK;
+}
+
+int cnf_coupling_forward(const cnf_coupling* c, const DLManagedTensor* u, const DLManagedTensor* params, DLManagedTensor* v,
+                         DLManagedTensor* logdet, DLManagedTensor* workspace, void* stream) {
+  return coupling_common(c, u, params, v, logdet, workspace, stream, HEAD_FWD);
+}
+
+int cnf_coupling_backward(const cnf_coupling* c, const DLManagedTensor* v, const DLManagedTensor* params, DLManagedTensor* u,
+                          DLManagedTensor* workspace, void* stream) {
+  return coupling_common(c, v, params, u, nullptr, workspace, stream, HEAD_INV);
+}
+
+int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1c, const DLManagedTensor* params, DLManagedTensor* A,
+                      DLManagedTensor* b, DLManagedTensor* workspace, void* stream) {
+  if (!c) return fail(CNF_ERR_ARG, "null coupling layer");
+  Ten I, P, TA, TB, W;
+  TRY(borrow(u1c, "u1_compressed", 4, &I));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(A, "A", 4, &TA));
+  TRY(borrow(b, "b", 4, &TB));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  if (I.shape[1] != c->h || I.shape[2] != c->w || I.shape[3] != c->c1)
+    return fail(CNF_ERR_SHAPE, "u1_compressed: expected shape [B,%d,%d,%d]", c->h, c->w, c->c1);
+  const int64_t B = I.shape[0];
+  for (const Ten* t : {&TA, &TB})
+    if (t->shape[0] != B || t->shape[1] != c->h || t->shape[2] != c->w || t->shape[3] != c->c2)
+      return fail(CNF_ERR_SHAPE, "A/b: expected shape [B,%d,%d,%d]", c->h, c->w, c->c2);
+  if (P.numel < 2 * c->net_stride) return fail(CNF_ERR_SHAPE, "params: need %lld floats, got %lld", (long long)(2 * c->net_stride), (long long)P.numel);
+  if (W.bytes < cnf_coupling_workspace_bytes(c, B)) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)cnf_coupling_workspace_bytes(c, B), (long long)W.bytes);
+  if (B == 0) return CNF_OK;
+  FlowView v = make_view(I.p, c->h, c->w, c->c1, 0);
+  return cuda_rc(run_coupling(c, P.p, v, MASK_DENSE, v, (int)B, HEAD_EMIT, nullptr, TA.p, TB.p, W.p, stream), "s/t networks");
+}
+
+int cnf_coupling_law(const DLManagedTensor* u, const DLManagedTensor* s, const DLManagedTensor* t, int which_mask,
+                     int inverse, DLManagedTensor* v, DLManagedTensor* logdet, void* stream) {
+  Ten U, S, T, V, L;
+  TRY(borrow(u, "u", 4, &U));
+  TRY(borrow(s, "s", 4, &S));
+  TRY(borrow(t, "t", 4, &T));
+  TRY(borrow(v, "v", 4, &V));
+  if (which_mask < 0 || which_mask > 3) return fail(CNF_ERR_ARG, "which_mask must be one of 0,1,2,3");
+  const int64_t B = U.shape[0];
+  const int H = (int)U.shape[1], Wd = (int)U.shape[2], D = (int)U.shape[3];
+  if (H % 2 || Wd % 2) return fail(CNF_ERR_ARG, "u/v must have spatial dimensions divisible by 2.");
+  const int mc = which_mask ^ 1;
+  int h, w, c2;
+  if (mc < 2) { h = H / 2; w = Wd / 2; c2 = 2 * D; }
+  else { h = H; w = Wd; c2 = mc == 2 ? (D + 1) / 2 : D / 2; }
+  for (const Ten* x : {&S, &T})
+    if (x->shape[0] != B || x->shape[1] != h || x->shape[2] != w || x->shape[3] != c2)
+      return fail(CNF_ERR_SHAPE, "s/t: expected the compressed complement shape [B,%d,%d,%d]", h, w, c2);
+  for (int i = 0; i < 4; ++i)
+    if (V.shape[i] != U.shape[i]) return fail(CNF_ERR_SHAPE, "v must have u's shape");
+  float* lp = nullptr;
+  if (logdet) {
+    TRY(borrow(logdet, "logdet", 1, &L));
+    if (L.shape[0] != B) return fail(CNF_ERR_SHAPE, "logdet must be [B]");
+    lp = L.p;
+  }
+  if ((int64_t)H * Wd * D >= (1LL << 31)) return fail(CNF_ERR_UNSUPPORTED, "sample too large");
+  if (B == 0) return CNF_OK;
+  if (B > 65535) return fail(CNF_ERR_UNSUPPORTED, "batch > 65535 in one call");
+  return cuda_rc(launch_coupling_law(U.p, S.p, T.p, V.p, lp, (int)B, H, Wd, D, which_mask, inverse, stream), "coupling law");
+}
+
+int cnf_mask(const DLManagedTensor* uv, int which_mask, int compress, DLManagedTensor* out, void* stream) {
+  Ten U, O;
+  TRY(borrow(uv, "uv", 4, &U));
+  TRY(borrow(out, "out", 4, &O));
+  if (which_mask < 0 || which_mask > 3) return fail(CNF_ERR_ARG, "which_mask must be one of 0,1,2,3");
+  const int B = (int)U.shape[0], H = (int)U.shape[1], W = (int)U.shape[2], D = (int)U.shape[3];
+  if (H % 2 || W % 2) return fail(CNF_ERR_ARG, "u/v must have spatial dimensions divisible by 2.");
+  int64_t want[4] = {B, H, W, D};
+  if (compress) {
+    if (which_mask < 2) { want[1] = H / 2; want[2] = W / 2; want[3] = 2 * D; }
+    else want[3] = which_mask == 2 ? (D + 1) / 2 : D / 2;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (O.shape[i] != want[i]) return fail(CNF_ERR_SHAPE, "out: expected [%lld,%lld,%lld,%lld]", (long long)want[0], (long long)want[1], (long long)want[2], (long long)want[3]);
+  return cuda_rc(launch_mask(U.p, O.p, B, H, W, D, which_mask, compress, stream), "mask");
+}
+
+int cnf_decompress_mask(const DLManagedTensor* uvc, int which_mask, DLManagedTensor* out, void* stream) {
+  Ten U, O;
+  TRY(borrow(uvc, "uv_masked_compressed", 4, &U));
+  TRY(borrow(out, "out", 4, &O));
+  if (which_mask < 0 || which_mask > 3) return fail(CNF_ERR_ARG, "which_mask must be one of 0,1,2,3");
+  const int B = (int)O.shape[0], H = (int)O.shape[1], W = (int)O.shape[2], D = (int)O.shape[3];
+  if (H % 2 || W % 2) return fail(CNF_ERR_ARG, "u/v must have spatial dimensions divisible by 2.");
+  int64_t want[4] = {B, H, W, D};
+  if (which_mask < 2) { want[1] = H / 2; want[2] = W / 2; want[3] = 2 * D; }
+  else want[3] = which_mask == 2 ? (D + 1) / 2 : D / 2;
+  for (int i = 0; i < 4; ++i)
+    if (U.shape[i] != want[i]) return fail(CNF_ERR_SHAPE, "uv_masked_compressed: expected [%lld,%lld,%lld,%lld]", (long long)want[0], (long long)want[1], (long long)want[2], (long long)want[3]);
+  return cuda_rc(launch_decompress(U.p, O.p, B, H, W, D, which_mask, stream), "decompress_mask");
+}
+
+int cnf_space_to_depth(const DLManagedTensor* in, DLManagedTensor* out, void* stream) {
+  Ten I, O;
+  TRY(borrow(in, "in", 4, &I));
+  TRY(borrow(out, "out", 4, &O));
+  const int B = (int)I.shape[0], H = (int)I.shape[1], W = (int)I.shape[2], C = (int)I.shape[3];
+  if (H % 2 || W % 2) return fail(CNF_ERR_ARG, "u must have spatial dimensions divisible by 2.");  // M:175-177
+  if (O.shape[0] != B || O.shape[1] != H / 2 || O.shape[2] != W / 2 || O.shape[3] != 4 * C)
+    return fail(CNF_ERR_SHAPE, "out: expected [%d,%d,%d,%d]", B, H / 2, W / 2, 4 * C);
+  return cuda_rc(launch_space_to_depth(I.p, O.p, B, H, W, C, 0, stream), "space_to_depth");
+}
+
+int cnf_depth_to_space(const DLManagedTensor* in, DLManagedTensor* out, void* stream) {
+  Ten I, O;
+  TRY(borrow(in, "in", 4, &I));
+  TRY(borrow(out, "out", 4, &O));
+  const int B = (int)I.shape[0], h = (int)I.shape[1], w = (int)I.shape[2], C4 = (int)I.shape[3];
+  if (C4 % 4) return fail(CNF_ERR_ARG, "v must have channel dimensions divisible by 4.");  // M:208-209
+  if (O.shape[0] != B || O.shape[1] != 2 * h || O.shape[2] != 2 * w || O.shape[3] != C4 / 4)
+    return fail(CNF_ERR_SHAPE, "out: expected [%d,%d,%d,%d]", B, 2 * h, 2 * w, C4 / 4);
+  return cuda_rc(launch_space_to_depth(I.p, O.p, B, 2 * h, 2 * w, C4 / 4, 1, stream), "depth_to_space");
+}
+
+// ---- toy ------------------------------------------------------------------------------------
+static long long toy_net_size_h(int I, int num_layers) {
+  return 2LL * I + I + (long long)num_layers * ((long long)I * I + I) + 2LL * I + 4;
+}
+
+int64_t cnf_toy_layer_offset(int layer, int intermediate_dims, int num_layers) {
+  return 2 * toy_net_size_h(intermediate_dims, num_layers) * layer;
+}
+
+int64_t cnf_toy_param_count(int num_coupling_layers, int intermediate_dims, int num_layers) {
+  return cnf_toy_layer_offset(num_coupling_layers, intermediate_dims, num_layers);
+}
+
+static int toy_check(int n, int width, int num_layers, const int* order) {
+  if (n < 1 || n > 256) return fail(CNF_ERR_UNSUPPORTED, "1..256 coupling layers are supported, got %d", n);
+  if (width != 8 && width != 16 && width != 32 && width != 64)
+    return fail(CNF_ERR_UNSUPPORTED, "intermediate_dims must be one of 8, 16, 32, 64 (got %d)", width);
+  if (num_layers < 0) return fail(CNF_ERR_ARG, "num_layers must be >= 0");
+  if (!order) return fail(CNF_ERR_ARG, "null mask_indices");
+  for (int i = 0; i < n; ++i)
+    if (order[i] < 0 || order[i] >= n) return fail(CNF_ERR_ARG, "mask_indices[%d] = %d out of range", i, order[i]);
+  return CNF_OK;
+}
+
+int cnf_toy_call(const DLManagedTensor* u, const DLManagedTensor* params, const int* mask_indices, int n, int width,
+                 int num_layers, int direction, DLManagedTensor* v, DLManagedTensor* logdet, void* stream) {
+  Ten U, P, V, L;
+  TRY(toy_check(n, width, num_layers, mask_indices));
+  if (direction != 1 && direction != -1) return fail(CNF_ERR_ARG, "direction must be +1 or -1");
+  TRY(borrow(u, "u", 2, &U));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(v, "v", 2, &V));
+  TRY(borrow(logdet, "logdet", 1, &L));
+  if (U.shape[1] != 3 || V.shape[1] != 3 || V.shape[0] != U.shape[0] || L.shape[0] != U.shape[0])
+    return fail(CNF_ERR_SHAPE, "u, v must be [B,3] and logdet [B]");
+  if (P.numel < cnf_toy_param_count(n, width, num_layers)) return fail(CNF_ERR_SHAPE, "params too small");
+  return cuda_rc(launch_toy(U.p, P.p, mask_indices, n, width, num_layers, direction, V.p, L.p, (int)U.shape[0], stream), "toy flow");
+}
+
+int cnf_toy_log_loss(const DLManagedTensor* xy, const DLManagedTensor* params, const int* mask_indices, int n, int width,
+                     int num_layers, int x_d, double lambda_y, DLManagedTensor* zy, DLManagedTensor* ll_z,
+                     DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4, void* stream) {
+  Ten X, A, Bt, L, F, Z;
+  TRY(borrow(xy, "xy", 2, &X));
+  TRY(borrow(zy, "zy", 2, &Z));
+  TRY(borrow(ll_z, "ll_z", 1, &A));
+  TRY(borrow(ll_y, "ll_y", 1, &Bt));
+  TRY(borrow(logdet, "logdet", 1, &L));
+  TRY(borrow(loss4, "loss4", 1, &F));
+  const int64_t B = X.shape[0];
+  if (B == 0) return fail(CNF_ERR_ARG, "empty batch: the batch means of the loss are undefined");
+  if (x_d < 1 || x_d > 3) return fail(CNF_ERR_ARG, "x_d out of range");
+  if (A.shape[0] != B || Bt.shape[0] != B || F.shape[0] != 4) return fail(CNF_ERR_SHAPE, "ll_z/ll_y must be [B] and loss4 [4]");
+  TRY(cnf_toy_call(xy, params, mask_indices, n, width, num_layers, -1, zy, logdet, stream));
+  return cuda_rc(launch_toy_loss(Z.p, X.p, L.p, (int)B, x_d, lambda_y, A.p, Bt.p, F.p, stream), "toy loss");
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// Internal (non-ABI) structures shared by the host planner, the launchers and the C-ABI layer.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "cnf.h"
+
+#define CNF_LRELU_SLOPE 0.3f  // keras LeakyReLU() default (F:345)
+#define CNF_LN_EPS 1e-3       // keras LayerNormalization default epsilon (F:358)
+
+namespace cnf {
+
+void set_error(const char* fmt, ...);
+
+struct ParamEntry {
+  std::string name;
+  int64_t offset;  // floats from the start of the net's block
+  int ndim;
+  int64_t shape[4];
+  int role;  // 0 kernel, 1 bias, 2 gamma, 3 beta, 4 tanh scale
+};
+
+struct Branch {
+  int dil, channels, groups, gin, gout;
+  int out_off;            // channel offset inside the concat (F:590)
+  int64_t w_off, b_off;   // packed [group][ky][kx][gin][gout] kernels, [channels] biases
+};
+
+struct ResBlockLayout {
+  int64_t ln1_g, ln1_b, pw1_w, pw1_b, ln2_g, ln2_b, ln3_g, ln3_b, pw2_w, pw2_b;
+  std::vector<Branch> br;
+};
+
+}  // namespace cnf
+
+// One coupling layer: shapes (M:355-439, M:474-498, M:1087-1104) and the flat parameter layout of
+// its two s/t networks (net A at 0, net b at net_stride; identical internal layout).
+struct cnf_coupling {
+  int H, W, D, mask, mask_c, R, card, nk, ks, ln;
+  int h, w, c1, c2, cat;
+  std::vector<int> dil;
+  int64_t stem_w, stem_b, lnf_g, lnf_b, head_w, head_b, tanh_w;
+  std::vector<cnf::ResBlockLayout> rb;
+  int64_t net_stride;
+  std::vector<cnf::ParamEntry> entries;
+  int n_ln() const { return ln ? 3 * R + 1 : 0; }
+  int hw() const { return h * w; }
+};
+
+struct cnf_plan {
+  int H, W, D, x_d, ks, ln;
+  double lambda_y;
+  std::vector<int> sq, resnext, nk, card, scale, npf;
+  std::vector<cnf_block_info> blocks;
+  struct LayerRef { int kind, aux; };
+  std::vector<LayerRef> layers;
+  std::vector<cnf_coupling*> couplings;
+  std::vector<int64_t> param_off;
+  std::vector<int> level;
+  int64_t param_count;
+  ~cnf_plan();
+};
+
+namespace cnf {
+
+// Strided view of an "active" tensor inside the original-layout [B,H,W,D] buffer: after L
+// squeeze+factor steps the active tensor is rows h = 2^L-1 (mod 2^L), each row reshaped to
+// (W/2^L, 2^L*D) (tests/test_oracle_masks.py::test_active_tensor_is_a_strided_view).
+struct FlowView {
+  float* base;
+  long long sb, sy, sx;  // element strides: sample, active row, active pixel (channels contiguous)
+  int H, W, D;           // active shape
+};
+
+inline FlowView make_view(float* buf, int H0, int W0, int D0, int level) {
+  FlowView v;
+  const int S = 1 << level;
+  v.base = buf + (long long)(S - 1) * W0 * D0;
+  v.sb = (long long)H0 * W0 * D0;
+  v.sy = (long long)S * W0 * D0;
+  v.sx = (long long)S * D0;
+  v.H = H0 / S;
+  v.W = W0 / S;
+  v.D = D0 * S;
+  return v;
+}
+
+enum HeadMode { HEAD_FWD = 0, HEAD_INV = 1, HEAD_EMIT = 2 };
+enum { MASK_DENSE = 4 };  // "already compressed" input for A_wrapper/b_wrapper (M:452-472)
+
+struct CouplingWorkspace {
+  float *X, *Y1, *Y2;
+  double* stats;  // [n_ln][2][B][2]
+};
+int64_t coupling_ws_bytes(const cnf_coupling* c, int64_t B);
+CouplingWorkspace carve_ws(const cnf_coupling* c, int64_t B, void* ws);
+
+// launchers (kernels.cu); all enqueue on `stream`, return cudaError as int (0 ok)
+int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask,
+                 FlowView out_view, int B, int mode, double* logdet_acc, float* outA, float* outB,
+                 void* ws, void* stream);
+int launch_copy(const float* src, float* dst, int64_t n, void* stream);
+int launch_logdet_finalize(const double* acc, float* out, int B, void* stream);
+int launch_prior_loss(const float* zy, const float* xy, const float* logdet, int B, int64_t HW, int D,
+                      int x_d, double lambda_y, float* ll_z, float* ll_y, float* loss4, void* stream);
+int launch_coupling_law(const float* u, const float* s, const float* t, float* v, float* logdet, int B,
+                        int H, int W, int D, int mask, int inverse, void* stream);
+int launch_mask(const float* uv, float* out, int B, int H, int W, int D, int mask, int compress,
+                void* stream);
+int launch_decompress(const float* uvc, float* out, int B, int H, int W, int D, int mask, void* stream);
+int launch_space_to_depth(const float* in, float* out, int B, int H, int W, int C, int inverse,
+                          void* stream);
+int launch_toy(const float* u, const float* params, const int* mask_idx_host, int n_layers_c, int width,
+               int num_layers, int direction, float* v, float* logdet, int B, void* stream);
+int launch_toy_loss(const float* zy, const float* xy, const float* logdet, int B, int x_d, double lambda_y,
+                    float* ll_z, float* ll_y, float* loss4, void* stream);
+
+}  // namespace cnf

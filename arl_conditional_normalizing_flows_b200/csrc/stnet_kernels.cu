@@ -1,0 +1,804 @@
+// s/t sub-network kernels of one coupling layer (fp32-exact path) and their orchestration.
+//
+// What the reference computes (conv_cINN_make_model.py M:1076-1213 with
+// conv_cINN_base_functions.py F:330-362, F:364-413, F:501-627), per net (A and b):
+//   x = Conv3x3(u1c)                                    "stem"  (M:1114, M:1159)
+//   R x { a = LN(LReLU(x)); y1 = Conv1x1(a)             "pw1"   (F:552-563)
+//         b = LN(LReLU(y1)); y2 = concat_d GroupedDilatedConv3x3(b[..., :nk//d])  "gconv" (F:565-590)
+//         c = LN(LReLU(y2)); x = x + Conv1x1(c) }       "pw2"   (F:604-625)
+//   out = Conv3x3(LN(LReLU(x)))                         "head"  (M:1133-1150); A = w*tanh(out) (M:1198)
+// followed by the coupling law and the per-sample log-det (M:1307-1326 / M:1379-1394).
+//
+// How it is laid out here: LayerNorm spans the whole sample, so every conv kernel (i) applies the
+// LReLU+LN of its INPUT while staging it into shared memory, using the per-sample (sum, sumsq) the
+// producing kernel left behind, and (ii) accumulates the (sum, sumsq) of LReLU(output) for its
+// consumer.  Both nets run in the same launches (blockIdx.z / in-CTA).  The masked gather of u1
+// (M:723-759) is folded into the stem's loads, and the head's epilogue applies tanh*w, exp, the
+// affine law and the decompress scatter (M:903-1071) straight into the flow buffer, so s, t and
+// the compressed tensors never exist in HBM.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "cnf_internal.h"
+#include "device_utils.cuh"
+
+namespace cnf {
+
+// ------------------------------------------------------------------------------------------
+// 1. GEMM-shaped convs: stem (implicit im2col of the masked input) and 1x1 convs.
+//    out[m, n] = sum_k A[m, k] W[k, n] + bias[n] (+ res[m, n]),  m = pixel of ONE sample.
+// ------------------------------------------------------------------------------------------
+struct GemmArgs {
+  // A operand
+  const float* in;            // PW: [2][B][hw][K]
+  long long in_net_stride;
+  FlowView view;              // STEM: masked gather source
+  int mask, h, w, c1, ks;
+  // parameters
+  const float* params;        // layer base; net n at params + n*net_stride
+  long long net_stride, w_off, b_off, g_off, be_off;
+  const double* stats_in;     // [2][B][2] or nullptr
+  double* stats_out;          // [2][B][2] or nullptr
+  float* out;                 // [2][B][hw][N]
+  const float* res;           // residual, same layout as out, may alias out; or nullptr
+  long long out_net_stride;
+  int B, hw, K, N, KC, ln;
+};
+
+template <int TN, int NQ, int RM, bool STEM>
+__global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
+  constexpr int NT = 128;
+  constexpr int CT = TN / (4 * NQ);  // threads along n
+  constexpr int RT = NT / CT;        // threads along m
+  constexpr int TM = RM * RT;
+  constexpr int RN = 4 * NQ;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[64];
+
+  const int tid = threadIdx.x;
+  const int tn = tid % CT, tm = tid / CT;
+  const int tiles_n = (a.N + TN - 1) / TN;
+  const int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+  const int b = blockIdx.y, net = blockIdx.z;
+  const int m0 = tile_m * TM, n0 = tile_n * TN;
+  const int KS = a.KC + 4;
+  float* As = smem;             // [TM][KS]
+  float* Bs = smem + TM * KS;   // [KC][TN]
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* Wg = P + a.w_off;
+  const bool n_vec = (a.N % 4) == 0;
+  const bool k_vec = (a.K % 4) == 0;
+
+  float mean = 0.f, rstd = 1.f;
+  if (!STEM && a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.hw * (double)a.K, mean, rstd);
+
+  float acc[RM][RN];
+#pragma unroll
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int c = 0; c < RN; ++c) acc[r][c] = 0.f;
+
+  for (int kc0 = 0; kc0 < a.K; kc0 += a.KC) {
+    const int kc = min(a.KC, ((a.K - kc0) + 3) & ~3);  // padded length of this K chunk
+    __syncthreads();
+    // ---- weights: Bs[k][n] = W[kc0+k][n0+n] (zero outside)
+    for (int idx = tid; idx < kc * (TN / 4); idx += NT) {
+      const int k = idx / (TN / 4), nq = idx % (TN / 4);
+      const int gk = kc0 + k, n = n0 + nq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < a.K) {
+        const float* src = Wg + (long long)gk * a.N + n;
+        if (n_vec && n + 3 < a.N) {
+          v = ld4(src);
+        } else {
+          if (n + 0 < a.N) v.x = src[0];
+          if (n + 1 < a.N) v.y = src[1];
+          if (n + 2 < a.N) v.z = src[2];
+          if (n + 3 < a.N) v.w = src[3];
+        }
+      }
+      st4(&Bs[k * TN + nq * 4], v);
+    }
+    // ---- activations
+    if (STEM) {
+      const int pad = (a.ks - 1) / 2;
+      for (int idx = tid; idx < TM * kc; idx += NT) {
+        const int m = idx / kc, k = idx % kc;
+        const int gk = kc0 + k, p = m0 + m;
+        float v = 0.f;
+        if (p < a.hw && gk < a.K) {
+          const int y = p / a.w, x = p % a.w;
+          const int tap = gk / a.c1, ci = gk % a.c1;
+          const int iy = y + tap / a.ks - pad, ix = x + tap % a.ks - pad;
+          if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w)
+            v = a.view.base[comp_off(a.view, a.mask, b, iy, ix, ci)];
+        }
+        As[m * KS + k] = v;
+      }
+    } else {
+      const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.hw * a.K;
+      const float* gam = P + a.g_off;
+      const float* bet = P + a.be_off;
+      if (k_vec) {
+        const int kq_n = kc / 4;
+        for (int idx = tid; idx < TM * kq_n; idx += NT) {
+          const int m = idx / kq_n, kq = idx % kq_n;
+          const int p = m0 + m;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p < a.hw) {
+            const long long e = (long long)p * a.K + kc0 + kq * 4;
+            v = ld4(src_s + e);
+            v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w);
+            if (a.ln) {
+              const float4 g = ld4(gam + e), be = ld4(bet + e);
+              v.x = (v.x - mean) * rstd * g.x + be.x;
+              v.y = (v.y - mean) * rstd * g.y + be.y;
+              v.z = (v.z - mean) * rstd * g.z + be.z;
+              v.w = (v.w - mean) * rstd * g.w + be.w;
+            }
+          }
+          st4(&As[m * KS + kq * 4], v);
+        }
+      } else {
+        for (int idx = tid; idx < TM * kc; idx += NT) {
+          const int m = idx / kc, k = idx % kc;
+          const int gk = kc0 + k, p = m0 + m;
+          float v = 0.f;
+          if (p < a.hw && gk < a.K) {
+            const long long e = (long long)p * a.K + gk;
+            v = lrelu(src_s[e]);
+            if (a.ln) v = (v - mean) * rstd * gam[e] + bet[e];
+          }
+          As[m * KS + k] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- FFMA tile
+    for (int k4 = 0; k4 < kc; k4 += 4) {
+      float4 av[RM];
+#pragma unroll
+      for (int r = 0; r < RM; ++r) av[r] = ld4(&As[(tm + RT * r) * KS + k4]);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float bv[RN];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 t = ld4(&Bs[(k4 + kk) * TN + q * (TN / NQ) + tn * 4]);
+          bv[q * 4 + 0] = t.x; bv[q * 4 + 1] = t.y; bv[q * 4 + 2] = t.z; bv[q * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          const float ar = kk == 0 ? av[r].x : kk == 1 ? av[r].y : kk == 2 ? av[r].z : av[r].w;
+#pragma unroll
+          for (int c = 0; c < RN; ++c) acc[r][c] = fmaf(ar, bv[c], acc[r][c]);
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: bias (+ residual), store, stats of LReLU(out) for the consumer's LayerNorm
+  const float* bias = P + a.b_off;
+  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.hw * a.N;
+  const float* res_s = a.res ? a.res + (long long)net * a.out_net_stride + (long long)b * a.hw * a.N : nullptr;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int r = 0; r < RM; ++r) {
+    const int p = m0 + tm + RT * r;
+    if (p >= a.hw) continue;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int n = n0 + q * (TN / NQ) + tn * 4;
+      if (n >= a.N) continue;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = acc[r][q * 4 + j];
+      const long long e = (long long)p * a.N + n;
+      if (n_vec) {
+        const float4 bb = ld4(bias + n);
+        o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+        if (res_s) {
+          const float4 rr = ld4(res_s + e);
+          o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+        }
+        st4(out_s + e, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float l = lrelu(o[j]);
+          s1 += l;
+          s2 += l * l;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n + j < a.N) {
+            float v = o[j] + bias[n + j];
+            if (res_s) v += res_s[e + j];
+            out_s[e + j] = v;
+            const float l = lrelu(v);
+            s1 += l;
+            s2 += l * l;
+          }
+        }
+      }
+    }
+  }
+  if (a.stats_out) {
+    double d1, d2;
+    block_sum2(s1, s2, red, d1, d2);
+    if (tid == 0) {
+      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+      atomicAdd(so, d1);
+      atomicAdd(so + 1, d2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. Grouped dilated 3x3 convs of one residual block, all dilation branches in one launch,
+//    written straight into the concat layout (F:397-411, F:577-590).
+// ------------------------------------------------------------------------------------------
+struct GconvBranch {
+  int dil, groups, gin, gout, out_off, first_item;
+  long long w_off, b_off;
+};
+struct GconvArgs {
+  const float* in;    // [2][B][hw][Cin]
+  float* out;         // [2][B][hw][Cout]
+  long long in_net_stride, out_net_stride;
+  const float* params;
+  long long net_stride, g_off, be_off;
+  const double* stats_in;
+  double* stats_out;
+  int B, h, w, Cin, Cout, ln, ks;
+  int TH, TW, tiles_y, tiles_x;
+  int n_br;
+  GconvBranch br[CNF_MAX_BRANCHES];
+};
+
+constexpr int GC_NT = 256;
+constexpr int GC_PX = 4;  // pixels per thread
+
+__host__ __device__ inline int gc_stride(int gin) { return gin + ((gin % 8) == 0 ? 4 : 0); }
+
+struct GcGeom {
+  int dil, ks, gin, gout, cbase, w, Cout;  // cbase = first output channel of this group in the concat
+};
+
+template <int G>
+__device__ __forceinline__ void gconv_compute(const GcGeom q, const float* in_s, const float* w_s,
+                                              const float* b_s, int SW, int GS, int th, int tw, int y0,
+                                              int x0, float* out_s, float& s1, float& s2) {
+  const int tid = threadIdx.x;
+  const int TP = th * tw;
+  const int npx = (TP + GC_NT - 1) / GC_NT;
+  const int d = q.dil, ks = q.ks;
+  float acc[GC_PX][G];
+  int poff[GC_PX];
+#pragma unroll
+  for (int j = 0; j < GC_PX; ++j) {
+    const int p = min(tid + j * GC_NT, TP - 1);
+    poff[j] = ((p / tw) * SW + (p % tw)) * GS;
+#pragma unroll
+    for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
+  }
+  for (int ky = 0; ky < ks; ++ky) {
+    for (int kx = 0; kx < ks; ++kx) {
+      const int toff = (ky * d * SW + kx * d) * GS;
+      const float* wt = w_s + (ky * ks + kx) * G * G;
+      float xv[GC_PX][G];
+#pragma unroll
+      for (int j = 0; j < GC_PX; ++j) {
+        if (j < npx) {
+          const float* src = in_s + poff[j] + toff;
+          if (G % 4 == 0) {
+#pragma unroll
+            for (int c4 = 0; c4 < G; c4 += 4) {
+              const float4 t = ld4(src + c4);
+              xv[j][c4] = t.x; xv[j][c4 + 1] = t.y; xv[j][c4 + 2] = t.z; xv[j][c4 + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < G; ++c) xv[j][c] = src[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < G; ++ci) {
+        float wv[G];
+        if (G % 4 == 0) {
+#pragma unroll
+          for (int c4 = 0; c4 < G; c4 += 4) {
+            const float4 t = ld4(wt + ci * G + c4);
+            wv[c4] = t.x; wv[c4 + 1] = t.y; wv[c4 + 2] = t.z; wv[c4 + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < G; ++c) wv[c] = wt[ci * G + c];
+        }
+#pragma unroll
+        for (int j = 0; j < GC_PX; ++j) {
+          if (j < npx) {
+#pragma unroll
+            for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[j][ci], wv[co], acc[j][co]);
+          }
+        }
+      }
+    }
+  }
+  const int cbase = q.cbase;
+  const bool vec = (G % 4 == 0) && (q.Cout % 4 == 0) && (cbase % 4 == 0);
+#pragma unroll
+  for (int j = 0; j < GC_PX; ++j) {
+    const int p = tid + j * GC_NT;
+    if (j < npx && p < TP) {
+      const int y = y0 + p / tw, x = x0 + p % tw;
+      float* dst = out_s + ((long long)y * q.w + x) * q.Cout + cbase;
+      float o[G];
+#pragma unroll
+      for (int co = 0; co < G; ++co) {
+        o[co] = acc[j][co] + b_s[co];
+        const float l = lrelu(o[co]);
+        s1 += l;
+        s2 += l * l;
+      }
+      if (vec) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
+      } else {
+#pragma unroll
+        for (int co = 0; co < G; ++co) dst[co] = o[co];
+      }
+    }
+  }
+}
+
+// any (gin, gout): one pixel per pass, outputs in chunks of 8 (cardinality 1, wide groups)
+__device__ __noinline__ void gconv_compute_generic(const GcGeom q, const float* in_s, const float* w_s,
+                                                   const float* b_s, int SW, int GS, int th, int tw, int y0,
+                                                   int x0, float* out_s, float* s12) {
+  float s1 = 0.f, s2 = 0.f;
+  const int TP = th * tw;
+  const int d = q.dil, ks = q.ks, gin = q.gin, gout = q.gout;
+  const int cbase = q.cbase;
+  for (int p = threadIdx.x; p < TP; p += GC_NT) {
+    const int poff = ((p / tw) * SW + (p % tw)) * GS;
+    const int y = y0 + p / tw, x = x0 + p % tw;
+    float* dst = out_s + ((long long)y * q.w + x) * q.Cout + cbase;
+    for (int co0 = 0; co0 < gout; co0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+      for (int ky = 0; ky < ks; ++ky)
+        for (int kx = 0; kx < ks; ++kx) {
+          const float* src = in_s + poff + (ky * d * SW + kx * d) * GS;
+          const float* wt = w_s + (long long)(ky * ks + kx) * gin * gout;
+          for (int ci = 0; ci < gin; ++ci) {
+            const float xv = src[ci];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (co0 + c < gout) acc[c] = fmaf(xv, wt[ci * gout + co0 + c], acc[c]);
+          }
+        }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (co0 + c < gout) {
+          const float o = acc[c] + b_s[co0 + c];
+          dst[co0 + c] = o;
+          const float l = lrelu(o);
+          s1 += l;
+          s2 += l * l;
+        }
+    }
+  }
+  s12[0] = s1;
+  s12[1] = s2;
+}
+
+__global__ void __launch_bounds__(GC_NT) gconv_kernel(const GconvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[64];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, net = blockIdx.z;
+  // select this CTA's branch with scalar copies (static indices keep the params in the constant bank)
+  int br_dil = a.br[0].dil, br_groups = a.br[0].groups, br_gin = a.br[0].gin, br_gout = a.br[0].gout;
+  int br_out_off = a.br[0].out_off, br_first = 0;
+  long long br_w_off = a.br[0].w_off, br_b_off = a.br[0].b_off;
+#pragma unroll
+  for (int i = 1; i < CNF_MAX_BRANCHES; ++i) {
+    if (i < a.n_br && (int)blockIdx.x >= a.br[i].first_item) {
+      br_dil = a.br[i].dil; br_groups = a.br[i].groups; br_gin = a.br[i].gin; br_gout = a.br[i].gout;
+      br_out_off = a.br[i].out_off; br_first = a.br[i].first_item;
+      br_w_off = a.br[i].w_off; br_b_off = a.br[i].b_off;
+    }
+  }
+  (void)br_groups;
+  const int local = blockIdx.x - br_first;
+  const int tiles = a.tiles_y * a.tiles_x;
+  const int g = local / tiles, tile = local % tiles;
+  const int y0 = (tile / a.tiles_x) * a.TH, x0 = (tile % a.tiles_x) * a.TW;
+  const int th = min(a.TH, a.h - y0), tw = min(a.TW, a.w - x0);
+  const int halo = br_dil * (a.ks - 1) / 2;
+  const int SH = th + 2 * halo, SW = tw + 2 * halo;
+  const int gin = br_gin, gout = br_gout;
+  const int GS = gc_stride(gin);
+  float* in_s = smem;                                   // [SH*SW][GS]
+  float* w_s = in_s + (((long long)SH * SW * GS + 3) & ~3);  // [ks*ks][gin][gout]
+  float* b_s = w_s + ((a.ks * a.ks * gin * gout + 3) & ~3);
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  float mean = 0.f, rstd = 1.f;
+  if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.Cin, mean, rstd);
+
+  // stage weights + bias of this group
+  {
+    const float* wsrc = P + br_w_off + (long long)g * a.ks * a.ks * gin * gout;
+    for (int i = tid; i < a.ks * a.ks * gin * gout; i += GC_NT) w_s[i] = wsrc[i];
+    const float* bsrc = P + br_b_off + g * gout;
+    for (int i = tid; i < gout; i += GC_NT) b_s[i] = bsrc[i];
+  }
+  // stage the LN(LReLU(.)) input tile with its halo; zero padding is applied AFTER the LayerNorm
+  {
+    const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.Cin;
+    const float* gam = P + a.g_off;
+    const float* bet = P + a.be_off;
+    const int cin0 = g * gin;  // F:402: group j reads channels [j*_d, (j+1)*_d) (cardinality 1: all)
+    const int n_stage = SH * SW * gin;
+    for (int idx = tid; idx < n_stage; idx += GC_NT) {
+      const int ci = idx % gin, pix = idx / gin;
+      const int gy = y0 - halo + pix / SW, gx = x0 - halo + pix % SW;
+      float v = 0.f;
+      if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) {
+        const long long e = ((long long)gy * a.w + gx) * a.Cin + cin0 + ci;
+        v = lrelu(src_s[e]);
+        if (a.ln) v = (v - mean) * rstd * gam[e] + bet[e];
+      }
+      in_s[pix * GS + ci] = v;
+    }
+  }
+  __syncthreads();
+
+  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.h * a.w * a.Cout;
+  float s1 = 0.f, s2 = 0.f;
+  GcGeom q;
+  q.dil = br_dil; q.ks = a.ks; q.gin = gin; q.gout = gout; q.cbase = br_out_off + g * gout; q.w = a.w; q.Cout = a.Cout;
+  const int G = (gin == gout) ? gin : 0;
+  switch (G) {
+    case 1: gconv_compute<1>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    case 2: gconv_compute<2>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    case 4: gconv_compute<4>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    case 8: gconv_compute<8>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    default: {
+      float s12[2];
+      gconv_compute_generic(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s12);
+      s1 = s12[0];
+      s2 = s12[1];
+      break;
+    }
+  }
+  if (a.stats_out) {
+    double d1, d2;
+    block_sum2(s1, s2, red, d1, d2);
+    if (tid == 0) {
+      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+      atomicAdd(so, d1);
+      atomicAdd(so + 1, d2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. Head conv (both nets) fused with tanh*w, exp, the affine coupling law, the decompress
+//    scatter into the flow buffer and the per-sample log-det (M:1133-1150, M:1198, M:1307-1326,
+//    M:1379-1394).  One thread per output pixel, all c2 channels of both nets.
+// ------------------------------------------------------------------------------------------
+struct HeadArgs {
+  const float* in;  // X [2][B][hw][nk]
+  long long in_net_stride;
+  const float* params;
+  long long net_stride, g_off, be_off, w_off, b_off, tanh_off;
+  const double* stats_in;
+  int B, h, w, nk, c2, ln, ks, mode;
+  FlowView view;   // where u2/v2 live (complement mask of the layer)
+  int mask_c;
+  double* logdet;  // [B], accumulated (forward only)
+  float *outA, *outB;  // HEAD_EMIT: [B][hw][c2]
+  int TH, CC;
+};
+
+constexpr int HD_NT = 256;
+
+template <int C2T>
+__global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[64];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * a.TH;
+  const int th = min(a.TH, a.h - y0);
+  const int pad = (a.ks - 1) / 2;
+  const int SH = th + 2 * pad, SW = a.w + 2 * pad;
+  const int CC = a.CC, CS = CC + 4;
+  const int in_sz = (SH * SW * CS + 3) & ~3;
+  const int w_sz = a.ks * a.ks * C2T * CC;
+  float* in_s = smem;               // [2][SH*SW][CS]
+  float* w_s = smem + 2 * in_sz;    // [2][ks*ks][C2T][CC]
+
+  const bool valid = tid < th * a.w;
+  const int py = valid ? tid / a.w : 0, px = valid ? tid % a.w : 0;
+
+  float mean[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
+  if (a.ln) {
+#pragma unroll
+    for (int net = 0; net < 2; ++net)
+      ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.nk, mean[net], rstd[net]);
+  }
+  float acc[2][C2T];
+#pragma unroll
+  for (int net = 0; net < 2; ++net)
+#pragma unroll
+    for (int co = 0; co < C2T; ++co) acc[net][co] = 0.f;
+
+  for (int c0 = 0; c0 < a.nk; c0 += CC) {
+    __syncthreads();
+    for (int net = 0; net < 2; ++net) {
+      const float* P = a.params + (long long)net * a.net_stride;
+      const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.nk;
+      const float* gam = P + a.g_off;
+      const float* bet = P + a.be_off;
+      float* dst = in_s + net * in_sz;
+      for (int idx = tid; idx < SH * SW * CC; idx += HD_NT) {
+        const int ci = idx % CC, pix = idx / CC;
+        const int gy = y0 - pad + pix / SW, gx = pix % SW - pad;
+        float v = 0.f;
+        if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w && c0 + ci < a.nk) {
+          const long long e = ((long long)gy * a.w + gx) * a.nk + c0 + ci;
+          v = lrelu(src_s[e]);
+          if (a.ln) v = (v - mean[net]) * rstd[net] * gam[e] + bet[e];
+        }
+        dst[pix * CS + ci] = v;
+      }
+      // weights: w_s[net][tap][co][ci] = W[tap][c0+ci][co]   (HWIO: ((tap*nk)+cin)*c2 + co)
+      const float* Wg = P + a.w_off;
+      float* wd = w_s + net * w_sz;
+      for (int idx = tid; idx < w_sz; idx += HD_NT) {
+        const int ci = idx % CC, co = (idx / CC) % C2T, tap = idx / (CC * C2T);
+        float v = 0.f;
+        if (co < a.c2 && c0 + ci < a.nk) v = Wg[((long long)tap * a.nk + c0 + ci) * a.c2 + co];
+        wd[idx] = v;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+        const float* src = in_s + net * in_sz;
+        const float* wn = w_s + net * w_sz;
+        for (int ky = 0; ky < a.ks; ++ky)
+          for (int kx = 0; kx < a.ks; ++kx) {
+            const float* s = src + ((py + ky) * SW + px + kx) * CS;
+            const float* wt = wn + (ky * a.ks + kx) * C2T * CC;
+            for (int c4 = 0; c4 < CC; c4 += 4) {
+              const float4 xv = ld4(s + c4);
+#pragma unroll
+              for (int co = 0; co < C2T; ++co) {
+                const float4 wv = ld4(wt + co * CC + c4);
+                acc[net][co] = fmaf(xv.x, wv.x, acc[net][co]);
+                acc[net][co] = fmaf(xv.y, wv.y, acc[net][co]);
+                acc[net][co] = fmaf(xv.z, wv.z, acc[net][co]);
+                acc[net][co] = fmaf(xv.w, wv.w, acc[net][co]);
+              }
+            }
+          }
+      }
+    }
+  }
+
+  float ld = 0.f;
+  if (valid) {
+    const float* PA = a.params;
+    const float* PB = a.params + a.net_stride;
+    const float tw_ = PA[a.tanh_off];
+    const int y = y0 + py, x = px;
+#pragma unroll
+    for (int co = 0; co < C2T; ++co) {
+      if (co < a.c2) {
+        const float A = tw_ * tanhf(acc[0][co] + PA[a.b_off + co]);  // M:1198, M:114-116
+        const float t = acc[1][co] + PB[a.b_off + co];
+        if (a.mode == HEAD_EMIT) {
+          const long long e = ((long long)b * a.h * a.w + (long long)y * a.w + x) * a.c2 + co;
+          a.outA[e] = A;
+          a.outB[e] = t;
+        } else {
+          float* ptr = a.view.base + comp_off(a.view, a.mask_c, b, y, x, co);
+          const float u2 = *ptr;
+          if (a.mode == HEAD_FWD) {
+            *ptr = __fadd_rn(__fmul_rn(expf(A), u2), t);                  // M:1307, M:1230-1231
+            ld += A;                                                      // M:1323
+          } else {
+            *ptr = __fmul_rn(__frcp_rn(expf(A)), __fsub_rn(u2, t));       // M:1379, M:1250-1251
+          }
+        }
+      }
+    }
+  }
+  if (a.mode == HEAD_FWD && a.logdet) {
+    double d1, d2;
+    block_sum2(ld, 0.f, red, d1, d2);
+    if (tid == 0) atomicAdd(a.logdet + b, d1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+#define CU_TRY(x)                      \
+  do {                                 \
+    cudaError_t e_ = (x);              \
+    if (e_ != cudaSuccess) return (int)e_; \
+  } while (0)
+
+template <int TN, int NQ, int RM, bool STEM>
+static int launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
+  constexpr int CT = TN / (4 * NQ), RT = 128 / CT, TM = RM * RT;
+  const size_t smem = ((size_t)TM * (a.KC + 4) + (size_t)a.KC * TN) * sizeof(float);
+  auto kern = gemm_kernel<TN, NQ, RM, STEM>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  const int tiles_m = (a.hw + TM - 1) / TM, tiles_n = (a.N + TN - 1) / TN;
+  dim3 grid(tiles_m * tiles_n, a.B, 2);
+  kern<<<grid, 128, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <bool STEM>
+static int launch_gemm(GemmArgs a, cudaStream_t st) {
+  const int Kp = (a.K + 3) & ~3;
+  a.KC = std::min(Kp, 128);
+  if (a.N > 32) return launch_gemm_t<64, 2, 8, STEM>(a, st);
+  if (a.N > 16) return launch_gemm_t<32, 1, 8, STEM>(a, st);
+  return launch_gemm_t<16, 1, 4, STEM>(a, st);
+}
+
+static int launch_gconv(GconvArgs a, cudaStream_t st) {
+  // whole plane when it fits 4 pixels/thread, else 32x32 tiles
+  a.TH = std::min(a.h, 32);
+  a.TW = std::min(a.w, 32);
+  a.tiles_y = (a.h + a.TH - 1) / a.TH;
+  a.tiles_x = (a.w + a.TW - 1) / a.TW;
+  const int tiles = a.tiles_y * a.tiles_x;
+  int items = 0;
+  size_t smem = 0;
+  for (int i = 0; i < a.n_br; ++i) {
+    a.br[i].first_item = items;
+    items += a.br[i].groups * tiles;
+    const int halo = a.br[i].dil * (a.ks - 1) / 2;
+    const size_t in_sz = (((size_t)(a.TH + 2 * halo) * (a.TW + 2 * halo) * gc_stride(a.br[i].gin)) + 3) & ~(size_t)3;
+    const size_t w_sz = ((size_t)a.ks * a.ks * a.br[i].gin * a.br[i].gout + 3) & ~(size_t)3;
+    smem = std::max(smem, (in_sz + w_sz + a.br[i].gout + 4) * sizeof(float));
+  }
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidConfiguration;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(gconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  dim3 grid(items, a.B, 2);
+  gconv_kernel<<<grid, GC_NT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int C2T>
+static int launch_head_t(const HeadArgs& a, cudaStream_t st) {
+  const int pad = (a.ks - 1) / 2;
+  const size_t in_sz = (((size_t)(a.TH + 2 * pad) * (a.w + 2 * pad) * (a.CC + 4)) + 3) & ~(size_t)3;
+  const size_t smem = (2 * in_sz + 2 * (size_t)a.ks * a.ks * C2T * a.CC) * sizeof(float);
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidConfiguration;
+  auto kern = head_kernel<C2T>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  dim3 grid((a.h + a.TH - 1) / a.TH, a.B);
+  kern<<<grid, HD_NT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+static int launch_head(HeadArgs a, cudaStream_t st) {
+  if (a.w > HD_NT) return (int)cudaErrorInvalidConfiguration;
+  const int n_tiles = (a.h * a.w + HD_NT - 1) / HD_NT;
+  a.TH = (a.h + n_tiles - 1) / n_tiles;
+  while (a.TH * a.w > HD_NT) --a.TH;
+  a.CC = std::min(16, (a.nk + 3) & ~3);
+  if (a.c2 <= 1) return launch_head_t<1>(a, st);
+  if (a.c2 <= 2) return launch_head_t<2>(a, st);
+  if (a.c2 <= 4) return launch_head_t<4>(a, st);
+  if (a.c2 <= 8) return launch_head_t<8>(a, st);
+  if (a.c2 <= 16) return launch_head_t<16>(a, st);
+  if (a.c2 <= 32) return launch_head_t<32>(a, st);
+  return (int)cudaErrorInvalidConfiguration;
+}
+
+// One coupling layer on `B` samples.  in_view/in_mask: where u1 is gathered from; out_view: where
+// u2 is read and v2 written (the same buffer for the in-place flow).  mode: HeadMode.
+int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
+                 int B, int mode, double* logdet_acc, float* outA, float* outB, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 0) return 0;
+  CouplingWorkspace W = carve_ws(c, B, ws);
+  const int hw = c->hw(), nk = c->nk, cat = c->cat;
+  const int n_ln = c->n_ln();
+  const long long slot = 2LL * B * 2;  // doubles per stats slot
+  if (n_ln) CU_TRY(cudaMemsetAsync(W.stats, 0, sizeof(double) * slot * n_ln, st));
+  auto stats = [&](int i) -> double* { return n_ln ? W.stats + slot * i : nullptr; };
+
+  {  // stem
+    GemmArgs a = {};
+    a.view = in_view; a.mask = in_mask; a.h = c->h; a.w = c->w; a.c1 = c->c1; a.ks = c->ks;
+    a.params = params; a.net_stride = c->net_stride; a.w_off = c->stem_w; a.b_off = c->stem_b;
+    a.stats_out = stats(0);
+    a.out = W.X; a.out_net_stride = (long long)B * hw * nk;
+    a.B = B; a.hw = hw; a.K = c->ks * c->ks * c->c1; a.N = nk; a.ln = 0;
+    CU_TRY((cudaError_t)launch_gemm<true>(a, st));
+  }
+  for (int r = 0; r < c->R; ++r) {
+    const ResBlockLayout& L = c->rb[r];
+    {  // pw1: X -> Y1
+      GemmArgs a = {};
+      a.in = W.X; a.in_net_stride = (long long)B * hw * nk;
+      a.params = params; a.net_stride = c->net_stride; a.w_off = L.pw1_w; a.b_off = L.pw1_b;
+      a.g_off = L.ln1_g; a.be_off = L.ln1_b;
+      a.stats_in = stats(3 * r); a.stats_out = stats(3 * r + 1);
+      a.out = W.Y1; a.out_net_stride = (long long)B * hw * nk;
+      a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln;
+      CU_TRY((cudaError_t)launch_gemm<false>(a, st));
+    }
+    {  // grouped dilated convs: Y1 -> Y2
+      GconvArgs a = {};
+      a.in = W.Y1; a.in_net_stride = (long long)B * hw * nk; a.Cin = nk;
+      a.out = W.Y2; a.out_net_stride = (long long)B * hw * cat; a.Cout = cat;
+      a.params = params; a.net_stride = c->net_stride; a.g_off = L.ln2_g; a.be_off = L.ln2_b;
+      a.stats_in = stats(3 * r + 1); a.stats_out = stats(3 * r + 2);
+      a.B = B; a.h = c->h; a.w = c->w; a.ln = c->ln; a.ks = c->ks;
+      a.n_br = (int)L.br.size();
+      for (int i = 0; i < a.n_br; ++i) {
+        const Branch& s = L.br[i];
+        a.br[i].dil = s.dil; a.br[i].groups = s.groups; a.br[i].gin = s.gin; a.br[i].gout = s.gout;
+        a.br[i].out_off = s.out_off; a.br[i].w_off = s.w_off; a.br[i].b_off = s.b_off;
+      }
+      CU_TRY((cudaError_t)launch_gconv(a, st));
+    }
+    {  // pw2 + residual: Y2 (+X) -> X
+      GemmArgs a = {};
+      a.in = W.Y2; a.in_net_stride = (long long)B * hw * cat;
+      a.params = params; a.net_stride = c->net_stride; a.w_off = L.pw2_w; a.b_off = L.pw2_b;
+      a.g_off = L.ln3_g; a.be_off = L.ln3_b;
+      a.stats_in = stats(3 * r + 2); a.stats_out = stats(3 * r + 3);
+      a.out = W.X; a.res = W.X; a.out_net_stride = (long long)B * hw * nk;
+      a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln;
+      CU_TRY((cudaError_t)launch_gemm<false>(a, st));
+    }
+  }
+  {  // head + coupling
+    HeadArgs a = {};
+    a.in = W.X; a.in_net_stride = (long long)B * hw * nk;
+    a.params = params; a.net_stride = c->net_stride; a.g_off = c->lnf_g; a.be_off = c->lnf_b;
+    a.w_off = c->head_w; a.b_off = c->head_b; a.tanh_off = c->tanh_w;
+    a.stats_in = stats(3 * c->R);
+    a.B = B; a.h = c->h; a.w = c->w; a.nk = nk; a.c2 = c->c2; a.ln = c->ln; a.ks = c->ks; a.mode = mode;
+    a.view = out_view; a.mask_c = c->mask_c;
+    a.logdet = logdet_acc; a.outA = outA; a.outB = outB;
+    CU_TRY((cudaError_t)launch_head(a, st));
+  }
+  return 0;
+}
+
+}  // namespace cnf

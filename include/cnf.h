@@ -1,0 +1,178 @@
+/* libcnf — C-ABI of the B200-native conditional RealNVP hot path.
+ *
+ * The reference (USArmyResearchLab/ARL_Conditional_Normalizing_Flows) has no FFI: its boundary is
+ * the Python class surface in conv_cINN_make_model.py (M), conv_cINN_base_functions.py (F) and
+ * TOYcINN_make_model.py (T).  Each entry point below names the reference interface it replaces.
+ * Python host code (arl_conditional_normalizing_flows_b200/) binds these with ctypes and passes
+ * tensors zero-copy as DLPack `DLManagedTensor*`.
+ *
+ * Conventions
+ *   - every function returns an int status (CNF_OK or a CNF_ERR_* class) and never throws;
+ *     `cnf_last_error()` returns the thread-local message of the last failure;
+ *   - tensors are fp32, on the CUDA device that is current for the calling thread, compact
+ *     row-major NHWC, 16-byte aligned; libcnf borrows them for the call and never frees them;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no
+ *     function synchronises, allocates device memory, or keeps global mutable state;
+ *   - the caller allocates every output and the workspace (`cnf_*_workspace_bytes`).
+ */
+#ifndef CNF_H_
+#define CNF_H_
+
+#include <stdint.h>
+#include "cnf_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNF_VERSION 100
+
+#define CNF_OK 0
+#define CNF_ERR_ARG 1          /* a reference `assert` would have fired      -> AssertionError     */
+#define CNF_ERR_SHAPE 2        /* tf.ensure_shape mismatch (M:621,1276,1348) -> ValueError         */
+#define CNF_ERR_DTYPE 3        /* not float32                                -> TypeError          */
+#define CNF_ERR_DEVICE 4       /* not on the current CUDA device             -> RuntimeError       */
+#define CNF_ERR_LAYOUT 5       /* not compact / not 16-byte aligned          -> ValueError         */
+#define CNF_ERR_CUDA 6         /* CUDA runtime error                         -> RuntimeError       */
+#define CNF_ERR_UNSUPPORTED 7  /* valid in the reference, not built here     -> NotImplementedError*/
+#define CNF_ERR_WORKSPACE 8    /* workspace too small                        -> ValueError         */
+
+#define CNF_MAX_BRANCHES 8
+#define CNF_MAX_BLOCKS 32
+#define CNF_NAME_CAP 64
+
+typedef struct cnf_coupling cnf_coupling; /* one coupling layer: masks + s/t nets (M:331-1394)  */
+typedef struct cnf_plan cnf_plan;         /* the whole flow: cFlow.__init__ planner (M:1431-1695) */
+
+int cnf_version(void);
+const char* cnf_last_error(void);
+
+/* ---- coupling layer descriptor ------------------------------------------------------------
+ * replaces coupling_layer.__init__ (M:355-439), get_masked_compressed_shape (M:474-498) and the
+ * shape logic of coupling_function (M:1087-1104).  Host ints only. */
+typedef struct {
+  int H, W, D;                 /* uncompressed input shape (in_shape)                             */
+  int mask, mask_complement;   /* which_mask, which_mask_complement (M:426-433)                   */
+  int R, cardinality, nk, ksize, layer_norm;   /* nk already halved for masks 0/1 (M:420-423)     */
+  int h, w, c1, c2;            /* compressed u1 shape and the depth of u2 / of A,b (M:1093-1104)  */
+  int cat;                     /* concat width after the dilated grouped convs (F:590)            */
+  int n_branches;
+  int dilation[CNF_MAX_BRANCHES];
+  int branch_channels[CNF_MAX_BRANCHES]; /* nk // d (F:579)                                       */
+  int groups[CNF_MAX_BRANCHES];          /* cardinality (1 => plain conv over all nk, F:389-395)  */
+  int group_in[CNF_MAX_BRANCHES];        /* input channels per group                              */
+  int group_out[CNF_MAX_BRANCHES];       /* output channels per group                             */
+  int n_ln;                    /* LayerNorms per net (3R+1, or 0)                                 */
+  int64_t net_stride;          /* floats from net A's parameters to net b's                       */
+  int64_t param_count;         /* floats for both nets (= 2*net_stride)                           */
+  int n_entries;               /* named parameter tensors per net                                 */
+} cnf_coupling_info;
+
+int cnf_coupling_create(const int in_shape[3], int which_mask, int num_res_blocks, int cardinality,
+                        int num_kernels, int kernel_size, int layer_norm, const int* which_dilations,
+                        int n_dilations, cnf_coupling** out);
+void cnf_coupling_destroy(cnf_coupling* c);
+int cnf_coupling_get_info(const cnf_coupling* c, cnf_coupling_info* info);
+/* idx-th named parameter of one net, Keras-shaped (HWIO kernels, flat LN vectors); `offset` is in
+ * floats from the start of that net's block.  role: 0 kernel, 1 bias, 2 gamma, 3 beta, 4 tanh scale */
+int cnf_coupling_param_entry(const cnf_coupling* c, int idx, char name[CNF_NAME_CAP], int64_t* offset,
+                             int* ndim, int64_t shape[4], int* role);
+int64_t cnf_coupling_workspace_bytes(const cnf_coupling* c, int64_t batch);
+
+/* ---- flow planner: replaces cFlow.__init__ (M:1431-1695) ---------------------------------- */
+typedef struct {
+  int n_blocks, n_coupling, n_layers; /* n_layers counts couplings + squeeze + factor layers     */
+  int H, W, D, x_d, ksize, layer_norm;
+  double lambda_y;
+  int64_t param_count;                /* floats, all coupling layers                              */
+} cnf_plan_info;
+
+typedef struct {
+  int scale, num_prev_factors;        /* scale_list[i], num_prev_factors_list[i] (M:1493-1518)    */
+  int H, W, D;                        /* io_shape_list[i] (M:1521-1536)                           */
+  int n_checkerboard, checkerboard[CNF_MAX_BRANCHES]; /* dilations_list[i] (M:1553-1617)          */
+  int n_channelwise, channelwise[CNF_MAX_BRANCHES];
+} cnf_block_info;
+
+int cnf_plan_create(const int io_shape[3], int x_d, int n_blocks, const int* squeeze_factor_block_list,
+                    const int* ResNeXt_block_list, const int* num_kernels_list,
+                    const int* cardinality_list, double lambda_y, int ksize, int layer_norm,
+                    int dilations, cnf_plan** out);
+void cnf_plan_destroy(cnf_plan* p);
+int cnf_plan_get_info(const cnf_plan* p, cnf_plan_info* info);
+int cnf_plan_block_info(const cnf_plan* p, int block, cnf_block_info* info);
+/* layers_list order (M:1636-1689): kind 0 coupling, 1 squeeze, 2 factor; aux = coupling index or
+ * num_prev_factors */
+int cnf_plan_layer(const cnf_plan* p, int idx, int* kind, int* aux);
+const cnf_coupling* cnf_plan_coupling(const cnf_plan* p, int coupling_idx);
+int64_t cnf_plan_coupling_param_offset(const cnf_plan* p, int coupling_idx);
+int cnf_plan_coupling_level(const cnf_plan* p, int coupling_idx); /* squeezes applied before it */
+int64_t cnf_plan_workspace_bytes(const cnf_plan* p, int64_t batch);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* cFlow.call(xy, direction=+1) (M:1743-1772): zy in the ORIGINAL (H,W,D) layout plus the PER-SAMPLE
+ * log-det vector [B] (superset of the reference's batch-mean scalar, Q1: scalar = mean of it). */
+int cnf_flow_forward(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                     DLManagedTensor* zy, DLManagedTensor* logdet, DLManagedTensor* workspace,
+                     void* stream);
+/* cFlow.call(zy, direction=-1) (M:1774-1798) */
+int cnf_flow_inverse(const cnf_plan* p, const DLManagedTensor* zy, const DLManagedTensor* params,
+                     DLManagedTensor* xy, DLManagedTensor* workspace, void* stream);
+/* cFlow.log_loss (M:1800-1848): forward + prior/L1 reductions.  ll_z, ll_y, logdet are [B];
+ * loss4 is [4] = (loss, z_loss, y_loss, detJ_loss) exactly as the reference returns them. */
+int cnf_flow_log_loss(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                      DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                      DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace,
+                      void* stream);
+/* prior / L1 part alone (M:1826-1848) given zy, xy [B,H,W,D] and a per-sample logdet [B]. */
+int cnf_prior_loss(const DLManagedTensor* zy, const DLManagedTensor* xy, const DLManagedTensor* logdet,
+                   int x_d, double lambda_y, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                   DLManagedTensor* loss4, void* stream);
+
+/* coupling_layer.forward_and_Jacobian (M:1258-1328) / .backward (M:1333-1394) on one [B,H,W,D]
+ * tensor; `out` must not alias `in`.  logdet [B] is ACCUMULATED into (caller zeroes it). */
+int cnf_coupling_forward(const cnf_coupling* c, const DLManagedTensor* u, const DLManagedTensor* params,
+                         DLManagedTensor* v, DLManagedTensor* logdet, DLManagedTensor* workspace,
+                         void* stream);
+int cnf_coupling_backward(const cnf_coupling* c, const DLManagedTensor* v, const DLManagedTensor* params,
+                          DLManagedTensor* u, DLManagedTensor* workspace, void* stream);
+/* A_wrapper / b_wrapper (M:452-472): both nets on an already-compressed u1 [B,h,w,c1];
+ * A = w*tanh(.) and b are [B,h,w,c2]. */
+int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1_compressed,
+                      const DLManagedTensor* params, DLManagedTensor* A, DLManagedTensor* b,
+                      DLManagedTensor* workspace, void* stream);
+
+/* fused standalone coupling law + mask addressing + per-sample log-det (M:1215-1253, M:1307-1326):
+ * v = mask(u,m,False) + decompress(exp(s)*u2c + t, m_bar)   (inverse: (u2c - t) / exp(s)).
+ * u, v are [B,H,W,D]; s, t are [B,h,w,c2] in the compressed layout of the complement mask;
+ * logdet [B] is overwritten with sum(s) per sample (may be NULL). */
+int cnf_coupling_law(const DLManagedTensor* u, const DLManagedTensor* s, const DLManagedTensor* t,
+                     int which_mask, int inverse, DLManagedTensor* v, DLManagedTensor* logdet,
+                     void* stream);
+
+/* pure index permutations, bit-exact: coupling_layer.mask (M:500-761), decompress_mask (M:763-1073),
+ * squeeze_layer (M:155-217: tf.nn.space_to_depth / depth_to_space, block 2). */
+int cnf_mask(const DLManagedTensor* uv, int which_mask, int compress, DLManagedTensor* out, void* stream);
+int cnf_decompress_mask(const DLManagedTensor* uv_compressed, int which_mask, DLManagedTensor* out,
+                        void* stream);
+int cnf_space_to_depth(const DLManagedTensor* in, DLManagedTensor* out, void* stream);
+int cnf_depth_to_space(const DLManagedTensor* in, DLManagedTensor* out, void* stream);
+
+/* ---- toy dense cINN: cINN_affine.call / log_loss (T:248-451), coupling_layer MLPs (T:29-97) --
+ * u, v are [B,3]; params is the flat buffer laid out by cnf_toy_param_count(); mask_indices[n]
+ * (host ints) is the layer order; direction follows the TOY convention (-1: xy->zy with log-det,
+ * +1: zy->xy).  logdet [B] is overwritten (zeros for +1). */
+int64_t cnf_toy_param_count(int num_coupling_layers, int intermediate_dims, int num_layers);
+int64_t cnf_toy_layer_offset(int layer, int intermediate_dims, int num_layers);
+int cnf_toy_call(const DLManagedTensor* u, const DLManagedTensor* params, const int* mask_indices,
+                 int num_coupling_layers, int intermediate_dims, int num_layers, int direction,
+                 DLManagedTensor* v, DLManagedTensor* logdet, void* stream);
+int cnf_toy_log_loss(const DLManagedTensor* xy, const DLManagedTensor* params, const int* mask_indices,
+                     int num_coupling_layers, int intermediate_dims, int num_layers, int x_d,
+                     double lambda_y, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                     DLManagedTensor* logdet, DLManagedTensor* loss4, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNF_H_ */

@@ -1,0 +1,363 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  * squeeze / masking / permutation indexing and the pass-through half of a coupling layer: BIT-EXACT;
+  * s/t nets, per-sample log-det, log-likelihood terms, samples from a fixed latent: 1e-4 relative
+    (fp32 kernels vs the fp64 oracle; `rel` below is max|a-b| / max|b|, per-sample quantities are also
+    checked element-wise with rtol 1e-4 and a small absolute floor).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import masks_np
+from oracle.flow_torch import FlowOracle
+from oracle.planner import plan_coupling
+from oracle.weights import init_weights, synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def mk(cfg, kind='rand', seed=1, dev="cuda:0", dtype=torch.float64):
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import cFlow
+    m = cFlow(**cfg, device=dev)
+    o = FlowOracle(**cfg, dtype=dtype)
+    W = init_weights(o.plan, kind, seed=seed)
+    o.set_weights(W)
+    m.set_weights(W)
+    return m, o
+
+
+TINY = dict(io_shape=[4, 4, 2], x_d=1, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
+            num_kernels_list=[8], cardinality_list=[2])
+SMALL = dict(io_shape=[8, 8, 3], x_d=2, squeeze_factor_block_list=[1, 0], ResNeXt_block_list=[2, 1],
+             num_kernels_list=[16, 8], cardinality_list=[2, 2])
+MID = dict(io_shape=[16, 16, 4], x_d=3, squeeze_factor_block_list=[0, 1, 1], ResNeXt_block_list=[1, 2, 1],
+           num_kernels_list=[32, 32, 16], cardinality_list=[4, 2, 2])
+CFG2 = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+            num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
+CFG3 = dict(io_shape=[32, 32, 4], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+            num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
+
+
+# ---------------------------------------------------------------------------------------------------
+# index permutations: bit-exact
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 6])
+@pytest.mark.parametrize("m", [0, 1, 2, 3])
+def test_mask_and_decompress_bit_exact(dev, m, D):
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import coupling_layer
+    if D == 1 and m == 3:
+        pytest.skip("mask 3 of one channel is empty")
+    L = coupling_layer([6, 8, D], 0, 1, 2, 8, 3, None, LAYER_NORM=True, which_dilations=[1], device=dev)
+    rng = np.random.default_rng(7)
+    u = rng.standard_normal((3, 6, 8, D)).astype(np.float32)
+    ut = torch.from_numpy(u).to(dev)
+    for compress in (False, True):
+        got = L.mask(ut, m, compress).cpu().numpy()
+        want = masks_np.mask(u, m, compress)
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
+    uc = masks_np.mask(u, m, True)
+    got = L.decompress_mask(torch.from_numpy(np.ascontiguousarray(uc)).to(dev), m, u.shape).cpu().numpy()
+    np.testing.assert_array_equal(got, masks_np.decompress_mask(uc, m, u.shape))
+
+
+def test_squeeze_and_factor_layers_bit_exact(dev):
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import squeeze_layer, factor_out_zy_layer
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal((2, 8, 12, 3)).astype(np.float32)
+    zy = rng.standard_normal((2, 8, 12, 5)).astype(np.float32)
+    sq, fa = squeeze_layer(), factor_out_zy_layer(1)
+    v, s, z2 = sq.forward_and_Jacobian(torch.from_numpy(u).to(dev), 0.5, torch.from_numpy(zy).to(dev))
+    wv, wz = masks_np.squeeze_forward(u, zy)
+    np.testing.assert_array_equal(v.cpu().numpy(), wv)
+    np.testing.assert_array_equal(z2.cpu().numpy(), wz)
+    assert s == 0.5
+    ub, zb = sq.backward(v, z2)
+    np.testing.assert_array_equal(ub.cpu().numpy(), u)
+    np.testing.assert_array_equal(zb.cpu().numpy(), zy)
+    v3, _, z3 = fa.forward_and_Jacobian(v, 0, z2)
+    wv3, wz3 = masks_np.factor_forward(wv, wz)
+    np.testing.assert_array_equal(v3.cpu().numpy(), wv3)
+    np.testing.assert_array_equal(z3.cpu().numpy(), wz3)
+    u4, z4 = fa.backward(v3, z3)
+    wu4, wz4 = masks_np.factor_backward(wv3, wz3, 1)
+    np.testing.assert_array_equal(u4.cpu().numpy(), wu4)
+    np.testing.assert_array_equal(z4.cpu().numpy(), wz4)
+    with pytest.raises(AssertionError):
+        sq.forward_and_Jacobian(torch.zeros(1, 3, 4, 2, device=dev), 0, None)
+    with pytest.raises(AssertionError):
+        sq.backward(torch.zeros(1, 2, 2, 6, device=dev), None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# one coupling layer: s/t nets, forward, inverse
+# ---------------------------------------------------------------------------------------------------
+LAYER_CASES = [
+    # in_shape, mask, R, card, num_kernels, dilations, LN
+    ([8, 8, 3], 0, 2, 2, 16, [1, 2], True),
+    ([8, 8, 3], 1, 1, 2, 16, [1], True),
+    ([8, 8, 3], 2, 2, 2, 16, [1, 2], True),       # odd depth: c1=2, c2=1
+    ([8, 8, 3], 3, 1, 2, 16, [1, 2], True),       # odd depth: c1=1, c2=2
+    ([12, 8, 4], 2, 1, 4, 32, [1, 2], False),     # no LayerNorm
+    ([28, 28, 2], 2, 3, 8, 64, [1, 2, 4], True),  # config-2 channel layer
+    ([28, 28, 2], 0, 3, 8, 64, [1, 2, 4], True),  # config-2 checkerboard layer (nk 32, groups of 4/2/1)
+    ([14, 14, 4], 3, 3, 4, 32, [1, 2], True),
+    ([16, 16, 4], 2, 1, 1, 16, [1, 2], True),     # cardinality 1: plain conv over all channels (F:389-395)
+    ([64, 64, 6], 0, 1, 4, 64, [1, 2, 4, 8], True),   # tiled grouped conv, wide head (c2 = 12)
+]
+
+
+@pytest.mark.parametrize("case", LAYER_CASES, ids=[f"{c[0]}m{c[1]}" for c in LAYER_CASES])
+def test_coupling_layer_vs_oracle(dev, case):
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import coupling_layer
+    from oracle.flow_torch import st_net, _t
+    shape, m, R, card, nk, dil, ln = case
+    L = plan_coupling(shape, m, R, card, nk, 3, dil)
+    L['ln'] = ln
+    W = init_weights({'layers': [L]}, 'rand', seed=11, ln=ln)[0]
+    layer = coupling_layer(shape, m, R, card, nk, 3, None, LAYER_NORM=ln, which_dilations=dil, device=dev)
+    layer.set_weights(W)
+    B = 3
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal((B, *shape)).astype(np.float32)
+
+    # oracle in fp64
+    u1c = masks_np.mask(u.astype(np.float64), m, True)
+    PA = {k: _t(v, torch.float64) for k, v in W['A'].items()}
+    Pb = {k: _t(v, torch.float64) for k, v in W['b'].items()}
+    with torch.no_grad():
+        A = st_net(_t(u1c, torch.float64), PA, L, True).numpy()
+        b = st_net(_t(u1c, torch.float64), Pb, L, False).numpy()
+    mc = L['mask_complement']
+    u2c = masks_np.mask(u.astype(np.float64), mc, True)
+    v_want = masks_np.mask(u.astype(np.float64), m, False) + masks_np.decompress_mask(np.exp(A) * u2c + b, mc, u.shape)
+    ld_want = A.sum(axis=(1, 2, 3))
+
+    # A_wrapper / b_wrapper on the compressed input
+    ut = torch.from_numpy(u).to(dev)
+    u1c_t = layer.mask(ut, m, True)
+    A_got = layer.A_wrapper(u1c_t).cpu().numpy()
+    b_got = layer.b_wrapper(u1c_t).cpu().numpy()
+    assert rel(A_got, A) < RTOL, rel(A_got, A)
+    assert rel(b_got, b) < RTOL, rel(b_got, b)
+
+    # forward_and_Jacobian
+    v, s, zy = layer.forward_and_Jacobian(ut, 0.25, None)
+    v = v.cpu().numpy()
+    assert zy is None
+    keep = masks_np.mask(np.ones_like(u), m, False) == 1
+    assert np.array_equal(v[keep], u[keep]), "pass-through half must be bit-exact"
+    assert rel(v, v_want) < RTOL, rel(v, v_want)
+    ld = layer.last_logdet_per_sample.cpu().numpy()
+    np.testing.assert_allclose(ld, ld_want, rtol=RTOL, atol=RTOL * np.abs(ld_want).mean())
+    np.testing.assert_allclose(float(s), 0.25 + ld_want.mean(), rtol=RTOL, atol=1e-5)
+
+    # backward inverts forward, and matches the oracle's inverse law on fresh input
+    ub, _ = layer.backward(torch.from_numpy(v).to(dev), None)
+    assert rel(ub.cpu().numpy(), u) < RTOL
+    u_inv_want = masks_np.mask(u.astype(np.float64), m, False) + \
+        masks_np.decompress_mask((u2c - b) / np.exp(A), mc, u.shape)
+    u_inv, _ = layer.backward(ut, None)
+    assert rel(u_inv.cpu().numpy(), u_inv_want) < RTOL
+
+    with pytest.raises(ValueError):      # tf.ensure_shape (M:1276)
+        layer.forward_and_Jacobian(torch.zeros(2, shape[0], shape[1] + 2, shape[2], device=dev), 0, None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the flow
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,cfg,B,kind", [
+    ("tiny", TINY, 5, 'rand'), ("small", SMALL, 4, 'rand'), ("small-init", SMALL, 4, 'init'),
+    ("mid", MID, 3, 'rand'), ("cfg2", CFG2, 2, 'rand'), ("cfg2-init", CFG2, 2, 'init'), ("cfg3", CFG3, 2, 'rand'),
+])
+def test_flow_forward_inverse_loss_vs_oracle(dev, name, cfg, B, kind):
+    m, o = mk(cfg, kind, seed=2)
+    H, W, D = cfg['io_shape']
+    if name.startswith("cfg2"):
+        x = synth_inputs('cfg2', B, seed=3)
+    elif name == "cfg3":
+        x = synth_inputs('cfg3', B, seed=3)
+    else:
+        x = synth_inputs(f'noise:{H}x{W}x{D}', B, seed=3)
+    xt = torch.from_numpy(x).to(dev)
+    four_want, ps = o.log_loss(x.astype(np.float64))
+
+    zy, ld = m(xt, 1)
+    assert rel(zy.cpu().numpy(), ps['zy']) < RTOL
+    ld_ps = m.last_logdet_per_sample.cpu().numpy()
+    np.testing.assert_allclose(ld_ps, ps['logdet'], rtol=RTOL, atol=RTOL * np.abs(ps['logdet']).mean())
+    np.testing.assert_allclose(float(ld), ps['logdet'].mean(), rtol=RTOL, atol=RTOL * np.abs(ps['logdet']).mean())
+    assert torch.equal(xt, torch.from_numpy(x).to(dev)), "the public call must not mutate its input"
+
+    four = [float(t) for t in m.log_loss(xt)]
+    np.testing.assert_allclose(m.last_per_sample['ll_z'].cpu().numpy(), ps['ll_z'], rtol=RTOL)
+    np.testing.assert_allclose(m.last_per_sample['ll_y'].cpu().numpy(), ps['ll_y'], rtol=RTOL,
+                               atol=RTOL * np.abs(ps['ll_y']).mean())
+    np.testing.assert_allclose(four[0], four_want[0], rtol=RTOL)
+    np.testing.assert_allclose(four[1], four_want[1], rtol=RTOL)
+    np.testing.assert_allclose(four[2], four_want[2], rtol=RTOL)
+    np.testing.assert_allclose(four[3], four_want[3], rtol=RTOL, atol=RTOL * np.abs(ps['logdet']).mean())
+    bpd = m.bits_per_dim(four[1], four[3])
+    from oracle.flow_torch import bits_per_dim
+    np.testing.assert_allclose(bpd, bits_per_dim(four_want[1], four_want[3], H, W, cfg['x_d']), rtol=RTOL, atol=1e-6)
+
+    # sampling from a fixed latent
+    z = synth_inputs(f'noise:{H}x{W}x{D}', B, seed=9)
+    z[..., cfg['x_d']:] = x[..., cfg['x_d']:]
+    xs_want = o.call(z.astype(np.float64), -1)
+    xs = m(torch.from_numpy(z).to(dev), -1)
+    assert rel(xs.cpu().numpy(), xs_want) < RTOL
+    # default direction is -1 (M:1725)
+    assert torch.equal(m(torch.from_numpy(z).to(dev)), xs)
+
+    td = m.test_step(xt)
+    assert set(td) == {'loss', 'z_loss', 'y_loss', 'detJ_loss'}
+    np.testing.assert_allclose(td['loss'], four_want[0], rtol=RTOL)
+
+
+def test_flow_layerwise_equals_fused_call(dev):
+    """Driving layers_list by hand exactly like cFlow.call (M:1743-1770) gives the fused in-place result."""
+    m, _ = mk(MID, 'rand', seed=4)
+    x = torch.from_numpy(synth_inputs('noise:16x16x4', 3, seed=1)).to(dev)
+    uv, ld, zy = x, 0, None
+    for layer in m.layers_list:
+        uv, ld, zy = layer.forward_and_Jacobian(uv, ld, zy)
+    zy = torch.cat([zy, uv], 3)
+    vu = None
+    for layer in reversed(m.squeeze_factor_layers_list):
+        vu, zy = layer.backward(vu, zy)
+    fused, ld_f = m(x, 1)
+    assert torch.equal(vu, fused)
+    np.testing.assert_allclose(float(ld), float(ld_f), rtol=1e-5)
+    # and the mirror image for direction -1 (M:1774-1798)
+    uv, zy = fused, None
+    for layer in m.squeeze_factor_layers_list:
+        uv, _, zy = layer.forward_and_Jacobian(uv, None, zy)
+    vu = uv
+    for layer in reversed(m.layers_list):
+        vu, zy = layer.backward(vu, zy)
+    assert torch.equal(vu, m(fused, -1))
+
+
+def test_full_size_roundtrip_cfg2(dev):
+    """BASELINE config 2 at its full batch: size-independent properties."""
+    m, _ = mk(CFG2, 'rand', seed=5, dtype=torch.float32)
+    x = torch.from_numpy(synth_inputs('cfg2', 256, seed=6)).to(dev)
+    zy, ld = m(x, 1)
+    assert torch.isfinite(zy).all() and torch.isfinite(m.last_logdet_per_sample).all()
+    xb = m(zy, -1)
+    assert float((xb - x).abs().max() / x.abs().max()) < 1e-4
+    # batch independence: any sub-batch gives the same per-sample results (no cross-sample op)
+    zy_a, _ = m(x[:7].contiguous(), 1)
+    ld_a = m.last_logdet_per_sample.clone()
+    m(x, 1)
+    assert float((zy_a - zy[:7]).abs().max()) < 1e-5
+    assert float((ld_a - m.last_logdet_per_sample[:7]).abs().max() / ld_a.abs().max()) < 1e-5
+    # loss decomposition (M:1840-1848)
+    loss, zl, yl, dl = (float(t) for t in m.log_loss(x))
+    np.testing.assert_allclose(loss, zl + yl + dl, rtol=1e-5)
+
+
+def test_edge_cases(dev):
+    m, o = mk(SMALL, 'rand', seed=2)
+    # batch of one, and an empty batch
+    x = synth_inputs('noise:8x8x3', 1, seed=3)
+    zy, _ = m(torch.from_numpy(x).to(dev), 1)
+    want, _, _ = o.call(x.astype(np.float64), 1)
+    assert rel(zy.cpu().numpy(), want) < RTOL
+    e = torch.zeros(0, 8, 8, 3, device=dev)
+    zy, ld = m(e, 1)
+    assert zy.shape == (0, 8, 8, 3)
+    assert m(e, -1).shape == (0, 8, 8, 3)
+    with pytest.raises(AssertionError):
+        m.log_loss(e)
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 8, 8, 4, device=dev), 1)
+    with pytest.raises(TypeError):
+        m(torch.zeros(2, 8, 8, 3, device=dev, dtype=torch.float64), 1)
+    assert m(torch.zeros(1, 8, 8, 3, device=dev), 0) is None      # M:1743/M:1774: neither branch
+    # non-contiguous input is accepted (made compact on the host side)
+    xx = torch.from_numpy(synth_inputs('noise:8x8x3', 4, seed=8)).to(dev)
+    a, _ = m(xx[::2], 1)
+    b_, _ = m(xx[::2].contiguous(), 1)
+    assert torch.equal(a, b_)
+
+
+# ---------------------------------------------------------------------------------------------------
+# standalone fused coupling-law kernel
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [[8, 8, 3], [28, 28, 2], [6, 10, 5], [32, 32, 4]])
+@pytest.mark.parametrize("m", [0, 1, 2, 3])
+def test_coupling_law_kernel(dev, shape, m):
+    from arl_conditional_normalizing_flows_b200 import _lib
+    rng = np.random.default_rng(m)
+    B = 5
+    u = rng.standard_normal((B, *shape))
+    mc = m ^ 1
+    u2c = masks_np.mask(u, mc, True)
+    s = 0.5 * rng.standard_normal(u2c.shape)
+    t = rng.standard_normal(u2c.shape)
+    want_f = masks_np.mask(u, m, False) + masks_np.decompress_mask(np.exp(s) * u2c + t, mc, u.shape)
+    want_i = masks_np.mask(u, m, False) + masks_np.decompress_mask((u2c - t) / np.exp(s), mc, u.shape)
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    ut, st_, tt = f32(u), f32(s), f32(t)
+    for inverse, want in ((0, want_f), (1, want_i)):
+        v = torch.empty_like(ut)
+        ld = torch.empty(B + (-B) % 4, device=dev)[:B]
+        br = _lib.Borrowed()
+        _lib.check(_lib.lib.cnf_coupling_law(br(ut), br(st_), br(tt), m, inverse, br(v), br(ld), _lib.stream_ptr()))
+        assert rel(v.cpu().numpy(), want) < 1e-5
+        keep = masks_np.mask(np.ones_like(u), m, False) == 1
+        assert np.array_equal(v.cpu().numpy()[keep], u.astype(np.float32)[keep])
+        np.testing.assert_allclose(ld.cpu().numpy(), s.astype(np.float32).sum(axis=(1, 2, 3)), rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# toy model (config 1)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("width,num_layers,n", [(32, 6, 24), (16, 2, 12), (8, 0, 6)])
+def test_toy_vs_oracle(dev, width, num_layers, n):
+    from arl_conditional_normalizing_flows_b200.TOYcINN_make_model import cINN_affine
+    from oracle.toy import ToyOracle, toy_init_weights
+    W = toy_init_weights(n, width, num_layers, seed=3, scale=1.5)
+    order = list(np.random.default_rng(1).permutation(n))
+    m = cINN_affine(3, 2, n, width, num_layers, None, mask_indices=order, device=dev)
+    for j, cl in enumerate(m.coupling_layers_list):
+        flat = []
+        for net in ('b', 'A'):
+            for Wm, bv in W[j][net]:
+                flat += [Wm, bv]
+        cl.set_weights(flat)
+    o = ToyOracle(3, 2, n, W, mask_indices=order, dtype=np.float64)
+    rng = np.random.default_rng(0)
+    B = 1000
+    xy = np.concatenate([rng.standard_normal((B, 2)), np.where(rng.uniform(size=(B, 1)) < 0.5, -1.0, 1.0)], 1)
+    four_want, ps = o.log_loss(xy)
+    xt = torch.from_numpy(xy.astype(np.float32)).to(dev)
+    zy, ld = m(xt, -1)
+    assert rel(zy.cpu().numpy(), ps['zy']) < RTOL
+    np.testing.assert_allclose(ld.cpu().numpy(), ps['logdet'], rtol=RTOL, atol=RTOL * np.abs(ps['logdet']).mean())
+    four = [float(t) for t in m.log_loss(xt)]
+    np.testing.assert_allclose(four, four_want, rtol=RTOL, atol=1e-5)
+    back, zero = m(zy, 1)
+    assert zero == 0
+    assert rel(back.cpu().numpy(), xy) < RTOL
+    want_inv, _ = o.call(xy, 1)
+    got_inv, _ = m(xt, 1)
+    assert rel(got_inv.cpu().numpy(), want_inv) < RTOL
