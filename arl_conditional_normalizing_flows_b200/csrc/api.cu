@@ -52,7 +52,7 @@ int borrow(const DLManagedTensor* m, const char* name, int ndim, Ten* t, bool by
     t->shape[i] = d.shape[i];
     t->numel *= d.shape[i];
   }
-  if (d.strides) {
+  if (d.strides && t->numel > 0) {
     int64_t expect = 1;
     for (int i = d.ndim - 1; i >= 0; --i) {
       if (d.shape[i] != 1 && d.strides[i] != expect)

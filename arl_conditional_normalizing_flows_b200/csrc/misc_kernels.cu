@@ -208,8 +208,9 @@ __global__ void mask_uncompressed_kernel(const float* __restrict__ uv, float* __
   const int c = (int)(e % D);
   const long long px = e / D;
   const int x = (int)(px % W), y = (int)((px / W) % H);
-  // literal 0/1 multiply (einsum at M:715-717): keeps the reference's signed zeros / NaN propagation (Q8)
-  out[e] = __fmul_rn(in_mask(m, y, x, c) ? 1.0f : 0.0f, uv[e]);
+  // literal 0/1 multiply accumulated into a zero output (einsum at M:715-717): masked-out elements are
+  // +0 (NaN for non-finite input), kept elements are u*1+0, i.e. a copy except -0.0 -> +0.0 (Q8)
+  out[e] = __fadd_rn(__fmul_rn(in_mask(m, y, x, c) ? 1.0f : 0.0f, uv[e]), 0.0f);
 }
 
 __global__ void mask_compressed_kernel(const float* __restrict__ uv, float* __restrict__ out, long long n, FlowView v,
