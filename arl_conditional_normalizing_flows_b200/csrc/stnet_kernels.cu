@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "cnf_internal.h"
 #include "device_utils.cuh"
@@ -237,6 +238,204 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
   }
 }
 
+}  // namespace cnf
+#include "tc_kernels.cuh"
+namespace cnf {
+
+// ------------------------------------------------------------------------------------------
+// 1b. 1x1 convs, multi-sample tiles.  A CTA owns PT pixels x S samples (M = PT*S = 256 rows):
+//     gamma/beta of a pixel slot are loaded ONCE and shared by the S samples, and the S activation
+//     loads of a slot are independent (S+2 128-bit loads in flight per thread), which removes both the
+//     3x L2 traffic and the load-latency serialisation of the per-sample tiling above.
+//     Rows are m = s*PT + p; thread (tm, tn) owns rows tm + PT*r, r = 0..S-1, i.e. pixel tm of every
+//     sample, so LayerNorm statistics fall out per (thread, r) without a segmented reduction.
+// ------------------------------------------------------------------------------------------
+template <int TN, int NQ>
+__global__ void __launch_bounds__(256, 2) pw_kernel(const GemmArgs a) {
+  constexpr int NT = 256;
+  constexpr int RN = 4 * NQ;
+  constexpr int CT = TN / RN;   // threads along n
+  constexpr int PT = NT / CT;   // pixels per tile (= threads along m)
+  constexpr int S = 8;          // samples per tile (= rows per thread)
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float mr[S][2];
+  __shared__ float red[NT / 32][2 * S];
+
+  const int tid = threadIdx.x;
+  const int tn = tid % CT, tm = tid / CT;
+  const int tiles_n = (a.N + TN - 1) / TN;
+  const int tile_p = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+  const int s0 = blockIdx.y * S, net = blockIdx.z;
+  const int p0 = tile_p * PT, n0 = tile_n * TN;
+  const int KS = a.KC + 4;
+  float* As = smem;                 // [S*PT][KS]
+  float* Bs = smem + S * PT * KS;   // [KC][TN]
+  const int ns = min(S, a.B - s0);  // valid samples in this tile
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* Wg = P + a.w_off;
+  const float* gam = P + a.g_off;
+  const float* bet = P + a.be_off;
+  const bool n_vec = (a.N % 4) == 0;
+
+  if (tid < S) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
+    mr[tid][0] = mean;
+    mr[tid][1] = rstd;
+  }
+
+  float acc[S][RN];
+#pragma unroll
+  for (int r = 0; r < S; ++r)
+#pragma unroll
+    for (int c = 0; c < RN; ++c) acc[r][c] = 0.f;
+
+  const float* src_n = a.in + (long long)net * a.in_net_stride;
+  for (int kc0 = 0; kc0 < a.K; kc0 += a.KC) {
+    const int kc = min(a.KC, a.K - kc0);  // K % 4 == 0 is a launch precondition
+    __syncthreads();
+    for (int idx = tid; idx < kc * (TN / 4); idx += NT) {
+      const int k = idx / (TN / 4), nq = idx % (TN / 4);
+      const int n = n0 + nq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = Wg + (long long)(kc0 + k) * a.N + n;
+      if (n_vec && n + 3 < a.N) {
+        v = ld4(src);
+      } else {
+        if (n + 0 < a.N) v.x = src[0];
+        if (n + 1 < a.N) v.y = src[1];
+        if (n + 2 < a.N) v.z = src[2];
+        if (n + 3 < a.N) v.w = src[3];
+      }
+      st4(&Bs[k * TN + nq * 4], v);
+    }
+    const int kq_n = kc >> 2;
+    for (int slot = tid; slot < PT * kq_n; slot += NT) {
+      const int p = slot / kq_n, kq = slot - p * kq_n;
+      const int gp = p0 + p;
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool pv = gp < a.hw;
+      const long long e = (long long)gp * a.K + kc0 + kq * 4;
+      if (pv && a.ln) {
+        g = ld4(gam + e);
+        be = ld4(bet + e);
+      }
+#pragma unroll
+      for (int h = 0; h < S; h += 4) {   // two batches of 4 independent 128-bit loads (register budget)
+        float4 xv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (pv && h + r < ns) xv[r] = ld4(src_n + ((long long)(s0 + h + r) * a.hw) * a.K + e);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pv && h + r < ns) {
+            const float mean = mr[h + r][0], rstd = mr[h + r][1];
+            v = xv[r];
+            v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w);
+            if (a.ln) {
+              v.x = (v.x - mean) * rstd * g.x + be.x;
+              v.y = (v.y - mean) * rstd * g.y + be.y;
+              v.z = (v.z - mean) * rstd * g.z + be.z;
+              v.w = (v.w - mean) * rstd * g.w + be.w;
+            }
+          }
+          st4(&As[((h + r) * PT + p) * KS + kq * 4], v);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k4 = 0; k4 < kc; k4 += 4) {
+      float4 av[S];
+#pragma unroll
+      for (int r = 0; r < S; ++r) av[r] = ld4(&As[(tm + PT * r) * KS + k4]);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float bv[RN];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 t = ld4(&Bs[(k4 + kk) * TN + q * (TN / NQ) + tn * 4]);
+          bv[q * 4 + 0] = t.x; bv[q * 4 + 1] = t.y; bv[q * 4 + 2] = t.z; bv[q * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+          const float ar = kk == 0 ? av[r].x : kk == 1 ? av[r].y : kk == 2 ? av[r].z : av[r].w;
+#pragma unroll
+          for (int c = 0; c < RN; ++c) acc[r][c] = fmaf(ar, bv[c], acc[r][c]);
+        }
+      }
+    }
+  }
+
+  // epilogue: bias (+ residual), store, per-sample stats of LReLU(out)
+  const float* bias = P + a.b_off;
+  const int gp = p0 + tm;
+  float st1[S], st2[S];
+#pragma unroll
+  for (int r = 0; r < S; ++r) {
+    st1[r] = 0.f;
+    st2[r] = 0.f;
+    if (gp >= a.hw || r >= ns) continue;
+    const long long row = ((long long)(s0 + r) * a.hw + gp) * a.N;
+    float* out_r = a.out + (long long)net * a.out_net_stride + row;
+    const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int n = n0 + q * (TN / NQ) + tn * 4;
+      if (n >= a.N) continue;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = acc[r][q * 4 + j];
+      if (n_vec) {
+        const float4 bb = ld4(bias + n);
+        o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+        if (res_r) {
+          const float4 rr = ld4(res_r + n);
+          o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+        }
+        st4(out_r + n, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float l = lrelu(o[j]);
+          st1[r] += l;
+          st2[r] += l * l;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < a.N) {
+            float v = o[j] + bias[n + j];
+            if (res_r) v += res_r[n + j];
+            out_r[n + j] = v;
+            const float l = lrelu(v);
+            st1[r] += l;
+            st2[r] += l * l;
+          }
+      }
+    }
+  }
+  if (a.stats_out) {
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+      const float v1 = warp_sum(st1[r]), v2 = warp_sum(st2[r]);
+      if (lane == 0) {
+        red[wid][2 * r] = v1;
+        red[wid][2 * r + 1] = v2;
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * S && (tid >> 1) < ns) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) t += (double)red[w][tid];
+      atomicAdd(a.stats_out + 2 * ((long long)net * a.B + s0 + (tid >> 1)) + (tid & 1), t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // 2. Grouped dilated 3x3 convs of one residual block, all dilation branches in one launch,
 //    written straight into the concat layout (F:397-411, F:577-590).
@@ -415,7 +614,7 @@ __global__ void __launch_bounds__(GC_NT) gconv_kernel(const GconvArgs a) {
       br_w_off = a.br[i].w_off; br_b_off = a.br[i].b_off;
     }
   }
-  (void)br_groups;
+
   const int local = blockIdx.x - br_first;
   const int tiles = a.tiles_y * a.tiles_x;
   const int g = local / tiles, tile = local % tiles;
@@ -478,6 +677,230 @@ __global__ void __launch_bounds__(GC_NT) gconv_kernel(const GconvArgs a) {
       s2 = s12[1];
       break;
     }
+  }
+  if (a.stats_out) {
+    double d1, d2;
+    block_sum2(s1, s2, red, d1, d2);
+    if (tid == 0) {
+      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+      atomicAdd(so, d1);
+      atomicAdd(so + 1, d2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2b. Grouped dilated convs, register-blocked: 128-thread CTAs; the weights of the current tap
+//     (G x G) live in registers and are reused by up to 8 pixels per thread (FFMA:LDS.128 = 16:1 at
+//     G = 8); the LN(LReLU(.)) tile is staged with 128/64/32-bit vector slots, four slots per thread
+//     in flight.  Used when every branch has gin == gout in {1,2,4,8}; other shapes take gconv_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int GC2_NT = 128;
+constexpr int GC2_PX = 8;
+
+template <int V> struct VecT;
+template <> struct VecT<4> { using T = float4; };
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<1> { using T = float; };
+
+template <int V>
+__device__ __forceinline__ void gc2_stage(const float* __restrict__ src_s, const float* __restrict__ gam,
+                                          const float* __restrict__ bet, float* __restrict__ in_s, int gin, int GS,
+                                          int cin0, int Cin, int h, int w, int y0, int x0, int halo, int SH, int SW,
+                                          int ln, float mean, float rstd) {
+  using T = typename VecT<V>::T;
+  constexpr int U = 4;
+  const int vpp = gin / V;  // vector slots per pixel
+  const int n_slots = SH * SW * vpp;
+  for (int base = threadIdx.x; base < n_slots; base += GC2_NT * U) {
+    T xv[U], gv[U], bv[U];
+    bool ok[U];
+    int dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int slot = base + u * GC2_NT;
+      ok[u] = false;
+      dst[u] = -1;
+      if (slot < n_slots) {
+        const int pix = slot / vpp, cv = slot - pix * vpp;
+        const int sy = pix / SW, sx = pix - sy * SW;
+        const int gy = y0 - halo + sy, gx = x0 - halo + sx;
+        dst[u] = pix * GS + cv * V;
+        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+          ok[u] = true;
+          const long long e = ((long long)gy * w + gx) * Cin + cin0 + cv * V;
+          xv[u] = *reinterpret_cast<const T*>(src_s + e);
+          if (ln) {
+            gv[u] = *reinterpret_cast<const T*>(gam + e);
+            bv[u] = *reinterpret_cast<const T*>(bet + e);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (dst[u] < 0) continue;
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.f;
+      if (ok[u]) {
+        const float* xf = reinterpret_cast<const float*>(&xv[u]);
+        const float* gf = reinterpret_cast<const float*>(&gv[u]);
+        const float* bf = reinterpret_cast<const float*>(&bv[u]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float v = lrelu(xf[i]);
+          if (ln) v = (v - mean) * rstd * gf[i] + bf[i];
+          o[i] = v;
+        }
+      }
+      *reinterpret_cast<T*>(in_s + dst[u]) = *reinterpret_cast<const T*>(o);
+    }
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void gc2_compute(const GcGeom q, const float* __restrict__ in_s, const float* __restrict__ w_s,
+                                            const float* __restrict__ b_s, int SW, int GS, int th, int tw, int y0,
+                                            int x0, float* __restrict__ out_s, float& s1, float& s2) {
+  const int tid = threadIdx.x;
+  const int TP = th * tw;
+  const int npx = (TP + GC2_NT - 1) / GC2_NT;
+  const int d = q.dil, ks = q.ks;
+  float acc[GC2_PX][G];
+  int poff[GC2_PX];
+#pragma unroll
+  for (int j = 0; j < GC2_PX; ++j) {
+    const int p = min(tid + j * GC2_NT, TP - 1);
+    poff[j] = ((p / tw) * SW + (p % tw)) * GS;
+#pragma unroll
+    for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
+  }
+  for (int ky = 0; ky < ks; ++ky) {
+    for (int kx = 0; kx < ks; ++kx) {
+      const int toff = (ky * d * SW + kx * d) * GS;
+      const float* wt = w_s + (ky * ks + kx) * G * G;
+      float wv[G][G];
+#pragma unroll
+      for (int ci = 0; ci < G; ++ci) {
+        if (G % 4 == 0) {
+#pragma unroll
+          for (int c4 = 0; c4 < G; c4 += 4) {
+            const float4 t = ld4(wt + ci * G + c4);
+            wv[ci][c4] = t.x; wv[ci][c4 + 1] = t.y; wv[ci][c4 + 2] = t.z; wv[ci][c4 + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < G; ++c) wv[ci][c] = wt[ci * G + c];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < GC2_PX; ++j) {
+        if (j < npx) {
+          const float* src = in_s + poff[j] + toff;
+          float xv[G];
+          if (G % 4 == 0) {
+#pragma unroll
+            for (int c4 = 0; c4 < G; c4 += 4) {
+              const float4 t = ld4(src + c4);
+              xv[c4] = t.x; xv[c4 + 1] = t.y; xv[c4 + 2] = t.z; xv[c4 + 3] = t.w;
+            }
+          } else if (G == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(src);
+            xv[0] = t.x; xv[G - 1] = t.y;
+          } else {
+            xv[0] = src[0];
+          }
+#pragma unroll
+          for (int ci = 0; ci < G; ++ci)
+#pragma unroll
+            for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[ci], wv[ci][co], acc[j][co]);
+        }
+      }
+    }
+  }
+  const int cbase = q.cbase;
+  const bool vec = (G % 4 == 0) && (q.Cout % 4 == 0) && (cbase % 4 == 0);
+#pragma unroll
+  for (int j = 0; j < GC2_PX; ++j) {
+    const int p = tid + j * GC2_NT;
+    if (j < npx && p < TP) {
+      const int y = y0 + p / tw, x = x0 + p % tw;
+      float* dst = out_s + ((long long)y * q.w + x) * q.Cout + cbase;
+      float o[G];
+#pragma unroll
+      for (int co = 0; co < G; ++co) {
+        o[co] = acc[j][co] + b_s[co];
+        const float l = lrelu(o[co]);
+        s1 += l;
+        s2 += l * l;
+      }
+      if (vec) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
+      } else {
+#pragma unroll
+        for (int co = 0; co < G; ++co) dst[co] = o[co];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GC2_NT) gconv2_kernel(const GconvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[64];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, net = blockIdx.z;
+  int br_dil = a.br[0].dil, br_gin = a.br[0].gin, br_out_off = a.br[0].out_off, br_first = 0;
+  long long br_w_off = a.br[0].w_off, br_b_off = a.br[0].b_off;
+#pragma unroll
+  for (int i = 1; i < CNF_MAX_BRANCHES; ++i) {
+    if (i < a.n_br && (int)blockIdx.x >= a.br[i].first_item) {
+      br_dil = a.br[i].dil; br_gin = a.br[i].gin; br_out_off = a.br[i].out_off; br_first = a.br[i].first_item;
+      br_w_off = a.br[i].w_off; br_b_off = a.br[i].b_off;
+    }
+  }
+  const int local = blockIdx.x - br_first;
+  const int tiles = a.tiles_y * a.tiles_x;
+  const int g = local / tiles, tile = local % tiles;
+  const int y0 = (tile / a.tiles_x) * a.TH, x0 = (tile % a.tiles_x) * a.TW;
+  const int th = min(a.TH, a.h - y0), tw = min(a.TW, a.w - x0);
+  const int halo = br_dil * (a.ks - 1) / 2;
+  const int SH = th + 2 * halo, SW = tw + 2 * halo;
+  const int G = br_gin;
+  const int GS = gc_stride(G);
+  float* in_s = smem;
+  float* w_s = in_s + (((long long)SH * SW * GS + 3) & ~3);
+  float* b_s = w_s + ((a.ks * a.ks * G * G + 3) & ~3);
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  float mean = 0.f, rstd = 1.f;
+  if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.Cin, mean, rstd);
+  {
+    const float* wsrc = P + br_w_off + (long long)g * a.ks * a.ks * G * G;
+    for (int i = tid; i < a.ks * a.ks * G * G; i += GC2_NT) w_s[i] = wsrc[i];
+    const float* bsrc = P + br_b_off + g * G;
+    if (tid < G) b_s[tid] = bsrc[tid];
+  }
+  const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.Cin;
+  const float* gam = P + a.g_off;
+  const float* bet = P + a.be_off;
+  const int cin0 = g * G;
+  const bool al4 = (a.Cin % 4) == 0, al2 = (a.Cin % 2) == 0;
+  if (G % 4 == 0 && al4) gc2_stage<4>(src_s, gam, bet, in_s, G, GS, cin0, a.Cin, a.h, a.w, y0, x0, halo, SH, SW, a.ln, mean, rstd);
+  else if (G % 2 == 0 && al2) gc2_stage<2>(src_s, gam, bet, in_s, G, GS, cin0, a.Cin, a.h, a.w, y0, x0, halo, SH, SW, a.ln, mean, rstd);
+  else gc2_stage<1>(src_s, gam, bet, in_s, G, GS, cin0, a.Cin, a.h, a.w, y0, x0, halo, SH, SW, a.ln, mean, rstd);
+  __syncthreads();
+
+  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.h * a.w * a.Cout;
+  float s1 = 0.f, s2 = 0.f;
+  GcGeom q;
+  q.dil = br_dil; q.ks = a.ks; q.gin = G; q.gout = G; q.cbase = br_out_off + g * G; q.w = a.w; q.Cout = a.Cout;
+  switch (G) {
+    case 1: gc2_compute<1>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    case 2: gc2_compute<2>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    case 4: gc2_compute<4>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
+    default: gc2_compute<8>(q, in_s, w_s, b_s, SW, GS, th, tw, y0, x0, out_s, s1, s2); break;
   }
   if (a.stats_out) {
     double d1, d2;
@@ -666,8 +1089,69 @@ static int launch_gemm(GemmArgs a, cudaStream_t st) {
   return launch_gemm_t<16, 1, 4, STEM>(a, st);
 }
 
+template <int TN, int NQ>
+static int launch_pw_t(GemmArgs a, cudaStream_t st) {
+  constexpr int CT = TN / (4 * NQ), PT = 256 / CT, S = 8;
+  const int nchunks = (a.K + 63) / 64;
+  a.KC = (((a.K + nchunks - 1) / nchunks) + 3) & ~3;
+  const size_t smem = ((size_t)S * PT * (a.KC + 4) + (size_t)a.KC * TN) * sizeof(float);
+  auto kern = pw_kernel<TN, NQ>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  const int tiles_p = (a.hw + PT - 1) / PT, tiles_n = (a.N + TN - 1) / TN;
+  dim3 grid(tiles_p * tiles_n, (a.B + S - 1) / S, 2);
+  kern<<<grid, 256, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int N>
+static int launch_pw_tc_t(const GemmArgs& a, cudaStream_t st) {
+  constexpr size_t smem = 2 * (size_t)(2 * 128 * 32 + 2 * N * 32) * sizeof(float);
+  auto kern = pw_tc_kernel<N>;
+  static bool configured = false;
+  if (!configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.hw + 31) / 32, (a.B + 3) / 4, 2);
+  kern<<<grid, 256, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+static bool use_tensor_cores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNF_PW_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// 1x1 conv dispatcher: tcgen05 3xTF32 kernel when the shape fits one UMMA tile family (N in {16,32,64},
+// K % 8 == 0); otherwise the FFMA multi-sample kernel (K % 4 == 0) or the per-sample generic kernel.
+static int launch_pw(const GemmArgs& a, cudaStream_t st) {
+  if (use_tensor_cores() && a.K % 8 == 0 && (a.B + 3) / 4 <= 65535) {
+    if (a.N == 64) return launch_pw_tc_t<64>(a, st);
+    if (a.N == 32) return launch_pw_tc_t<32>(a, st);
+    if (a.N == 16) return launch_pw_tc_t<16>(a, st);
+  }
+  if (a.K % 4 == 0 && a.B <= 65535 * 8) {
+    if (a.N > 32) return launch_pw_t<64, 2>(a, st);
+    return launch_pw_t<32, 1>(a, st);
+  }
+  return launch_gemm<false>(a, st);
+}
+
 static int launch_gconv(GconvArgs a, cudaStream_t st) {
-  // whole plane when it fits 4 pixels/thread, else 32x32 tiles
+  bool v2 = true;
+  for (int i = 0; i < a.n_br; ++i) {
+    const int g = a.br[i].gin;
+    if (a.br[i].gin != a.br[i].gout || !(g == 1 || g == 2 || g == 4 || g == 8)) v2 = false;
+  }
+  // whole plane when it fits the pixels-per-thread budget, else 32x32 tiles
   a.TH = std::min(a.h, 32);
   a.TW = std::min(a.w, 32);
   a.tiles_y = (a.h + a.TH - 1) / a.TH;
@@ -684,13 +1168,23 @@ static int launch_gconv(GconvArgs a, cudaStream_t st) {
     smem = std::max(smem, (in_sz + w_sz + a.br[i].gout + 4) * sizeof(float));
   }
   if (smem > 227 * 1024) return (int)cudaErrorInvalidConfiguration;
+  dim3 grid(items, a.B, 2);
+  if (v2) {
+    static size_t configured2 = 0;
+    if (smem > configured2) {
+      CU_TRY(cudaFuncSetAttribute(gconv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)std::max(smem, (size_t)48 * 1024)));
+      configured2 = std::max(smem, (size_t)48 * 1024);
+    }
+    gconv2_kernel<<<grid, GC2_NT, smem, st>>>(a);
+    return (int)cudaGetLastError();
+  }
   static size_t configured = 0;
   if (smem > configured) {
     CU_TRY(cudaFuncSetAttribute(gconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)std::max(smem, (size_t)48 * 1024)));
     configured = std::max(smem, (size_t)48 * 1024);
   }
-  dim3 grid(items, a.B, 2);
   gconv_kernel<<<grid, GC_NT, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
@@ -759,7 +1253,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
       a.stats_in = stats(3 * r); a.stats_out = stats(3 * r + 1);
       a.out = W.Y1; a.out_net_stride = (long long)B * hw * nk;
       a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln;
-      CU_TRY((cudaError_t)launch_gemm<false>(a, st));
+      CU_TRY((cudaError_t)launch_pw(a, st));
     }
     {  // grouped dilated convs: Y1 -> Y2
       GconvArgs a = {};
@@ -784,7 +1278,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
       a.stats_in = stats(3 * r + 2); a.stats_out = stats(3 * r + 3);
       a.out = W.X; a.res = W.X; a.out_net_stride = (long long)B * hw * nk;
       a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln;
-      CU_TRY((cudaError_t)launch_gemm<false>(a, st));
+      CU_TRY((cudaError_t)launch_pw(a, st));
     }
   }
   {  // head + coupling

@@ -1,0 +1,321 @@
+// tcgen05 / TMEM 1x1-conv kernel (sm_100a only).
+//
+// out[m, n] = sum_k LN(LReLU(x))[m, k] * W[k, n] + bias[n] (+ res[m, n]) on the 5th-generation tensor
+// cores with fp32-level accuracy: every fp32 operand is split x = hi + lo with hi = x truncated to TF32
+// (low 13 mantissa bits cleared, exactly what kind::tf32 reads) and lo = x - hi (exact in fp32), and three
+// MMAs hi*hi + lo*hi + hi*lo accumulate into one fp32 TMEM tile (the dropped lo*lo term is ~2^-20 relative).
+//
+// A CTA owns 128 rows = 4 samples x 32 pixels (gamma/beta of a pixel slot are loaded once and shared by
+// the 4 samples).  K is consumed in chunks of 32 through a 2-stage shared-memory ring: all 8 warps apply
+// LReLU + LayerNorm + the hi/lo split in registers and store the operands in the canonical K-major
+// no-swizzle UMMA layout (core matrix = 8 rows x 16 B; LBO = 128 B between K chunks, SBO = 1 KB between
+// 8-row groups); one thread then issues 12 tcgen05.mma (4 K-steps x 3 terms) and a tcgen05.commit that
+// releases the stage, so the next chunk's loads overlap the tensor-core work.  The epilogue reads the
+// accumulators back with tcgen05.ld (32 lanes x 32b x N/2 columns per thread), adds bias/residual, stores
+// and accumulates the LayerNorm statistics of LReLU(out) for the consumer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cnf_internal.h"
+#include "device_utils.cuh"
+
+namespace cnf {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Bounded wait: a malformed descriptor must surface as a trap (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major, no swizzle: start address, leading (K-chunk) byte offset, stride (8-row group) byte offset.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
+  tmem_ld<16>(taddr, v);
+  tmem_ld<16>(taddr + 16, v + 16);
+}
+
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256, 2) pw_tc_kernel(const GemmArgs a) {
+  constexpr int NT = 256;
+  constexpr int S = 4, PT = 32, M = 128;
+  constexpr int KC = 32;                       // K chunk (floats) per pipeline stage
+  constexpr int A_ST = M * KC;                 // floats per A operand image (hi or lo)
+  constexpr int B_ST = N * KC;
+  constexpr int STAGE = 2 * A_ST + 2 * B_ST;   // floats per stage
+  constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
+  constexpr int NC = N / 2;                    // accumulator columns per thread in the epilogue
+  extern __shared__ __align__(128) float tc_smem[];
+  float* smem = tc_smem;
+  __shared__ __align__(8) uint64_t bar_free[2];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float mr[S][2];
+  __shared__ float red[NT / 32][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p0 = blockIdx.x * PT;
+  const int s0 = blockIdx.y * S, net = blockIdx.z;
+  const int ns = min(S, a.B - s0);
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* Wg = P + a.w_off;
+  const float* gam = P + a.g_off;
+  const float* bet = P + a.be_off;
+  const float* src_n = a.in + (long long)net * a.in_net_stride;
+
+  if (tid == 0) {
+    mbar_init(&bar_free[0], 1);
+    mbar_init(&bar_free[1], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < S) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
+    mr[tid][0] = mean;
+    mr[tid][1] = rstd;
+  }
+  if (wid == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  const int nchunks = (a.K + KC - 1) / KC;
+  // A staging role of this thread: row r of an 8-row group, K quad kq (16 B) of the chunk
+  const int ar = lane & 7, akq = (lane >> 3) + 4 * (wid >> 2);  // kq in 0..7
+  const int ap = 8 * (wid & 3) + ar;                            // pixel inside the tile, 0..31
+  const int gp = p0 + ap;
+  const bool pv = gp < a.hw;
+  // B staging role: n row nr of an 8-row group, k = 4*kq + (lane>>3)
+  const int bnr = lane & 7, bkr = lane >> 3;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int stage = c & 1;
+    float* As_hi = smem + stage * STAGE;
+    float* As_lo = As_hi + A_ST;
+    float* Bs_hi = As_lo + A_ST;
+    float* Bs_lo = Bs_hi + B_ST;
+    const int k0 = c * KC;
+    const int kc = min(KC, a.K - k0);   // multiple of 8 (launch precondition)
+    if (c >= 2) mbar_wait(&bar_free[stage], ((c >> 1) - 1) & 1);   // MMAs of chunk c-2 have drained this stage
+
+    // ---- A: LReLU + LayerNorm + split, canonical K-major layout
+    if (akq * 4 < kc) {
+      const long long e = (long long)gp * a.K + k0 + akq * 4;
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 xv[S];
+      if (pv) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          if (s < ns) xv[s] = ld4(src_n + ((long long)(s0 + s) * a.hw) * a.K + e);
+        if (a.ln) {
+          g = ld4(gam + e);
+          be = ld4(bet + e);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pv && s < ns) {
+          const float mean = mr[s][0], rstd = mr[s][1];
+          v[0] = lrelu(xv[s].x); v[1] = lrelu(xv[s].y); v[2] = lrelu(xv[s].z); v[3] = lrelu(xv[s].w);
+          if (a.ln) {
+            v[0] = (v[0] - mean) * rstd * g.x + be.x;
+            v[1] = (v[1] - mean) * rstd * g.y + be.y;
+            v[2] = (v[2] - mean) * rstd * g.z + be.z;
+            v[3] = (v[3] - mean) * rstd * g.w + be.w;
+          }
+        }
+        float h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tf32_split(v[i], h[i], l[i]);
+        // row m = s*32 + ap -> 8-row group (m >> 3), row (m & 7) = ar; 16-B unit = ar + 8*akq + 64*group
+        const int unit = ar + 8 * akq + 64 * ((s * PT + ap) >> 3);
+        st4(As_hi + 4 * unit, make_float4(h[0], h[1], h[2], h[3]));
+        st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
+      }
+    }
+    // ---- B: W[k][n] -> K-major [n][k] images (hi / lo)
+    for (int it = wid; it < (N / 8) * (KC / 4); it += NT / 32) {
+      const int ng = it % (N / 8), kq = it / (N / 8);
+      const int n = ng * 8 + bnr, k = kq * 4 + bkr;
+      float w = 0.f;
+      if (k < kc) w = Wg[(long long)(k0 + k) * a.N + n];
+      float h, l;
+      tf32_split(w, h, l);
+      const int off = 4 * (bnr + 8 * kq + (KC / 4) * 8 * ng) + bkr;
+      Bs_hi[off] = h;
+      Bs_lo[off] = l;
+    }
+    fence_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(N);
+      const uint32_t a_hi = smem_u32(As_hi), a_lo = smem_u32(As_lo), b_hi = smem_u32(Bs_hi), b_lo = smem_u32(Bs_lo);
+      constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
+      for (int ks = 0; ks < kc / 8; ++ks) {
+        const uint32_t adv = ks * 2 * LBO;    // 8 tf32 = two 16-B K chunks per MMA
+        const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
+        const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
+        umma_tf32(tmem_d, dah, dbh, idesc, (c | ks) != 0);
+        umma_tf32(tmem_d, dal, dbh, idesc, 1);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1);
+      }
+      umma_commit(&bar_free[stage]);
+      if (c == nchunks - 1) umma_commit(&bar_done);
+    }
+  }
+
+  // ---- epilogue
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  const int quarter = wid & 3, half = wid >> 2;
+  const int m = quarter * 32 + lane;           // accumulator row == TMEM lane
+  const int es = m / PT, ep = m % PT;          // sample / pixel of this row (PT == 32: es == quarter)
+  float v[NC];
+  tmem_ld<NC>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC), v);
+  const int egp = p0 + ep;
+  float s1 = 0.f, s2 = 0.f;
+  if (egp < a.hw && es < ns) {
+    const long long row = ((long long)(s0 + es) * a.hw + egp) * a.N + half * NC;
+    float* out_r = a.out + (long long)net * a.out_net_stride + row;
+    const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
+    const float* bias = P + a.b_off + half * NC;
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const float4 bb = ld4(bias + j);
+      float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
+      if (res_r) {
+        const float4 rr = ld4(res_r + j);
+        o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
+      }
+      st4(out_r + j, make_float4(o0, o1, o2, o3));
+      float l;
+      l = lrelu(o0); s1 += l; s2 += l * l;
+      l = lrelu(o1); s1 += l; s2 += l * l;
+      l = lrelu(o2); s1 += l; s2 += l * l;
+      l = lrelu(o3); s1 += l; s2 += l * l;
+    }
+  }
+  if (a.stats_out) {
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      red[wid][0] = s1;
+      red[wid][1] = s2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (a.stats_out && tid < 2 * S && (tid >> 1) < ns) {
+    // sample s is covered by warps s (columns [0, N/2)) and s + 4 (columns [N/2, N))
+    const int s = tid >> 1, which = tid & 1;
+    const double t = (double)red[s][which] + (double)red[s + 4][which];
+    atomicAdd(a.stats_out + 2 * ((long long)net * a.B + s0 + s) + which, t);
+  }
+  if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+}  // namespace cnf
