@@ -3,8 +3,10 @@
 // coupling_layer.forward_and_Jacobian / backward (M:1258-1394).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "cnf_internal.h"
@@ -96,17 +98,44 @@ int64_t max_coupling_ws(const cnf_plan* p, int64_t B) {
   return m;
 }
 
+// Samples per pass through the layers.  Every op is per-sample, so the batch can be cut into chunks
+// whose s/t-net activations (3 buffers of 2*chunk*h*w*nk floats) stay resident in the 126 MB L2 between the
+// kernel that writes them and the kernel that reads them.  CNF_BATCH_CHUNK overrides (0 = whole batch).
+int batch_chunk(const cnf_plan* p, int64_t B) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("CNF_BATCH_CHUNK");
+    env = e ? atoi(e) : -1;
+  }
+  if (env <= 0) return (int)B;   // default: whole batch (measured: chunking under-fills the small layers)
+  if (env > 0) return (int)std::min<int64_t>(B, env);
+  // (unused) auto policy: keep the two live buffers of the widest layer under ~48 MB
+  int64_t per_sample = 0;
+  for (auto* c : p->couplings) {
+    const int64_t b = 2LL * c->hw() * (c->nk + std::max(c->nk, c->cat)) * 4;
+    per_sample = std::max(per_sample, b);
+  }
+  int64_t chunk = (48LL << 20) / std::max<int64_t>(per_sample, 1);
+  chunk = std::max<int64_t>(8, (chunk / 8) * 8);
+  return (int)std::min<int64_t>(B, chunk);
+}
+
 // direction +1: all couplings in order, in place on `buf`; -1: reversed with the inverse law.
 int run_flow(const cnf_plan* p, const float* params, float* buf, int B, int direction, double* ldacc, void* ws,
              void* stream) {
   const int n = (int)p->couplings.size();
-  for (int s = 0; s < n; ++s) {
-    const int li = direction == 1 ? s : n - 1 - s;
-    const cnf_coupling* c = p->couplings[li];
-    FlowView v = make_view(buf, p->H, p->W, p->D, p->level[li]);
-    const int e = run_coupling(c, params + p->param_off[li], v, c->mask, v, B, direction == 1 ? HEAD_FWD : HEAD_INV,
-                               ldacc, nullptr, nullptr, ws, stream);
-    if (e) return cuda_rc(e, "coupling layer");
+  const int chunk = batch_chunk(p, B);
+  const long long per = (long long)p->H * p->W * p->D;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    for (int s = 0; s < n; ++s) {
+      const int li = direction == 1 ? s : n - 1 - s;
+      const cnf_coupling* c = p->couplings[li];
+      FlowView v = make_view(buf + b0 * per, p->H, p->W, p->D, p->level[li]);
+      const int e = run_coupling(c, params + p->param_off[li], v, c->mask, v, nb, direction == 1 ? HEAD_FWD : HEAD_INV,
+                                 ldacc ? ldacc + b0 : nullptr, nullptr, nullptr, ws, stream);
+      if (e) return cuda_rc(e, "coupling layer");
+    }
   }
   return CNF_OK;
 }

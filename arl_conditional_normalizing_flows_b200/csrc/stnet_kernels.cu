@@ -689,6 +689,10 @@ __global__ void __launch_bounds__(GC_NT) gconv_kernel(const GconvArgs a) {
   }
 }
 
+}  // namespace cnf
+#include "tc_gconv.cuh"
+namespace cnf {
+
 // ------------------------------------------------------------------------------------------
 // 2b. Grouped dilated convs, register-blocked: 128-thread CTAs; the weights of the current tap
 //     (G x G) live in registers and are reused by up to 8 pixels per thread (FFMA:LDS.128 = 16:1 at
@@ -914,6 +918,194 @@ __global__ void __launch_bounds__(GC2_NT) gconv2_kernel(const GconvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// 2c. Grouped dilated convs, one branch per launch, templated on group width G and pixels per
+//     thread PX (no per-pixel branches; out-of-range pixels are clamped and simply not stored).
+//     Tap loops are NOT unrolled (the body is ~9 KB of SASS and stays in the instruction cache);
+//     staging walks rows and vector slots without integer divisions; the LayerNorm coefficients are
+//     computed once per CTA (fp64) and broadcast through shared memory.
+// ------------------------------------------------------------------------------------------
+template <int G, int PX>
+__global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
+  constexpr int V = G >= 4 ? 4 : G;        // staging vector width (floats)
+  constexpr int VPP = G / V;               // vector slots per pixel
+  constexpr int GS = G + ((G % 8) == 0 ? 4 : 0);
+  using T = typename VecT<V>::T;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[64];
+  __shared__ float mr[2];
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
+  const int b = blockIdx.y, net = blockIdx.z;
+  const GconvBranch& br = a.br[0];
+  const int tiles = a.tiles_y * a.tiles_x;
+  const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const int y0 = (tile / a.tiles_x) * a.TH, x0 = (tile % a.tiles_x) * a.TW;
+  const int th = min(a.TH, a.h - y0), tw = min(a.TW, a.w - x0);
+  const int d = br.dil;
+  const int halo = d;                      // ksize 3
+  const int SH = th + 2 * halo, SW = tw + 2 * halo;
+  float* in_s = smem;                                        // [SH*SW][GS]
+  float* w_s = in_s + ((SH * SW * GS + 3) & ~3);             // [9][G][G]
+  float* b_s = w_s + ((9 * G * G + 3) & ~3);
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  if (tid == 0) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.Cin, mean, rstd);
+    mr[0] = mean;
+    mr[1] = rstd;
+  }
+  {
+    const float* wsrc = P + br.w_off + (long long)g * 9 * G * G;
+    for (int i = tid; i < 9 * G * G; i += NT) w_s[i] = wsrc[i];
+    if (tid < G) b_s[tid] = P[br.b_off + g * G + tid];
+  }
+  __syncthreads();
+  const float mean = mr[0], rstd = mr[1];
+  {
+    const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.Cin;
+    const float* gam = P + a.g_off;
+    const float* bet = P + a.be_off;
+    const int cin0 = g * G;
+    const int row_slots = SW * VPP;
+    for (int sy = wid; sy < SH; sy += nw) {
+      const int gy = y0 - halo + sy;
+      const bool rowok = gy >= 0 && gy < a.h;
+      for (int sl0 = 0; sl0 < row_slots; sl0 += 64) {       // two slots per lane in flight
+        T xv[2], gv[2], bv[2];
+        bool ok[2];
+        int sl[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          sl[u] = sl0 + u * 32 + lane;
+          const int sx = sl[u] / VPP, cv = sl[u] % VPP;
+          const int gx = x0 - halo + sx;
+          ok[u] = rowok && sl[u] < row_slots && gx >= 0 && gx < a.w;
+          if (ok[u]) {
+            const long long e = ((long long)gy * a.w + gx) * a.Cin + cin0 + cv * V;
+            xv[u] = *reinterpret_cast<const T*>(src_s + e);
+            if (a.ln) {
+              gv[u] = *reinterpret_cast<const T*>(gam + e);
+              bv[u] = *reinterpret_cast<const T*>(bet + e);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (sl[u] >= row_slots) continue;
+          float o[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = 0.f;
+          if (ok[u]) {
+            const float* xf = reinterpret_cast<const float*>(&xv[u]);
+            const float* gf = reinterpret_cast<const float*>(&gv[u]);
+            const float* bf = reinterpret_cast<const float*>(&bv[u]);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              float v = lrelu(xf[i]);
+              if (a.ln) v = (v - mean) * rstd * gf[i] + bf[i];
+              o[i] = v;
+            }
+          }
+          const int sx = sl[u] / VPP, cv = sl[u] % VPP;
+          *reinterpret_cast<T*>(in_s + (sy * SW + sx) * GS + cv * V) = *reinterpret_cast<const T*>(o);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const int TP = th * tw;
+  float acc[PX][G];
+  int poff[PX];
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    const int p = min(tid + j * NT, TP - 1);
+    poff[j] = ((p / tw) * SW + (p % tw)) * GS;
+#pragma unroll
+    for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
+  }
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int toff = (ky * d * SW + kx * d) * GS;
+    const float* wt = w_s + tap * G * G;
+    float wv[G][G];
+#pragma unroll
+    for (int ci = 0; ci < G; ++ci) {
+      if (G % 4 == 0) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) {
+          const float4 t = ld4(wt + ci * G + c4);
+          wv[ci][c4] = t.x; wv[ci][c4 + 1] = t.y; wv[ci][c4 + 2] = t.z; wv[ci][c4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < G; ++c) wv[ci][c] = wt[ci * G + c];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      const float* src = in_s + poff[j] + toff;
+      float xv[G];
+      if (G % 4 == 0) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) {
+          const float4 t = ld4(src + c4);
+          xv[c4] = t.x; xv[c4 + 1] = t.y; xv[c4 + 2] = t.z; xv[c4 + 3] = t.w;
+        }
+      } else if (G == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(src);
+        xv[0] = t.x; xv[G - 1] = t.y;
+      } else {
+        xv[0] = src[0];
+      }
+#pragma unroll
+      for (int ci = 0; ci < G; ++ci)
+#pragma unroll
+        for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[ci], wv[ci][co], acc[j][co]);
+    }
+  }
+
+  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.h * a.w * a.Cout;
+  const int cbase = br.out_off + g * G;
+  const bool vec = (G % 4 == 0) && (a.Cout % 4 == 0) && (cbase % 4 == 0);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    const int p = tid + j * NT;
+    if (p < TP) {
+      const int y = y0 + p / tw, x = x0 + p % tw;
+      float* dst = out_s + ((long long)y * a.w + x) * a.Cout + cbase;
+      float o[G];
+#pragma unroll
+      for (int co = 0; co < G; ++co) {
+        o[co] = acc[j][co] + b_s[co];
+        const float l = lrelu(o[co]);
+        s1 += l;
+        s2 += l * l;
+      }
+      if (vec) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
+      } else {
+#pragma unroll
+        for (int co = 0; co < G; ++co) dst[co] = o[co];
+      }
+    }
+  }
+  if (a.stats_out) {
+    double d1, d2;
+    block_sum2(s1, s2, red, d1, d2);
+    if (tid == 0) {
+      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+      atomicAdd(so, d1);
+      atomicAdd(so + 1, d2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 3. Head conv (both nets) fused with tanh*w, exp, the affine coupling law, the decompress
 //    scatter into the flow buffer and the per-sample log-det (M:1133-1150, M:1198, M:1307-1326,
 //    M:1379-1394).  One thread per output pixel, all c2 channels of both nets.
@@ -953,12 +1145,15 @@ __global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
   const bool valid = tid < th * a.w;
   const int py = valid ? tid / a.w : 0, px = valid ? tid % a.w : 0;
 
-  float mean[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
-  if (a.ln) {
-#pragma unroll
-    for (int net = 0; net < 2; ++net)
-      ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.nk, mean[net], rstd[net]);
+  __shared__ float mr_s[2][2];
+  if (tid < 2) {
+    float m_ = 0.f, r_ = 1.f;
+    if (a.ln) ln_coeffs(a.stats_in, (long long)tid * a.B + b, (double)a.h * a.w * (double)a.nk, m_, r_);
+    mr_s[tid][0] = m_;
+    mr_s[tid][1] = r_;
   }
+  __syncthreads();
+  const float mean[2] = {mr_s[0][0], mr_s[1][0]}, rstd[2] = {mr_s[0][1], mr_s[1][1]};
   float acc[2][C2T];
 #pragma unroll
   for (int net = 0; net < 2; ++net)
@@ -1145,7 +1340,134 @@ static int launch_pw(const GemmArgs& a, cudaStream_t st) {
   return launch_gemm<false>(a, st);
 }
 
+static bool use_tensor_cores_gconv() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNF_GC_TC");
+    v = (e && e[0] == '1') ? 1 : 0;   // default: FFMA gconv3 (8-wide groups are smem-read bound on tcgen05)
+  }
+  return v == 1;
+}
+
+// One dilation branch on tcgen05 (tc_gconv.cuh).  Returns 1 if the shape is not eligible.
+static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
+  const GconvBranch& br = g.br[bi];
+  const int G = br.gin, C = br.groups * br.gout;
+  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8 || G == 16)) return 1;
+  if (C % 16 || g.Cin % 4 || g.Cout % 4 || br.out_off % 4 || g.B > 65535) return 1;
+  const int halo = br.dil, SW = g.w + 2 * halo;
+  const int th_max = (GCT_MT * 128) / SW;
+  if (th_max < 1) return 1;
+  const int n_bands = (g.h + th_max - 1) / th_max;
+  const int TH = (g.h + n_bands - 1) / n_bands;
+  const int Q = (TH + 2 * halo) * SW;
+  int Qp = Q + 128 + 2 * halo + 1;
+  while ((Qp & 7) != 2) ++Qp;
+  const size_t smem = ((size_t)2 * 16 * Qp + 2 * 9 * 256) * sizeof(float);
+  if (smem > 200 * 1024) return 1;
+  GcTcArgs a = {};
+  a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
+  a.params = g.params; a.net_stride = g.net_stride; a.g_off = g.g_off; a.be_off = g.be_off;
+  a.stats_in = g.stats_in; a.stats_out = g.stats_out;
+  a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
+  a.TH = TH; a.n_bands = n_bands; a.Qp_max = Qp;
+  { const char* e = getenv("CNF_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.n_br = 1;
+  a.br[0] = br;
+  a.br[0].first_item = 0;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  dim3 grid((C / 16) * n_bands, g.B, 2);
+  gconv_tc_kernel<<<grid, GCT_NT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int G, int PX>
+static int launch_gconv3_t(const GconvArgs& a, int NT, size_t smem, cudaStream_t st) {
+  auto kern = gconv3_kernel<G, PX>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  dim3 grid(a.br[0].groups * a.tiles_y * a.tiles_x, a.B, 2);
+  kern<<<grid, NT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int G>
+static int launch_gconv3_g(const GconvArgs& a, int PX, int NT, size_t smem, cudaStream_t st) {
+  switch (PX) {
+    case 1: return launch_gconv3_t<G, 1>(a, NT, smem, st);
+    case 2: return launch_gconv3_t<G, 2>(a, NT, smem, st);
+    case 3: return launch_gconv3_t<G, 3>(a, NT, smem, st);
+    case 4: return launch_gconv3_t<G, 4>(a, NT, smem, st);
+    case 5: return launch_gconv3_t<G, 5>(a, NT, smem, st);
+    case 6: return launch_gconv3_t<G, 6>(a, NT, smem, st);
+    case 7: return launch_gconv3_t<G, 7>(a, NT, smem, st);
+    default: return launch_gconv3_t<G, 8>(a, NT, smem, st);
+  }
+}
+
+// One branch with gin == gout in {1,2,4,8}, ksize 3.  Returns 1 if not eligible.
+static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
+  const GconvBranch& br = g.br[bi];
+  const int G = br.gin;
+  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || g.B > 65535) return 1;
+  if ((G >= 4 && g.Cin % 4) || (G == 2 && g.Cin % 2)) return 1;
+  GconvArgs a = g;
+  a.n_br = 1;
+  a.br[0] = br;
+  a.br[0].first_item = 0;
+  a.TH = std::min(a.h, 32);
+  a.TW = std::min(a.w, 32);
+  a.tiles_y = (a.h + a.TH - 1) / a.TH;
+  a.tiles_x = (a.w + a.TW - 1) / a.TW;
+  const int TP = a.TH * a.TW;
+  int best_px = 8, best_nt = 128, best_waste = 1 << 30;
+  for (int px = 8; px >= 1; --px) {
+    int nt = ((TP + px - 1) / px + 31) / 32 * 32;
+    if (nt < 64) nt = 64;
+    if (nt > 256) continue;
+    const int waste = nt * px - TP;
+    if (waste < best_waste) { best_waste = waste; best_px = px; best_nt = nt; }
+  }
+  const int halo = br.dil;
+  const int GS = G + ((G % 8) == 0 ? 4 : 0);
+  const size_t in_sz = (((size_t)(a.TH + 2 * halo) * (a.TW + 2 * halo) * GS) + 3) & ~(size_t)3;
+  const size_t smem = (in_sz + ((9 * G * G + 3) & ~3) + G + 4) * sizeof(float);
+  if (smem > 227 * 1024) return 1;
+  switch (G) {
+    case 1: return launch_gconv3_g<1>(a, best_px, best_nt, smem, st);
+    case 2: return launch_gconv3_g<2>(a, best_px, best_nt, smem, st);
+    case 4: return launch_gconv3_g<4>(a, best_px, best_nt, smem, st);
+    default: return launch_gconv3_g<8>(a, best_px, best_nt, smem, st);
+  }
+}
+
+static int launch_gconv_ffma(GconvArgs a, cudaStream_t st);
+
 static int launch_gconv(GconvArgs a, cudaStream_t st) {
+  const bool tc = use_tensor_cores_gconv();
+  static int v2 = -1;
+  if (v2 < 0) { const char* e = getenv("CNF_GC_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
+  if (v2) return launch_gconv_ffma(a, st);
+  GconvArgs rest = a;
+  rest.n_br = 0;
+  for (int i = 0; i < a.n_br; ++i) {
+    const int rc = tc ? launch_gconv_tc_branch(a, i, st) : launch_gconv3_branch(a, i, st);
+    if (rc == 1) rest.br[rest.n_br++] = a.br[i];
+    else if (rc != 0) return rc;
+  }
+  if (rest.n_br) return launch_gconv_ffma(rest, st);
+  return 0;
+}
+
+static int launch_gconv_ffma(GconvArgs a, cudaStream_t st) {
   bool v2 = true;
   for (int i = 0; i < a.n_br; ++i) {
     const int g = a.br[i].gin;
