@@ -36,12 +36,15 @@ __device__ __forceinline__ long long comp_off(const FlowView& v, int m, int b, i
 // producing kernel.  Biased variance, eps 1e-3 (F:350-360 -> keras LayerNormalization defaults).
 __device__ __forceinline__ void ln_coeffs(const double* __restrict__ stats, long long idx, double n,
                                           float& mean, float& rstd) {
-  const double s = stats[2 * idx], ss = stats[2 * idx + 1];
-  const double m = s / n;
-  double var = ss / n - m * m;
-  var = var > 0.0 ? var : 0.0;
-  mean = (float)m;
-  rstd = (float)(1.0 / sqrt(var + CNF_LN_EPS));
+  // The sums are accumulated in fp64; the three scalar ops below run in fp32 (relative error ~1e-7,
+  // far inside the 1e-4 budget) because fp64 divide / sqrt sequences are slow on B200 and would
+  // serialise the prologue of every CTA.
+  const float inv_n = 1.0f / (float)n;
+  const float m = (float)stats[2 * idx] * inv_n;
+  float var = fmaf(-m, m, (float)stats[2 * idx + 1] * inv_n);
+  var = fmaxf(var, 0.f);
+  mean = m;
+  rstd = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

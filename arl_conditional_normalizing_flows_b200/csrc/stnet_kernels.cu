@@ -454,6 +454,7 @@ struct GconvArgs {
   double* stats_out;
   int B, h, w, Cin, Cout, ln, ks;
   int TH, TW, tiles_y, tiles_x;
+  int dbg;  // debug: bit0 skip global loads in staging, bit1 skip the FFMA taps
   int n_br;
   GconvBranch br[CNF_MAX_BRANCHES];
 };
@@ -924,18 +925,19 @@ __global__ void __launch_bounds__(GC2_NT) gconv2_kernel(const GconvArgs a) {
 //     staging walks rows and vector slots without integer divisions; the LayerNorm coefficients are
 //     computed once per CTA (fp64) and broadcast through shared memory.
 // ------------------------------------------------------------------------------------------
-template <int G, int PX>
-__global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
+template <int G, int PX, int S>
+__global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
   constexpr int V = G >= 4 ? 4 : G;        // staging vector width (floats)
   constexpr int VPP = G / V;               // vector slots per pixel
   constexpr int GS = G + ((G % 8) == 0 ? 4 : 0);
   using T = typename VecT<V>::T;
   extern __shared__ __align__(16) float smem[];
-  __shared__ float red[64];
-  __shared__ float mr[2];
-  const int tid = threadIdx.x, NT = blockDim.x;
+  __shared__ float red[32][2];
+  __shared__ float mr[S][2];
+  const int tid = threadIdx.x, NT = blockDim.x, NT1 = NT / S;   // NT1: threads per sample (multiple of 32)
   const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
-  const int b = blockIdx.y, net = blockIdx.z;
+  const int b0 = blockIdx.y * S, net = blockIdx.z;
+  const int ns = min(S, a.B - b0);
   const GconvBranch& br = a.br[0];
   const int tiles = a.tiles_y * a.tiles_x;
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
@@ -944,16 +946,17 @@ __global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
   const int d = br.dil;
   const int halo = d;                      // ksize 3
   const int SH = th + 2 * halo, SW = tw + 2 * halo;
-  float* in_s = smem;                                        // [SH*SW][GS]
-  float* w_s = in_s + ((SH * SW * GS + 3) & ~3);             // [9][G][G]
+  const int in_sz = (SH * SW * GS + 3) & ~3;
+  float* in_s = smem;                                        // [S][SH*SW][GS]
+  float* w_s = in_s + S * in_sz;                             // [9][G][G]
   float* b_s = w_s + ((9 * G * G + 3) & ~3);
 
   const float* P = a.params + (long long)net * a.net_stride;
-  if (tid == 0) {
+  if (tid < S) {
     float mean = 0.f, rstd = 1.f;
-    if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.Cin, mean, rstd);
-    mr[0] = mean;
-    mr[1] = rstd;
+    if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + b0 + tid, (double)a.h * a.w * (double)a.Cin, mean, rstd);
+    mr[tid][0] = mean;
+    mr[tid][1] = rstd;
   }
   {
     const float* wsrc = P + br.w_off + (long long)g * 9 * G * G;
@@ -961,9 +964,9 @@ __global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
     if (tid < G) b_s[tid] = P[br.b_off + g * G + tid];
   }
   __syncthreads();
-  const float mean = mr[0], rstd = mr[1];
   {
-    const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.Cin;
+    const long long sample_stride = (long long)a.h * a.w * a.Cin;
+    const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b0 * sample_stride;
     const float* gam = P + a.g_off;
     const float* bet = P + a.be_off;
     const int cin0 = g * G;
@@ -972,7 +975,7 @@ __global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
       const int gy = y0 - halo + sy;
       const bool rowok = gy >= 0 && gy < a.h;
       for (int sl0 = 0; sl0 < row_slots; sl0 += 64) {       // two slots per lane in flight
-        T xv[2], gv[2], bv[2];
+        T xv[2][S], gv[2], bv[2];
         bool ok[2];
         int sl[2];
 #pragma unroll
@@ -980,10 +983,12 @@ __global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
           sl[u] = sl0 + u * 32 + lane;
           const int sx = sl[u] / VPP, cv = sl[u] % VPP;
           const int gx = x0 - halo + sx;
-          ok[u] = rowok && sl[u] < row_slots && gx >= 0 && gx < a.w;
+          ok[u] = rowok && sl[u] < row_slots && gx >= 0 && gx < a.w && !(a.dbg & 1);
           if (ok[u]) {
             const long long e = ((long long)gy * a.w + gx) * a.Cin + cin0 + cv * V;
-            xv[u] = *reinterpret_cast<const T*>(src_s + e);
+#pragma unroll
+            for (int q = 0; q < S; ++q)
+              if (q < ns) xv[u][q] = *reinterpret_cast<const T*>(src_s + q * sample_stride + e);
             if (a.ln) {
               gv[u] = *reinterpret_cast<const T*>(gam + e);
               bv[u] = *reinterpret_cast<const T*>(bet + e);
@@ -993,114 +998,128 @@ __global__ void __launch_bounds__(256) gconv3_kernel(const GconvArgs a) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (sl[u] >= row_slots) continue;
-          float o[V];
-#pragma unroll
-          for (int i = 0; i < V; ++i) o[i] = 0.f;
-          if (ok[u]) {
-            const float* xf = reinterpret_cast<const float*>(&xv[u]);
-            const float* gf = reinterpret_cast<const float*>(&gv[u]);
-            const float* bf = reinterpret_cast<const float*>(&bv[u]);
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-              float v = lrelu(xf[i]);
-              if (a.ln) v = (v - mean) * rstd * gf[i] + bf[i];
-              o[i] = v;
-            }
-          }
           const int sx = sl[u] / VPP, cv = sl[u] % VPP;
-          *reinterpret_cast<T*>(in_s + (sy * SW + sx) * GS + cv * V) = *reinterpret_cast<const T*>(o);
+          const float* gf = reinterpret_cast<const float*>(&gv[u]);
+          const float* bf = reinterpret_cast<const float*>(&bv[u]);
+#pragma unroll
+          for (int q = 0; q < S; ++q) {
+            float o[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) o[i] = 0.f;
+            if (ok[u] && q < ns) {
+              const float* xf = reinterpret_cast<const float*>(&xv[u][q]);
+              const float mean = mr[q][0], rstd = mr[q][1];
+#pragma unroll
+              for (int i = 0; i < V; ++i) {
+                float v = lrelu(xf[i]);
+                if (a.ln) v = (v - mean) * rstd * gf[i] + bf[i];
+                o[i] = v;
+              }
+            }
+            *reinterpret_cast<T*>(in_s + q * in_sz + (sy * SW + sx) * GS + cv * V) = *reinterpret_cast<const T*>(o);
+          }
         }
       }
     }
   }
   __syncthreads();
 
+  const int sidx = tid / NT1, t1 = tid - sidx * NT1;   // warp-uniform: NT1 is a multiple of 32
   const int TP = th * tw;
-  float acc[PX][G];
-  int poff[PX];
-#pragma unroll
-  for (int j = 0; j < PX; ++j) {
-    const int p = min(tid + j * NT, TP - 1);
-    poff[j] = ((p / tw) * SW + (p % tw)) * GS;
-#pragma unroll
-    for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
-  }
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int ky = tap / 3, kx = tap - ky * 3;
-    const int toff = (ky * d * SW + kx * d) * GS;
-    const float* wt = w_s + tap * G * G;
-    float wv[G][G];
-#pragma unroll
-    for (int ci = 0; ci < G; ++ci) {
-      if (G % 4 == 0) {
-#pragma unroll
-        for (int c4 = 0; c4 < G; c4 += 4) {
-          const float4 t = ld4(wt + ci * G + c4);
-          wv[ci][c4] = t.x; wv[ci][c4 + 1] = t.y; wv[ci][c4 + 2] = t.z; wv[ci][c4 + 3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < G; ++c) wv[ci][c] = wt[ci * G + c];
-      }
-    }
+  float s1 = 0.f, s2 = 0.f;
+  if (sidx < ns) {
+    const float* in_q = in_s + sidx * in_sz;
+    float acc[PX][G];
+    int poff[PX];
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
-      const float* src = in_s + poff[j] + toff;
-      float xv[G];
-      if (G % 4 == 0) {
+      const int p = min(t1 + j * NT1, TP - 1);
+      poff[j] = ((p / tw) * SW + (p % tw)) * GS;
 #pragma unroll
-        for (int c4 = 0; c4 < G; c4 += 4) {
-          const float4 t = ld4(src + c4);
-          xv[c4] = t.x; xv[c4 + 1] = t.y; xv[c4 + 2] = t.z; xv[c4 + 3] = t.w;
-        }
-      } else if (G == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(src);
-        xv[0] = t.x; xv[G - 1] = t.y;
-      } else {
-        xv[0] = src[0];
-      }
-#pragma unroll
-      for (int ci = 0; ci < G; ++ci)
-#pragma unroll
-        for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[ci], wv[ci][co], acc[j][co]);
+      for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
     }
-  }
-
-  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.h * a.w * a.Cout;
-  const int cbase = br.out_off + g * G;
-  const bool vec = (G % 4 == 0) && (a.Cout % 4 == 0) && (cbase % 4 == 0);
-  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < ((a.dbg & 2) ? 0 : 9); ++tap) {
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int toff = (ky * d * SW + kx * d) * GS;
+      const float* wt = w_s + tap * G * G;
+      float xv[PX][G];
 #pragma unroll
-  for (int j = 0; j < PX; ++j) {
-    const int p = tid + j * NT;
-    if (p < TP) {
-      const int y = y0 + p / tw, x = x0 + p % tw;
-      float* dst = out_s + ((long long)y * a.w + x) * a.Cout + cbase;
-      float o[G];
+      for (int j = 0; j < PX; ++j) {
+        const float* src = in_q + poff[j] + toff;
+        if (G % 4 == 0) {
 #pragma unroll
-      for (int co = 0; co < G; ++co) {
-        o[co] = acc[j][co] + b_s[co];
-        const float l = lrelu(o[co]);
-        s1 += l;
-        s2 += l * l;
+          for (int c4 = 0; c4 < G; c4 += 4) {
+            const float4 t = ld4(src + c4);
+            xv[j][c4] = t.x; xv[j][c4 + 1] = t.y; xv[j][c4 + 2] = t.z; xv[j][c4 + 3] = t.w;
+          }
+        } else if (G == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(src);
+          xv[j][0] = t.x; xv[j][G - 1] = t.y;
+        } else {
+          xv[j][0] = src[0];
+        }
       }
-      if (vec) {
 #pragma unroll
-        for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
-      } else {
+      for (int ci = 0; ci < G; ++ci) {
+        float wv[G];
+        if (G % 4 == 0) {
 #pragma unroll
-        for (int co = 0; co < G; ++co) dst[co] = o[co];
+          for (int c4 = 0; c4 < G; c4 += 4) {
+            const float4 t = ld4(wt + ci * G + c4);
+            wv[c4] = t.x; wv[c4 + 1] = t.y; wv[c4 + 2] = t.z; wv[c4 + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < G; ++c) wv[c] = wt[ci * G + c];
+        }
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
+#pragma unroll
+          for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[j][ci], wv[co], acc[j][co]);
+      }
+    }
+
+    float* out_s = a.out + (long long)net * a.out_net_stride + (long long)(b0 + sidx) * a.h * a.w * a.Cout;
+    const int cbase = br.out_off + g * G;
+    const bool vec = (G % 4 == 0) && (a.Cout % 4 == 0) && (cbase % 4 == 0);
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      const int p = t1 + j * NT1;
+      if (p < TP) {
+        const int y = y0 + p / tw, x = x0 + p % tw;
+        float* dst = out_s + ((long long)y * a.w + x) * a.Cout + cbase;
+        float o[G];
+#pragma unroll
+        for (int co = 0; co < G; ++co) {
+          o[co] = acc[j][co] + b_s[co];
+          const float l = lrelu(o[co]);
+          s1 += l;
+          s2 += l * l;
+        }
+        if (vec) {
+#pragma unroll
+          for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
+        } else {
+#pragma unroll
+          for (int co = 0; co < G; ++co) dst[co] = o[co];
+        }
       }
     }
   }
   if (a.stats_out) {
-    double d1, d2;
-    block_sum2(s1, s2, red, d1, d2);
-    if (tid == 0) {
-      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
-      atomicAdd(so, d1);
-      atomicAdd(so + 1, d2);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      red[wid][0] = s1;
+      red[wid][1] = s2;
+    }
+    __syncthreads();
+    if (tid < 2 * S && (tid >> 1) < ns) {
+      const int q = tid >> 1, which = tid & 1, w1 = NT1 >> 5;
+      double t = 0.0;
+      for (int i = 0; i < w1; ++i) t += (double)red[q * w1 + i][which];
+      atomicAdd(a.stats_out + 2 * ((long long)net * a.B + b0 + q) + which, t);
     }
   }
 }
@@ -1316,6 +1335,50 @@ static int launch_pw_tc_t(const GemmArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+// persistent tcgen05 1x1 conv; returns 1 when the resident-W image does not fit shared memory
+template <int N>
+static int launch_pw_tc2_t(const GemmArgs& a, cudaStream_t st) {
+  const int nchunks = (a.K + 31) / 32;
+  const size_t smem = ((size_t)4 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
+  if (smem > 220 * 1024) return 1;
+  auto kern = pw_tc2_kernel<N>;
+  static size_t configured = 0;
+  static int n_sm = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    configured = smem;
+  }
+  const int tiles_p = (a.hw + 31) / 32, tiles_s = (a.B + 3) / 4;
+  const int grid = std::min(2 * tiles_p * tiles_s, n_sm & ~1);   // even: CTAs alternate between the two nets
+  kern<<<grid, 256, smem, st>>>(a, tiles_p, tiles_s);
+  return (int)cudaGetLastError();
+}
+
+// warp-specialised persistent tcgen05 1x1 conv; returns 1 when the resident-W image does not fit
+template <int N>
+static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
+  const int nchunks = (a.K + 31) / 32;
+  const size_t smem = ((size_t)4 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
+  if (smem > 220 * 1024) return 1;
+  auto kern = pw_tc3_kernel<N>;
+  static size_t configured = 0;
+  static int n_sm = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    configured = smem;
+  }
+  const int tiles_p = (a.hw + 31) / 32, tiles_s = (a.B + 3) / 4;
+  const int grid = std::min(2 * tiles_p * tiles_s, n_sm & ~1);
+  kern<<<grid, 416, smem, st>>>(a, tiles_p, tiles_s);
+  return (int)cudaGetLastError();
+}
+
 static bool use_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -1328,6 +1391,16 @@ static bool use_tensor_cores() {
 // 1x1 conv dispatcher: tcgen05 3xTF32 kernel when the shape fits one UMMA tile family (N in {16,32,64},
 // K % 8 == 0); otherwise the FFMA multi-sample kernel (K % 4 == 0) or the per-sample generic kernel.
 static int launch_pw(const GemmArgs& a, cudaStream_t st) {
+  static int v2 = -1;
+  if (v2 < 0) { const char* e = getenv("CNF_PW_V2"); v2 = e ? atoi(e) : 3; }   // 3: warp-specialised, 2: persistent, 0: per-tile CTAs
+  if (use_tensor_cores() && v2 == 3 && a.K % 8 == 0 && (a.N == 64 || a.N == 32 || a.N == 16)) {
+    const int rc = a.N == 64 ? launch_pw_tc3_t<64>(a, st) : a.N == 32 ? launch_pw_tc3_t<32>(a, st) : launch_pw_tc3_t<16>(a, st);
+    if (rc != 1) return rc;
+  }
+  if (use_tensor_cores() && v2 && a.K % 8 == 0 && (a.N == 64 || a.N == 32 || a.N == 16)) {
+    const int rc = a.N == 64 ? launch_pw_tc2_t<64>(a, st) : a.N == 32 ? launch_pw_tc2_t<32>(a, st) : launch_pw_tc2_t<16>(a, st);
+    if (rc != 1) return rc;
+  }
   if (use_tensor_cores() && a.K % 8 == 0 && (a.B + 3) / 4 <= 65535) {
     if (a.N == 64) return launch_pw_tc_t<64>(a, st);
     if (a.N == 32) return launch_pw_tc_t<32>(a, st);
@@ -1386,30 +1459,30 @@ static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-template <int G, int PX>
+template <int G, int PX, int S>
 static int launch_gconv3_t(const GconvArgs& a, int NT, size_t smem, cudaStream_t st) {
-  auto kern = gconv3_kernel<G, PX>;
+  auto kern = gconv3_kernel<G, PX, S>;
   static size_t configured = 0;
   if (smem > configured) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
     configured = std::max(smem, (size_t)48 * 1024);
   }
-  dim3 grid(a.br[0].groups * a.tiles_y * a.tiles_x, a.B, 2);
-  kern<<<grid, NT, smem, st>>>(a);
+  dim3 grid(a.br[0].groups * a.tiles_y * a.tiles_x, (a.B + S - 1) / S, 2);
+  kern<<<grid, NT * S, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
-template <int G>
+template <int G, int S>
 static int launch_gconv3_g(const GconvArgs& a, int PX, int NT, size_t smem, cudaStream_t st) {
   switch (PX) {
-    case 1: return launch_gconv3_t<G, 1>(a, NT, smem, st);
-    case 2: return launch_gconv3_t<G, 2>(a, NT, smem, st);
-    case 3: return launch_gconv3_t<G, 3>(a, NT, smem, st);
-    case 4: return launch_gconv3_t<G, 4>(a, NT, smem, st);
-    case 5: return launch_gconv3_t<G, 5>(a, NT, smem, st);
-    case 6: return launch_gconv3_t<G, 6>(a, NT, smem, st);
-    case 7: return launch_gconv3_t<G, 7>(a, NT, smem, st);
-    default: return launch_gconv3_t<G, 8>(a, NT, smem, st);
+    case 1: return launch_gconv3_t<G, 1, S>(a, NT, smem, st);
+    case 2: return launch_gconv3_t<G, 2, S>(a, NT, smem, st);
+    case 3: return launch_gconv3_t<G, 3, S>(a, NT, smem, st);
+    case 4: return launch_gconv3_t<G, 4, S>(a, NT, smem, st);
+    case 5: return launch_gconv3_t<G, 5, S>(a, NT, smem, st);
+    case 6: return launch_gconv3_t<G, 6, S>(a, NT, smem, st);
+    case 7: return launch_gconv3_t<G, 7, S>(a, NT, smem, st);
+    default: return launch_gconv3_t<G, 8, S>(a, NT, smem, st);
   }
 }
 
@@ -1423,6 +1496,7 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   a.n_br = 1;
   a.br[0] = br;
   a.br[0].first_item = 0;
+  { const char* e = getenv("CNF_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.TH = std::min(a.h, 32);
   a.TW = std::min(a.w, 32);
   a.tiles_y = (a.h + a.TH - 1) / a.TH;
@@ -1439,13 +1513,26 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   const int halo = br.dil;
   const int GS = G + ((G % 8) == 0 ? 4 : 0);
   const size_t in_sz = (((size_t)(a.TH + 2 * halo) * (a.TW + 2 * halo) * GS) + 3) & ~(size_t)3;
-  const size_t smem = (in_sz + ((9 * G * G + 3) & ~3) + G + 4) * sizeof(float);
+  const size_t tail = ((9 * G * G + 3) & ~3) + G + 4;
+  // two samples per CTA share gamma/beta loads and double the warps that walk the staging rows
+  static int s_env = -1;
+  if (s_env < 0) { const char* e = getenv("CNF_GC_S"); s_env = e ? atoi(e) : 2; }
+  const bool two = s_env >= 2 && a.B >= 2 && (2 * in_sz + tail) * sizeof(float) <= 110 * 1024 && 2 * best_nt <= 320;
+  const size_t smem = ((two ? 2 : 1) * in_sz + tail) * sizeof(float);
   if (smem > 227 * 1024) return 1;
+  if (two) {
+    switch (G) {
+      case 1: return launch_gconv3_g<1, 2>(a, best_px, best_nt, smem, st);
+      case 2: return launch_gconv3_g<2, 2>(a, best_px, best_nt, smem, st);
+      case 4: return launch_gconv3_g<4, 2>(a, best_px, best_nt, smem, st);
+      default: return launch_gconv3_g<8, 2>(a, best_px, best_nt, smem, st);
+    }
+  }
   switch (G) {
-    case 1: return launch_gconv3_g<1>(a, best_px, best_nt, smem, st);
-    case 2: return launch_gconv3_g<2>(a, best_px, best_nt, smem, st);
-    case 4: return launch_gconv3_g<4>(a, best_px, best_nt, smem, st);
-    default: return launch_gconv3_g<8>(a, best_px, best_nt, smem, st);
+    case 1: return launch_gconv3_g<1, 1>(a, best_px, best_nt, smem, st);
+    case 2: return launch_gconv3_g<2, 1>(a, best_px, best_nt, smem, st);
+    case 4: return launch_gconv3_g<4, 1>(a, best_px, best_nt, smem, st);
+    default: return launch_gconv3_g<8, 1>(a, best_px, best_nt, smem, st);
   }
 }
 

@@ -318,4 +318,526 @@ __global__ void __launch_bounds__(256, 2) pw_tc_kernel(const GemmArgs a) {
   if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks a list of 128-row tiles.  Raw activations / gamma / beta are
+// streamed with cp.async (16 B per thread, thread-private slots) into a DEPTH-deep shared-memory ring
+// that runs ahead across chunk AND tile boundaries, so ~70 KB of loads stay in flight per SM while the
+// warps do LReLU + LayerNorm + hi/lo split, the tensor core runs, and the epilogue stores.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int N>
+__global__ void __launch_bounds__(256, 1) pw_tc2_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
+  constexpr int NT = 256;
+  constexpr int S = 4, PT = 32, M = 128;
+  constexpr int KC = 32;
+  constexpr int DEPTH = 3;                     // cp.async ring depth (chunks in flight)
+  constexpr int A_ST = M * KC, B_ST = N * KC;
+  constexpr int RAW = 6 * NT * 4;              // floats per ring entry: 4 x-slots + gamma + beta per thread
+  constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
+  constexpr int NC = N / 2;
+  extern __shared__ __align__(128) float tc2_smem[];
+  const int nchunks = (a.K + KC - 1) / KC;
+  float* opsA = tc2_smem;                      // [2 stages][hi, lo][A_ST]
+  float* raw = opsA + 4 * A_ST;                // [DEPTH][6][NT] float4
+  float* Bres = raw + DEPTH * RAW;             // [nchunks][hi, lo][B_ST]  (resident for the whole kernel)
+  __shared__ __align__(8) uint64_t bar_free[2];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float mr[2][S][2];                // (rstd, -mean*rstd) per sample, double-buffered by tile parity
+  __shared__ float red[NT / 32][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // one net per CTA (even CTAs: net A, odd: net b) so that W stays resident
+  const int net = blockIdx.x & 1;
+  const int cta = blockIdx.x >> 1, ncta = (gridDim.x + 1 - net) >> 1;
+  const int ntiles = tiles_p * tiles_s;        // tiles of one net
+  const int my_tiles = cta < ntiles ? (ntiles - 1 - cta) / ncta + 1 : 0;
+  const int total = my_tiles * nchunks;
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* src_n = a.in + (long long)net * a.in_net_stride;
+  const float* gam = P + a.g_off;
+  const float* bet = P + a.be_off;
+
+  if (tid == 0) {
+    mbar_init(&bar_free[0], 1);
+    mbar_init(&bar_free[1], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+
+  // staging roles: row ar of an 8-row group, K quad akq, pixel ap (see pw_tc_kernel)
+  const int ar = lane & 7, akq = (lane >> 3) + 4 * (wid >> 2);
+  const int ap = 8 * (wid & 3) + ar;
+
+  // prefetch cursor (tile, chunk) of the next chunk to issue; advanced without divisions
+  int pf_tl = 0, pf_c = 0, pf_r = cta;
+  int pf_s0 = (pf_r / tiles_p) * S, pf_p0 = (pf_r % tiles_p) * PT;
+  int pf_slot = 0;
+  auto issue = [&]() {
+    if (pf_tl < my_tiles) {
+      const int k0 = pf_c * KC, kc = min(KC, a.K - k0);
+      const int gp = pf_p0 + ap;
+      if (akq * 4 < kc && gp < a.hw) {
+        float* dst = raw + pf_slot * RAW;
+        const long long e = (long long)gp * a.K + k0 + akq * 4;
+        const int ns = min(S, a.B - pf_s0);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          if (s < ns) cp_async16_cg(dst + (s * NT + tid) * 4, src_n + ((long long)(pf_s0 + s) * a.hw) * a.K + e);
+        if (a.ln) {
+          cp_async16_ca(dst + (4 * NT + tid) * 4, gam + e);
+          cp_async16_ca(dst + (5 * NT + tid) * 4, bet + e);
+        }
+      }
+      if (++pf_c == nchunks) {
+        pf_c = 0;
+        ++pf_tl;
+        pf_r += ncta;
+        pf_s0 = (pf_r / tiles_p) * S;
+        pf_p0 = (pf_r % tiles_p) * PT;
+      }
+    }
+    pf_slot = pf_slot + 1 == DEPTH ? 0 : pf_slot + 1;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < DEPTH; ++i) issue();
+
+  // resident B operand: W[k][n] -> K-major hi/lo images per chunk
+  {
+    const float* Wg = P + a.w_off;
+    const int bnr = lane & 7, bkr = lane >> 3;
+    for (int it = wid; it < nchunks * (N / 8) * (KC / 4); it += NT / 32) {
+      const int c = it / ((N / 8) * (KC / 4)), r = it % ((N / 8) * (KC / 4));
+      const int ng = r % (N / 8), kq = r / (N / 8);
+      const int n = ng * 8 + bnr, k = c * KC + kq * 4 + bkr;
+      float w = 0.f;
+      if (k < a.K) w = Wg[(long long)k * a.N + n];
+      float h, l;
+      tf32_split(w, h, l);
+      const int off = c * 2 * B_ST + 4 * (bnr + 8 * kq + (KC / 4) * 8 * ng) + bkr;
+      Bres[off] = h;
+      Bres[off + B_ST] = l;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  int gi = 0, slot = 0;
+  int r = cta;
+  for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
+    const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+    const int ns = min(S, a.B - s0);
+    if (tid < S) {
+      float mean = 0.f, rstd = 1.f;
+      if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
+      mr[tl & 1][tid][0] = rstd;
+      mr[tl & 1][tid][1] = -mean * rstd;
+    }
+    __syncthreads();
+    const bool pv = (p0 + ap) < a.hw;
+    const int quarter = wid & 3, half = wid >> 2;
+    const int m = quarter * 32 + lane;
+    const int es = m / PT, egp = p0 + (m % PT);
+    const bool erow = egp < a.hw && es < ns;
+    const long long row = ((long long)(s0 + es) * a.hw + egp) * a.N + half * NC;
+    float4 resv[NC / 4];
+
+    for (int c = 0; c < nchunks; ++c, ++gi) {
+      const int stage = gi & 1;
+      float* As_hi = opsA + stage * 2 * A_ST;
+      float* As_lo = As_hi + A_ST;
+      const int kc = min(KC, a.K - c * KC);
+      if (c == nchunks - 1 && a.res && erow) {   // residual rows: in flight during the last chunk
+        const float* res_r = a.res + (long long)net * a.out_net_stride + row;
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) resv[j] = ld4(res_r + 4 * j);
+      }
+      cp_async_wait<DEPTH - 1>();               // this thread's copies of chunk gi have landed
+      if (gi >= 2) mbar_wait(&bar_free[stage], ((gi >> 1) - 1) & 1);
+      if (akq * 4 < kc) {
+        const float* src = raw + slot * RAW;
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pv && a.ln) {
+          g = ld4(src + (4 * NT + tid) * 4);
+          be = ld4(src + (5 * NT + tid) * 4);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (pv && s < ns) {
+            const float4 xv = ld4(src + (s * NT + tid) * 4);
+            const float sc = mr[tl & 1][s][0], sh = mr[tl & 1][s][1];
+            v[0] = fmaxf(xv.x, CNF_LRELU_SLOPE * xv.x);
+            v[1] = fmaxf(xv.y, CNF_LRELU_SLOPE * xv.y);
+            v[2] = fmaxf(xv.z, CNF_LRELU_SLOPE * xv.z);
+            v[3] = fmaxf(xv.w, CNF_LRELU_SLOPE * xv.w);
+            if (a.ln) {   // ((v - mean) * rstd) * gamma + beta with (v - mean) * rstd = fma(v, rstd, -mean * rstd)
+              v[0] = fmaf(fmaf(v[0], sc, sh), g.x, be.x);
+              v[1] = fmaf(fmaf(v[1], sc, sh), g.y, be.y);
+              v[2] = fmaf(fmaf(v[2], sc, sh), g.z, be.z);
+              v[3] = fmaf(fmaf(v[3], sc, sh), g.w, be.w);
+            }
+          }
+          float h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tf32_split(v[i], h[i], l[i]);
+          const int unit = ar + 8 * akq + 64 * ((s * PT + ap) >> 3);
+          st4(As_hi + 4 * unit, make_float4(h[0], h[1], h[2], h[3]));
+          st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
+        }
+      }
+      issue();                                  // refill the ring entry this thread has just consumed
+      slot = slot + 1 == DEPTH ? 0 : slot + 1;
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_tf32(N);
+        const uint32_t a_hi = smem_u32(As_hi), a_lo = smem_u32(As_lo);
+        const uint32_t b_hi = smem_u32(Bres + c * 2 * B_ST), b_lo = b_hi + B_ST * 4;
+        constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
+        for (int ks = 0; ks < kc / 8; ++ks) {
+          const uint32_t adv = ks * 2 * LBO;
+          const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
+          const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
+          umma_tf32(tmem_d, dah, dbh, idesc, (c | ks) != 0);
+          umma_tf32(tmem_d, dal, dbh, idesc, 1);
+          umma_tf32(tmem_d, dah, dbl, idesc, 1);
+        }
+        umma_commit(&bar_free[stage]);
+        if (c == nchunks - 1) umma_commit(&bar_done);
+      }
+    }
+
+    // ---- epilogue of this tile
+    mbar_wait(&bar_done, tl & 1);
+    tc_fence_after();
+    float v[NC];
+    tmem_ld<NC>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC), v);
+    float s1 = 0.f, s2 = 0.f;
+    if (erow) {
+      float* out_r = a.out + (long long)net * a.out_net_stride + row;
+      const float* bias = P + a.b_off + half * NC;
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 bb = ld4(bias + j);
+        float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
+        if (a.res) {
+          const float4 rr = resv[j / 4];
+          o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
+        }
+        st4(out_r + j, make_float4(o0, o1, o2, o3));
+        float l;
+        l = fmaxf(o0, CNF_LRELU_SLOPE * o0); s1 += l; s2 = fmaf(l, l, s2);
+        l = fmaxf(o1, CNF_LRELU_SLOPE * o1); s1 += l; s2 = fmaf(l, l, s2);
+        l = fmaxf(o2, CNF_LRELU_SLOPE * o2); s1 += l; s2 = fmaf(l, l, s2);
+        l = fmaxf(o3, CNF_LRELU_SLOPE * o3); s1 += l; s2 = fmaf(l, l, s2);
+      }
+    }
+    if (a.stats_out) {
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        red[wid][0] = s1;
+        red[wid][1] = s2;
+      }
+    }
+    tc_fence_before();   // order this tile's tcgen05.ld before the next tile's first MMA (issued after a barrier)
+    __syncthreads();
+    if (a.stats_out && tid < 2 * S && (tid >> 1) < ns) {
+      const int s = tid >> 1, which = tid & 1;
+      const double t = (double)red[s][which] + (double)red[s + 4][which];
+      atomicAdd(a.stats_out + 2 * ((long long)net * a.B + s0 + s) + which, t);
+    }
+  }
+  cp_async_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised persistent variant (the one the flow uses):
+//   warps 0-7   transform: cp.async ring -> LReLU + LayerNorm + hi/lo split -> UMMA operand stages
+//   warp  8     MMA issuer (one lane): waits full[stage], issues 3 tcgen05.mma per K-step, commits free[stage]
+//   warps 9-12  epilogue: wait tmem_full[buf], tcgen05.ld, + bias (+ residual), store, LN statistics,
+//               arrive tmem_empty[buf]   (epilogue warp w owns TMEM lanes 32*(w%4).. = sample w%4)
+// The accumulator is double-buffered in TMEM (2 x N columns), so the epilogue of tile t overlaps the
+// transform + MMA of tile t+1, and nothing but the ring depth bounds the loads in flight.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
+  constexpr int NTT = 256;                     // transform threads
+  constexpr int S = 4, PT = 32, M = 128;
+  constexpr int KC = 32;
+  constexpr int DEPTH = 3;
+  constexpr int A_ST = M * KC, B_ST = N * KC;
+  constexpr int RAW = 6 * NTT * 4;
+  constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  extern __shared__ __align__(128) float tc3_smem[];
+  const int nchunks = (a.K + KC - 1) / KC;
+  float* opsA = tc3_smem;                      // [2 stages][hi, lo][A_ST]
+  float* raw = opsA + 4 * A_ST;                // [DEPTH][6][NTT] float4
+  float* Bres = raw + DEPTH * RAW;             // [nchunks][hi, lo][B_ST]
+  __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float mr[2][S][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int net = blockIdx.x & 1;
+  const int cta = blockIdx.x >> 1, ncta = (gridDim.x + 1 - net) >> 1;
+  const int ntiles = tiles_p * tiles_s;
+  const int my_tiles = cta < ntiles ? (ntiles - 1 - cta) / ncta + 1 : 0;
+
+  const float* P = a.params + (long long)net * a.net_stride;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_full[i], NTT);
+      mbar_init(&bar_free[i], 1);
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == 8) tmem_alloc(&tmem_slot, TMEM_COLS);
+  // resident B operand (all threads help)
+  {
+    const float* Wg = P + a.w_off;
+    const int bnr = lane & 7, bkr = lane >> 3;
+    for (int it = wid; it < nchunks * (N / 8) * (KC / 4); it += 13) {
+      const int c = it / ((N / 8) * (KC / 4)), r = it % ((N / 8) * (KC / 4));
+      const int ng = r % (N / 8), kq = r / (N / 8);
+      const int n = ng * 8 + bnr, k = c * KC + kq * 4 + bkr;
+      float w = 0.f;
+      if (k < a.K) w = Wg[(long long)k * a.N + n];
+      float h, l;
+      tf32_split(w, h, l);
+      const int off = c * 2 * B_ST + 4 * (bnr + 8 * kq + (KC / 4) * 8 * ng) + bkr;
+      Bres[off] = h;
+      Bres[off + B_ST] = l;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (wid < 8) {
+    // =============================== transform warps ===============================
+    const float* src_n = a.in + (long long)net * a.in_net_stride;
+    const float* gam = P + a.g_off;
+    const float* bet = P + a.be_off;
+    const int ar = lane & 7, akq = (lane >> 3) + 4 * (wid >> 2);
+    const int ap = 8 * (wid & 3) + ar;
+    int pf_tl = 0, pf_c = 0, pf_r = cta;
+    int pf_s0 = (pf_r / tiles_p) * S, pf_p0 = (pf_r % tiles_p) * PT;
+    int pf_slot = 0;
+    auto issue = [&]() {
+      if (pf_tl < my_tiles) {
+        const int k0 = pf_c * KC, kc = min(KC, a.K - k0);
+        const int gp = pf_p0 + ap;
+        if (akq * 4 < kc && gp < a.hw) {
+          float* dst = raw + pf_slot * RAW;
+          const long long e = (long long)gp * a.K + k0 + akq * 4;
+          const int ns = min(S, a.B - pf_s0);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            if (s < ns) cp_async16_cg(dst + (s * NTT + tid) * 4, src_n + ((long long)(pf_s0 + s) * a.hw) * a.K + e);
+          if (a.ln) {
+            cp_async16_ca(dst + (4 * NTT + tid) * 4, gam + e);
+            cp_async16_ca(dst + (5 * NTT + tid) * 4, bet + e);
+          }
+        }
+        if (++pf_c == nchunks) {
+          pf_c = 0;
+          ++pf_tl;
+          pf_r += ncta;
+          pf_s0 = (pf_r / tiles_p) * S;
+          pf_p0 = (pf_r % tiles_p) * PT;
+        }
+      }
+      pf_slot = pf_slot + 1 == DEPTH ? 0 : pf_slot + 1;
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < DEPTH; ++i) issue();
+
+    int gi = 0, slot = 0, r = cta;
+    for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
+      const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+      const int ns = min(S, a.B - s0);
+      if (tid < S) {
+        float mean = 0.f, rstd = 1.f;
+        if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
+        mr[tl & 1][tid][0] = rstd;
+        mr[tl & 1][tid][1] = -mean * rstd;
+      }
+      named_bar_sync(1, NTT);
+      const bool pv = (p0 + ap) < a.hw;
+      for (int c = 0; c < nchunks; ++c, ++gi) {
+        const int stage = gi & 1;
+        float* As_hi = opsA + stage * 2 * A_ST;
+        float* As_lo = As_hi + A_ST;
+        const int kc = min(KC, a.K - c * KC);
+        cp_async_wait<DEPTH - 1>();
+        if (gi >= 2) mbar_wait(&bar_free[stage], ((gi >> 1) - 1) & 1);
+        if (akq * 4 < kc) {
+          const float* src = raw + slot * RAW;
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pv && a.ln) {
+            g = ld4(src + (4 * NTT + tid) * 4);
+            be = ld4(src + (5 * NTT + tid) * 4);
+          }
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pv && s < ns) {
+              const float4 xv = ld4(src + (s * NTT + tid) * 4);
+              const float sc = mr[tl & 1][s][0], sh = mr[tl & 1][s][1];
+              v[0] = fmaxf(xv.x, CNF_LRELU_SLOPE * xv.x);
+              v[1] = fmaxf(xv.y, CNF_LRELU_SLOPE * xv.y);
+              v[2] = fmaxf(xv.z, CNF_LRELU_SLOPE * xv.z);
+              v[3] = fmaxf(xv.w, CNF_LRELU_SLOPE * xv.w);
+              if (a.ln) {
+                v[0] = fmaf(fmaf(v[0], sc, sh), g.x, be.x);
+                v[1] = fmaf(fmaf(v[1], sc, sh), g.y, be.y);
+                v[2] = fmaf(fmaf(v[2], sc, sh), g.z, be.z);
+                v[3] = fmaf(fmaf(v[3], sc, sh), g.w, be.w);
+              }
+            }
+            float h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tf32_split(v[i], h[i], l[i]);
+            const int unit = ar + 8 * akq + 64 * ((s * PT + ap) >> 3);
+            st4(As_hi + 4 * unit, make_float4(h[0], h[1], h[2], h[3]));
+            st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
+          }
+        }
+        issue();
+        slot = slot + 1 == DEPTH ? 0 : slot + 1;
+        fence_async_smem();          // my generic-proxy writes -> async proxy, then signal the MMA warp
+        mbar_arrive(&bar_full[stage]);
+      }
+    }
+    cp_async_wait<0>();
+  } else if (wid == 8) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(N);
+      constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
+      const uint32_t a_base = smem_u32(opsA), b_base = smem_u32(Bres);
+      int gi = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int buf = tl & 1;
+        if (tl >= 2) mbar_wait(&bar_tempty[buf], ((tl >> 1) - 1) & 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_addr = tmem_d + buf * N;
+        for (int c = 0; c < nchunks; ++c, ++gi) {
+          const int stage = gi & 1;
+          const int kc = min(KC, a.K - c * KC);
+          mbar_wait(&bar_full[stage], (gi >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = a_base + stage * 2 * A_ST * 4, a_lo = a_hi + A_ST * 4;
+          const uint32_t b_hi = b_base + c * 2 * B_ST * 4, b_lo = b_hi + B_ST * 4;
+          for (int ks = 0; ks < kc / 8; ++ks) {
+            const uint32_t adv = ks * 2 * LBO;
+            const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
+            const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
+            umma_tf32(d_addr, dah, dbh, idesc, (c | ks) != 0);
+            umma_tf32(d_addr, dal, dbh, idesc, 1);
+            umma_tf32(d_addr, dah, dbl, idesc, 1);
+          }
+          umma_commit(&bar_free[stage]);
+          if (c == nchunks - 1) umma_commit(&bar_tfull[buf]);
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int quarter = wid & 3;                 // TMEM lane quarter this warp may access == sample index (PT == 32)
+    int r = cta;
+    const float* bias = P + a.b_off;
+    for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
+      const int buf = tl & 1;
+      const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+      const int ns = min(S, a.B - s0);
+      const int egp = p0 + lane;
+      const bool erow = egp < a.hw && quarter < ns;
+      const long long row = ((long long)(s0 + quarter) * a.hw + egp) * a.N;
+      float* out_r = a.out + (long long)net * a.out_net_stride + row;
+      const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
+      mbar_wait(&bar_tfull[buf], (tl >> 1) & 1);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < N; cb += 16) {
+        float v[16];
+        float4 rr[4];
+        if (res_r && erow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = ld4(res_r + cb + 4 * j);
+        }
+        tmem_ld<16>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + cb), v);
+        if (erow) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 bb = ld4(bias + cb + j);
+            float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
+            if (res_r) {
+              o0 += rr[j / 4].x; o1 += rr[j / 4].y; o2 += rr[j / 4].z; o3 += rr[j / 4].w;
+            }
+            st4(out_r + cb + j, make_float4(o0, o1, o2, o3));
+            float l;
+            l = fmaxf(o0, CNF_LRELU_SLOPE * o0); s1 += l; s2 = fmaf(l, l, s2);
+            l = fmaxf(o1, CNF_LRELU_SLOPE * o1); s1 += l; s2 = fmaf(l, l, s2);
+            l = fmaxf(o2, CNF_LRELU_SLOPE * o2); s1 += l; s2 = fmaf(l, l, s2);
+            l = fmaxf(o3, CNF_LRELU_SLOPE * o3); s1 += l; s2 = fmaf(l, l, s2);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_tempty[buf]);             // accumulator buffer may be overwritten
+      if (a.stats_out) {
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0 && quarter < ns) {
+          double* so = a.stats_out + 2 * ((long long)net * a.B + s0 + quarter);
+          atomicAdd(so, (double)s1);
+          atomicAdd(so + 1, (double)s2);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 8) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
 }  // namespace cnf
