@@ -282,6 +282,18 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1c, const D
   return cuda_rc(run_coupling(c, P.p, v, MASK_DENSE, v, (int)B, HEAD_EMIT, nullptr, TA.p, TB.p, W.p, stream), "s/t networks");
 }
 
+int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace, int64_t batch,
+                      int which, void* stream) {
+  if (!c) return fail(CNF_ERR_ARG, "null coupling layer");
+  Ten P, W;
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  if (batch < 1 || which < 0 || which > 1) return fail(CNF_ERR_ARG, "batch >= 1 and which in {0,1} required");
+  if (P.numel < 2 * c->net_stride) return fail(CNF_ERR_SHAPE, "params too small");
+  if (W.bytes < cnf_coupling_workspace_bytes(c, batch)) return fail(CNF_ERR_WORKSPACE, "workspace too small");
+  return cuda_rc(run_pw_only(c, P.p, (int)batch, which, W.p, stream), "1x1 conv");
+}
+
 int cnf_coupling_law(const DLManagedTensor* u, const DLManagedTensor* s, const DLManagedTensor* t, int which_mask,
                      int inverse, DLManagedTensor* v, DLManagedTensor* logdet, void* stream) {
   Ten U, S, T, V, L;

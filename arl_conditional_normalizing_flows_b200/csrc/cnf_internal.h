@@ -101,6 +101,7 @@ CouplingWorkspace carve_ws(const cnf_coupling* c, int64_t B, void* ws);
 int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask,
                  FlowView out_view, int B, int mode, double* logdet_acc, float* outA, float* outB,
                  void* ws, void* stream);
+int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, void* ws, void* stream);
 int launch_copy(const float* src, float* dst, int64_t n, void* stream);
 int launch_logdet_finalize(const double* acc, float* out, int B, void* stream);
 int launch_prior_loss(const float* zy, const float* xy, const float* logdet, int B, int64_t HW, int D,

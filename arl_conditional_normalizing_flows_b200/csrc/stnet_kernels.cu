@@ -1187,16 +1187,64 @@ __global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
       const float* gam = P + a.g_off;
       const float* bet = P + a.be_off;
       float* dst = in_s + net * in_sz;
-      for (int idx = tid; idx < SH * SW * CC; idx += HD_NT) {
-        const int ci = idx % CC, pix = idx / CC;
-        const int gy = y0 - pad + pix / SW, gx = pix % SW - pad;
-        float v = 0.f;
-        if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w && c0 + ci < a.nk) {
-          const long long e = ((long long)gy * a.w + gx) * a.nk + c0 + ci;
-          v = lrelu(src_s[e]);
-          if (a.ln) v = (v - mean[net]) * rstd[net] * gam[e] + bet[e];
+      if ((a.nk & 3) == 0) {
+        // 128-bit slots, rows walked by warps, two slots per lane in flight (no integer divisions by runtime values
+        // other than the quad count, 6 independent loads per lane per step)
+        const int lane = tid & 31, wid = tid >> 5;
+        const int qpp = CC >> 2;                  // quads per pixel in this chunk
+        const int row_slots = SW * qpp;
+        for (int sy = wid; sy < SH; sy += HD_NT / 32) {
+          const int gy = y0 - pad + sy;
+          const bool rowok = gy >= 0 && gy < a.h;
+          for (int sl0 = 0; sl0 < row_slots; sl0 += 64) {
+            float4 xv[2], gv[2], bv[2];
+            bool ok[2];
+            int sl[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              sl[u] = sl0 + u * 32 + lane;
+              const int sx = sl[u] / qpp, cq = sl[u] - sx * qpp;
+              const int gx = sx - pad;
+              ok[u] = rowok && sl[u] < row_slots && gx >= 0 && gx < a.w && c0 + 4 * cq < a.nk;
+              if (ok[u]) {
+                const long long e = ((long long)gy * a.w + gx) * a.nk + c0 + 4 * cq;
+                xv[u] = ld4(src_s + e);
+                if (a.ln) {
+                  gv[u] = ld4(gam + e);
+                  bv[u] = ld4(bet + e);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (sl[u] >= row_slots) continue;
+              const int sx = sl[u] / qpp, cq = sl[u] - sx * qpp;
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok[u]) {
+                o.x = lrelu(xv[u].x); o.y = lrelu(xv[u].y); o.z = lrelu(xv[u].z); o.w = lrelu(xv[u].w);
+                if (a.ln) {
+                  o.x = (o.x - mean[net]) * rstd[net] * gv[u].x + bv[u].x;
+                  o.y = (o.y - mean[net]) * rstd[net] * gv[u].y + bv[u].y;
+                  o.z = (o.z - mean[net]) * rstd[net] * gv[u].z + bv[u].z;
+                  o.w = (o.w - mean[net]) * rstd[net] * gv[u].w + bv[u].w;
+                }
+              }
+              st4(dst + (sy * SW + sx) * CS + 4 * cq, o);
+            }
+          }
         }
-        dst[pix * CS + ci] = v;
+      } else {
+        for (int idx = tid; idx < SH * SW * CC; idx += HD_NT) {
+          const int ci = idx % CC, pix = idx / CC;
+          const int gy = y0 - pad + pix / SW, gx = pix % SW - pad;
+          float v = 0.f;
+          if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w && c0 + ci < a.nk) {
+            const long long e = ((long long)gy * a.w + gx) * a.nk + c0 + ci;
+            v = lrelu(src_s[e]);
+            if (a.ln) v = (v - mean[net]) * rstd[net] * gam[e] + bet[e];
+          }
+          dst[pix * CS + ci] = v;
+        }
       }
       // weights: w_s[net][tap][co][ci] = W[tap][c0+ci][co]   (HWIO: ((tap*nk)+cin)*c2 + co)
       const float* Wg = P + a.w_off;
@@ -1702,6 +1750,35 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
     CU_TRY((cudaError_t)launch_head(a, st));
   }
   return 0;
+}
+
+// Measurement hook (cnf_debug_pw_conv): one 1x1-conv launch of residual block 0 on the current workspace.
+int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->R < 1) return (int)cudaErrorInvalidValue;
+  CouplingWorkspace W = carve_ws(c, B, ws);
+  const int hw = c->hw(), nk = c->nk, cat = c->cat;
+  const long long slot = 2LL * B * 2;
+  const ResBlockLayout& L = c->rb[0];
+  GemmArgs a = {};
+  a.params = params; a.net_stride = c->net_stride;
+  a.B = B; a.hw = hw; a.N = nk; a.ln = c->ln;
+  a.out_net_stride = (long long)B * hw * nk;
+  // the statistics outputs go to the spare slot (index n_ln) so that repeated launches do not disturb the layer
+  double* spare = c->n_ln() ? W.stats + slot * c->n_ln() : nullptr;
+  if (spare) CU_TRY(cudaMemsetAsync(spare, 0, sizeof(double) * slot, st));
+  if (which == 0) {
+    a.in = W.X; a.in_net_stride = (long long)B * hw * nk; a.K = nk;
+    a.w_off = L.pw1_w; a.b_off = L.pw1_b; a.g_off = L.ln1_g; a.be_off = L.ln1_b;
+    a.stats_in = c->n_ln() ? W.stats : nullptr; a.stats_out = spare;
+    a.out = W.Y1;
+  } else {
+    a.in = W.Y2; a.in_net_stride = (long long)B * hw * cat; a.K = cat;
+    a.w_off = L.pw2_w; a.b_off = L.pw2_b; a.g_off = L.ln3_g; a.be_off = L.ln3_b;
+    a.stats_in = c->n_ln() ? W.stats + slot * 2 : nullptr; a.stats_out = spare;
+    a.out = W.Y1; a.res = W.X;     // out-of-place so that X is not accumulated into
+  }
+  return launch_pw(a, st);
 }
 
 }  // namespace cnf

@@ -607,6 +607,7 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
   __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float mr[2][S][2];
+  __shared__ __align__(16) float bias_s[N];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int net = blockIdx.x & 1;
@@ -626,6 +627,7 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (wid == 8) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid < N) bias_s[tid] = P[a.b_off + tid];
   // resident B operand (all threads help)
   {
     const float* Wg = P + a.w_off;
@@ -690,16 +692,40 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
     for (int i = 0; i < DEPTH; ++i) issue();
 
     int gi = 0, slot = 0, r = cta;
+    // LayerNorm coefficients: the (sum, sumsq) pair of tile tl+1 is loaded while tile tl is transformed, so the
+    // L2 round trip never sits between a tile's barrier and its first chunk
+    const float inv_n = 1.0f / ((float)a.hw * (float)a.K);
+    double st_s = 0.0, st_q = 0.0;
+    auto load_stats = [&](int rr) {
+      const int s0n = (rr / tiles_p) * S;
+      if (a.ln && tid < S && s0n + tid < a.B) {
+        const double* sp = a.stats_in + 2 * ((long long)net * a.B + s0n + tid);
+        st_s = sp[0];
+        st_q = sp[1];
+      }
+    };
+    auto store_coeffs = [&](int par) {
+      if (tid < S) {
+        float sc = 1.f, shf = 0.f;
+        if (a.ln) {
+          const float m_ = (float)st_s * inv_n;
+          const float var = fmaxf(fmaf(-m_, m_, (float)st_q * inv_n), 0.f);
+          sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
+          shf = -m_ * sc;
+        }
+        mr[par][tid][0] = sc;
+        mr[par][tid][1] = shf;
+      }
+    };
+    if (my_tiles > 0) {
+      load_stats(cta);
+      store_coeffs(0);
+    }
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
       const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
       const int ns = min(S, a.B - s0);
-      if (tid < S) {
-        float mean = 0.f, rstd = 1.f;
-        if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
-        mr[tl & 1][tid][0] = rstd;
-        mr[tl & 1][tid][1] = -mean * rstd;
-      }
-      named_bar_sync(1, NTT);
+      named_bar_sync(1, NTT);                      // publishes mr[tl & 1] (written before this barrier)
+      if (tl + 1 < my_tiles) load_stats(r + ncta);  // in flight during this tile
       const bool pv = (p0 + ap) < a.hw;
       for (int c = 0; c < nchunks; ++c, ++gi) {
         const int stage = gi & 1;
@@ -745,6 +771,7 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
         fence_async_smem();          // my generic-proxy writes -> async proxy, then signal the MMA warp
         mbar_arrive(&bar_full[stage]);
       }
+      if (tl + 1 < my_tiles) store_coeffs((tl + 1) & 1);   // other parity: nobody reads it during tile tl
     }
     cp_async_wait<0>();
   } else if (wid == 8) {
@@ -783,7 +810,6 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
     // =============================== epilogue warps ===============================
     const int quarter = wid & 3;                 // TMEM lane quarter this warp may access == sample index (PT == 32)
     int r = cta;
-    const float* bias = P + a.b_off;
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
       const int buf = tl & 1;
       const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
@@ -793,25 +819,26 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
       const long long row = ((long long)(s0 + quarter) * a.hw + egp) * a.N;
       float* out_r = a.out + (long long)net * a.out_net_stride + row;
       const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
+      float4 rr[N / 4];                            // residual row: in flight while the MMAs of this tile run
+      if (res_r && erow) {
+#pragma unroll
+        for (int j = 0; j < N / 4; ++j) rr[j] = ld4(res_r + 4 * j);
+      }
       mbar_wait(&bar_tfull[buf], (tl >> 1) & 1);
       tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int cb = 0; cb < N; cb += 16) {
         float v[16];
-        float4 rr[4];
-        if (res_r && erow) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rr[j] = ld4(res_r + cb + 4 * j);
-        }
         tmem_ld<16>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + cb), v);
         if (erow) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 bb = ld4(bias + cb + j);
+            const float4 bb = ld4(bias_s + cb + j);
             float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
             if (res_r) {
-              o0 += rr[j / 4].x; o1 += rr[j / 4].y; o2 += rr[j / 4].z; o3 += rr[j / 4].w;
+              const float4 q4 = rr[(cb + j) / 4];
+              o0 += q4.x; o1 += q4.y; o2 += q4.z; o3 += q4.w;
             }
             st4(out_r + cb + j, make_float4(o0, o1, o2, o3));
             float l;

@@ -246,32 +246,69 @@ def run_ours(args):
     ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
     ms_e2e = timed(step_e2e, K, 2)
 
-    # ---- dominant kernel: 1x1-conv GEMM of the 28x28x64 channel layers, timed alone on the launch stream
+    # ---- dominant kernel (profiles/: ~40 % of the step): the 1x1 convolution of the 28x28x64 channel layers,
+    # tcgen05 3xTF32 (pw_tc3_kernel<64>), timed ALONE with CUDA events on the stream it is launched on.
     layer = model.coupling_layers[2]        # block 0, mask 2: h,w,nk = 28,28,64
     info = layer._info
     hw, nk, cat = info.h * info.w, info.nk, info.cat
     u1c = torch.randn(B, info.h, info.w, info.c1, device=dev)
-    for _ in range(2):
-        layer.A_wrapper(u1c)
+    layer.A_wrapper(u1c)                    # fills the layer workspace (X, Y1, Y2, LayerNorm statistics)
+    ws = layer._workspace(B)
+
+    def time_pw(which, reps=20):
+        br = _lib.Borrowed()
+        pp, pw_ = br(layer.params), br(ws)
+        for _ in range(3):
+            _lib.check(_lib.lib.cnf_debug_pw_conv(layer._h, pp, pw_, B, which, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            _lib.check(_lib.lib.cnf_debug_pw_conv(layer._h, pp, pw_, B, which, _lib.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_pw1 = time_pw(0)
+    ms_pw2 = time_pw(1)
+    # algorithmic bytes per launch (both nets): read the input once, write the output once (+ residual read);
+    # gamma/beta (0.4 MB per net, L2-resident across the batch) and W (16-28 KB) are not counted
+    pw1_bytes = 2 * B * hw * (nk + nk) * 4
+    pw2_bytes = 2 * B * hw * (cat + nk + nk) * 4
+    pw_flops = 2 * 2 * B * hw * nk * (nk + cat)
+    hbm_peak, peak_src = peaks()
+    ach = (pw1_bytes + pw2_bytes) / ((ms_pw1 + ms_pw2) * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "pw_tc3_kernel<64>: 1x1 convs (64->64 and 112->64 + residual) of a 28x28x64 channel "
+            "layer with LReLU+LayerNorm-on-load, tcgen05 3xTF32, both nets, B=256 (two launches averaged by bytes)",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "peak_source": peak_src, "ms_per_launch": {"pw1_64to64": ms_pw1, "pw2_112to64_res": ms_pw2},
+            "algorithmic_bytes_per_launch": {"pw1": pw1_bytes, "pw2": pw2_bytes},
+            "tflops_fp32_equivalent": pw_flops / ((ms_pw1 + ms_pw2) * 1e-3) / 1e12}
+
+    # ---- the stand-alone fused coupling-law kernel (mask addressing + affine law + per-sample log-det), the
+    # HBM-bound kernel the north star names: 12 bytes per element of u
+    Bl, Hl, Wl, Dl = 512, 128, 128, 4
+    ul = torch.randn(Bl, Hl, Wl, Dl, device=dev)
+    sl = 0.1 * torch.randn(Bl, Hl, Wl, Dl // 2, device=dev)
+    tl_ = torch.randn(Bl, Hl, Wl, Dl // 2, device=dev)
+    vl = torch.empty_like(ul)
+    ldl = torch.empty(Bl, device=dev)
+
+    def law():
+        br = _lib.Borrowed()
+        _lib.check(_lib.lib.cnf_coupling_law(br(ul), br(sl), br(tl_), 2, 0, br(vl), br(ldl), _lib.stream_ptr()))
+    for _ in range(3):
+        law()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
     e0.record()
-    for _ in range(reps):
-        layer.A_wrapper(u1c)
+    for _ in range(10):
+        law()
     e1.record()
     torch.cuda.synchronize()
-    ms_layer = e0.elapsed_time(e1) / reps
-    # algorithmic bytes of the whole layer's s/t nets (every conv reads its input once and writes its output
-    # once; LN gamma/beta once per sample-tile from L2 are excluded): per sample and net
-    R = info.R
-    per_sample_net = 4 * hw * (nk + R * (nk + nk + nk + cat + cat + nk + nk) + nk)   # stem out; pw1 in/out; gc in/out; pw2 in/res/out; head in
-    layer_bytes = 2 * B * per_sample_net
-    hbm_peak, peak_src = peaks()
-    roof = {"bound": "hbm", "kernel": "s/t nets of one 28x28x64 channel coupling layer (11 launches: stem, 3x[pw1,gconv,pw2], head)",
-            "achieved": layer_bytes / (ms_layer * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": layer_bytes / (ms_layer * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "ms_per_launch_group": ms_layer, "algorithmic_bytes": layer_bytes}
+    ms_law = e0.elapsed_time(e1) / 10
+    law_gbs = 12 * ul.numel() / (ms_law * 1e-3) / 1e9
+    del ul, sl, tl_, vl
 
     n_coupling = len(model.coupling_layers)
     launches_per_dir = sum(2 + 3 * l._info.R for l in model.coupling_layers)
@@ -289,6 +326,8 @@ def run_ours(args):
                              "(> 126 MB L2) and inputs rotate over 8 distinct batches",
                        "eval_images_per_s": B * world * K / (ms_eval * 1e-3),
                        "sample_images_per_s": B * world * K / (ms_samp * 1e-3),
+                       "coupling_law_kernel": {"shape": [512, 128, 128, 4], "ms": ms_law, "GB/s": law_gbs,
+                                               "frac_of_hbm_peak": law_gbs / hbm_peak, "bytes_per_element": 12},
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": imgs * K / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": 2 * B * H * W * D * 4, "d2h_bytes_per_step": (4 + 3 * B) * 4 + B * H * W * D * 4},

@@ -142,6 +142,13 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1_compresse
                       const DLManagedTensor* params, DLManagedTensor* A, DLManagedTensor* b,
                       DLManagedTensor* workspace, void* stream);
 
+/* measurement hook: launches ONLY the dominant 1x1-conv kernel of residual block 0 (which = 0: pw1,
+ * X -> Y1 with LayerNorm-on-load; which = 1: pw2, Y2 (+X) -> X) on the workspace state left by a
+ * previous cnf_coupling_nets / cnf_coupling_forward call with the same batch.  Used by bench.py to time that
+ * kernel alone with CUDA events (roofline).  Replaces nothing in the reference. */
+int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace,
+                      int64_t batch, int which, void* stream);
+
 /* fused standalone coupling law + mask addressing + per-sample log-det (M:1215-1253, M:1307-1326):
  * v = mask(u,m,False) + decompress(exp(s)*u2c + t, m_bar)   (inverse: (u2c - t) / exp(s)).
  * u, v are [B,H,W,D]; s, t are [B,h,w,c2] in the compressed layout of the complement mask;
