@@ -87,7 +87,7 @@ inline FlowView make_view(float* buf, int H0, int W0, int D0, int level) {
   return v;
 }
 
-enum HeadMode { HEAD_FWD = 0, HEAD_INV = 1, HEAD_EMIT = 2 };
+enum HeadMode { HEAD_FWD = 0, HEAD_INV = 1, HEAD_EMIT = 2, HEAD_EMIT_TANH = 3 };  // 3: outA = tanh(raw) (training)
 enum { MASK_DENSE = 4 };  // "already compressed" input for A_wrapper/b_wrapper (M:452-472)
 
 struct CouplingWorkspace {

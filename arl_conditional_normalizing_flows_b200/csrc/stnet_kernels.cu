@@ -46,6 +46,8 @@ struct GemmArgs {
   const float* res;           // residual, same layout as out, may alias out; or nullptr
   long long out_net_stride;
   int B, hw, K, N, KC, ln;
+  // backward-pass uses of gemm_kernel: raw_in = no LReLU/LN on A; w_trans = B[k][n] = W[n*ldw + k]; no_bias
+  int raw_in, w_trans, ldw, no_bias;
 };
 
 template <int TN, int NQ, int RM, bool STEM>
@@ -91,14 +93,21 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
       const int gk = kc0 + k, n = n0 + nq * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gk < a.K) {
-        const float* src = Wg + (long long)gk * a.N + n;
-        if (n_vec && n + 3 < a.N) {
-          v = ld4(src);
+        if (a.w_trans) {
+          if (n + 0 < a.N) v.x = Wg[(long long)(n + 0) * a.ldw + gk];
+          if (n + 1 < a.N) v.y = Wg[(long long)(n + 1) * a.ldw + gk];
+          if (n + 2 < a.N) v.z = Wg[(long long)(n + 2) * a.ldw + gk];
+          if (n + 3 < a.N) v.w = Wg[(long long)(n + 3) * a.ldw + gk];
         } else {
-          if (n + 0 < a.N) v.x = src[0];
-          if (n + 1 < a.N) v.y = src[1];
-          if (n + 2 < a.N) v.z = src[2];
-          if (n + 3 < a.N) v.w = src[3];
+          const float* src = Wg + (long long)gk * a.N + n;
+          if (n_vec && n + 3 < a.N) {
+            v = ld4(src);
+          } else {
+            if (n + 0 < a.N) v.x = src[0];
+            if (n + 1 < a.N) v.y = src[1];
+            if (n + 2 < a.N) v.z = src[2];
+            if (n + 3 < a.N) v.w = src[3];
+          }
         }
       }
       st4(&Bs[k * TN + nq * 4], v);
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
           if (p < a.hw) {
             const long long e = (long long)p * a.K + kc0 + kq * 4;
             v = ld4(src_s + e);
-            v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w);
+            if (!a.raw_in) { v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w); }
             if (a.ln) {
               const float4 g = ld4(gam + e), be = ld4(bet + e);
               v.x = (v.x - mean) * rstd * g.x + be.x;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
           float v = 0.f;
           if (p < a.hw && gk < a.K) {
             const long long e = (long long)p * a.K + gk;
-            v = lrelu(src_s[e]);
+            v = a.raw_in ? src_s[e] : lrelu(src_s[e]);
             if (a.ln) v = (v - mean) * rstd * gam[e] + bet[e];
           }
           As[m * KS + k] = v;
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
       for (int j = 0; j < 4; ++j) o[j] = acc[r][q * 4 + j];
       const long long e = (long long)p * a.N + n;
       if (n_vec) {
-        const float4 bb = ld4(bias + n);
+        const float4 bb = a.no_bias ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(bias + n);
         o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
         if (res_s) {
           const float4 rr = ld4(res_s + e);
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (n + j < a.N) {
-            float v = o[j] + bias[n + j];
+            float v = o[j] + (a.no_bias ? 0.f : bias[n + j]);
             if (res_s) v += res_s[e + j];
             out_s[e + j] = v;
             const float l = lrelu(v);
@@ -442,6 +451,7 @@ __global__ void __launch_bounds__(256, 2) pw_kernel(const GemmArgs a) {
 // ------------------------------------------------------------------------------------------
 struct GconvBranch {
   int dil, groups, gin, gout, out_off, first_item;
+  int in_off;   // first input channel of the branch inside the input tensor (0 in the forward pass)
   long long w_off, b_off;
 };
 struct GconvArgs {
@@ -455,6 +465,8 @@ struct GconvArgs {
   int B, h, w, Cin, Cout, ln, ks;
   int TH, TW, tiles_y, tiles_x;
   int dbg;  // debug: bit0 skip global loads in staging, bit1 skip the FFMA taps
+  // backward-input mode: raw input (no LReLU/LN), flipped+transposed weights, accumulate into `out`, no bias, no stats
+  int bwd;
   int n_br;
   GconvBranch br[CNF_MAX_BRANCHES];
 };
@@ -960,8 +972,17 @@ __global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
   }
   {
     const float* wsrc = P + br.w_off + (long long)g * 9 * G * G;
-    for (int i = tid; i < 9 * G * G; i += NT) w_s[i] = wsrc[i];
-    if (tid < G) b_s[tid] = P[br.b_off + g * G + tid];
+    if (!a.bwd) {
+      for (int i = tid; i < 9 * G * G; i += NT) w_s[i] = wsrc[i];
+    } else {
+      // dA[q, ci] = sum_tap sum_co dOut[q - off(tap), co] W[tap][ci][co]: a forward-form conv with taps flipped
+      // and (ci, co) swapped: w'[tap'][co][ci] = W[8 - tap'][ci][co]
+      for (int i = tid; i < 9 * G * G; i += NT) {
+        const int tap = i / (G * G), r2 = i % (G * G), in_c = r2 / G, out_c = r2 % G;
+        w_s[i] = wsrc[((8 - tap) * G + out_c) * G + in_c];
+      }
+    }
+    if (tid < G) b_s[tid] = a.bwd ? 0.f : P[br.b_off + g * G + tid];
   }
   __syncthreads();
   {
@@ -969,7 +990,7 @@ __global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
     const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b0 * sample_stride;
     const float* gam = P + a.g_off;
     const float* bet = P + a.be_off;
-    const int cin0 = g * G;
+    const int cin0 = br.in_off + g * G;
     const int row_slots = SW * VPP;
     for (int sy = wid; sy < SH; sy += nw) {
       const int gy = y0 - halo + sy;
@@ -1011,7 +1032,7 @@ __global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
               const float mean = mr[q][0], rstd = mr[q][1];
 #pragma unroll
               for (int i = 0; i < V; ++i) {
-                float v = lrelu(xf[i]);
+                float v = a.bwd ? xf[i] : lrelu(xf[i]);
                 if (a.ln) v = (v - mean) * rstd * gf[i] + bf[i];
                 o[i] = v;
               }
@@ -1093,6 +1114,7 @@ __global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
 #pragma unroll
         for (int co = 0; co < G; ++co) {
           o[co] = acc[j][co] + b_s[co];
+          if (a.bwd) o[co] += dst[co];      // branches overlap on input channels: accumulate (launches are sequential)
           const float l = lrelu(o[co]);
           s1 += l;
           s2 += l * l;
@@ -1120,6 +1142,205 @@ __global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
       double t = 0.0;
       for (int i = 0; i < w1; ++i) t += (double)red[q * w1 + i][which];
       atomicAdd(a.stats_out + 2 * ((long long)net * a.B + b0 + q) + which, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2d. Grouped dilated convs with fully asynchronous staging: every thread issues ALL of its raw copies
+//     (x, gamma, beta; cp.async, 16/8/4 B) for the CTA's tile at once, waits once, applies
+//     LReLU + LayerNorm in shared memory on the slots it copied itself, and only then does the CTA
+//     synchronise and run the register-blocked FFMA taps of gconv3.  One global-latency exposure per
+//     CTA instead of one per staging row; row bands keep the three raw tiles small enough for 3 CTAs/SM.
+// ------------------------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async_any(void* smem_dst, const void* gsrc) {
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+  else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int G, int PX>
+__global__ void __launch_bounds__(256) gconv4_kernel(const GconvArgs a) {
+  constexpr int V = G >= 4 ? 4 : G;
+  constexpr int VPP = G / V;
+  constexpr int GS = G + ((G % 8) == 0 ? 4 : 0);
+  using T = typename VecT<V>::T;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[64];
+  __shared__ float mr[2];
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
+  const int b = blockIdx.y, net = blockIdx.z;
+  const GconvBranch& br = a.br[0];
+  const int tiles = a.tiles_y * a.tiles_x;
+  const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const int y0 = (tile / a.tiles_x) * a.TH, x0 = (tile % a.tiles_x) * a.TW;
+  const int th = min(a.TH, a.h - y0), tw = min(a.TW, a.w - x0);
+  const int d = br.dil, halo = d;
+  const int SH = th + 2 * halo, SW = tw + 2 * halo;
+  const int in_sz = (SH * SW * GS + 3) & ~3;
+  float* x_s = smem;                       // [SH*SW][GS] raw x, then LN(LReLU(x)) in place
+  float* g_s = x_s + in_sz;                // raw gamma
+  float* be_s = g_s + in_sz;               // raw beta
+  float* w_s = be_s + in_sz;               // [9][G][G]
+  float* b_s = w_s + ((9 * G * G + 3) & ~3);
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.Cin;
+  const float* gam = P + a.g_off;
+  const float* bet = P + a.be_off;
+  const int cin0 = g * G;
+  const int row_slots = SW * VPP;
+  // ---- issue everything
+  for (int sy = wid; sy < SH; sy += nw) {
+    const int gy = y0 - halo + sy;
+    if (gy < 0 || gy >= a.h) continue;
+    for (int sl = lane; sl < row_slots; sl += 32) {
+      const int sx = sl / VPP, cv = sl % VPP;
+      const int gx = x0 - halo + sx;
+      if (gx < 0 || gx >= a.w) continue;
+      const long long e = ((long long)gy * a.w + gx) * a.Cin + cin0 + cv * V;
+      const int so = (sy * SW + sx) * GS + cv * V;
+      cp_async_any<4 * V>(x_s + so, src_s + e);
+      if (a.ln) {
+        cp_async_any<4 * V>(g_s + so, gam + e);
+        cp_async_any<4 * V>(be_s + so, bet + e);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid == 0) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.Cin, mean, rstd);
+    mr[0] = rstd;
+    mr[1] = -mean * rstd;
+  }
+  {
+    const float* wsrc = P + br.w_off + (long long)g * 9 * G * G;
+    for (int i = tid; i < 9 * G * G; i += NT) w_s[i] = wsrc[i];
+    if (tid < G) b_s[tid] = P[br.b_off + g * G + tid];
+  }
+  __syncthreads();                         // mr visible
+  const float sc = mr[0], shf = mr[1];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- transform the slots this thread copied (same loops), zero the padding
+  for (int sy = wid; sy < SH; sy += nw) {
+    const int gy = y0 - halo + sy;
+    const bool rowok = gy >= 0 && gy < a.h;
+    for (int sl = lane; sl < row_slots; sl += 32) {
+      const int sx = sl / VPP, cv = sl % VPP;
+      const int gx = x0 - halo + sx;
+      const int so = (sy * SW + sx) * GS + cv * V;
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.f;
+      if (rowok && gx >= 0 && gx < a.w) {
+        const T xv = *reinterpret_cast<const T*>(x_s + so);
+        const float* xf = reinterpret_cast<const float*>(&xv);
+        if (a.ln) {
+          const T gv = *reinterpret_cast<const T*>(g_s + so);
+          const T bv = *reinterpret_cast<const T*>(be_s + so);
+          const float* gf = reinterpret_cast<const float*>(&gv);
+          const float* bf = reinterpret_cast<const float*>(&bv);
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = fmaf(fmaf(fmaxf(xf[i], CNF_LRELU_SLOPE * xf[i]), sc, shf), gf[i], bf[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = fmaxf(xf[i], CNF_LRELU_SLOPE * xf[i]);
+        }
+      }
+      *reinterpret_cast<T*>(x_s + so) = *reinterpret_cast<const T*>(o);
+    }
+  }
+  __syncthreads();
+
+  const int TP = th * tw;
+  float acc[PX][G];
+  int poff[PX];
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    const int p = min(tid + j * NT, TP - 1);
+    poff[j] = ((p / tw) * SW + (p % tw)) * GS;
+#pragma unroll
+    for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
+  }
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int toff = (ky * d * SW + kx * d) * GS;
+    const float* wt = w_s + tap * G * G;
+    float xv[PX][G];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      const float* src = x_s + poff[j] + toff;
+      if (G % 4 == 0) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) {
+          const float4 t = ld4(src + c4);
+          xv[j][c4] = t.x; xv[j][c4 + 1] = t.y; xv[j][c4 + 2] = t.z; xv[j][c4 + 3] = t.w;
+        }
+      } else if (G == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(src);
+        xv[j][0] = t.x; xv[j][G - 1] = t.y;
+      } else {
+        xv[j][0] = src[0];
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < G; ++ci) {
+      float wv[G];
+      if (G % 4 == 0) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) {
+          const float4 t = ld4(wt + ci * G + c4);
+          wv[c4] = t.x; wv[c4 + 1] = t.y; wv[c4 + 2] = t.z; wv[c4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < G; ++c) wv[c] = wt[ci * G + c];
+      }
+#pragma unroll
+      for (int j = 0; j < PX; ++j)
+#pragma unroll
+        for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[j][ci], wv[co], acc[j][co]);
+    }
+  }
+
+  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.h * a.w * a.Cout;
+  const int cbase = br.out_off + g * G;
+  const bool vec = (G % 4 == 0) && (a.Cout % 4 == 0) && (cbase % 4 == 0);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    const int p = tid + j * NT;
+    if (p < TP) {
+      const int y = y0 + p / tw, x = x0 + p % tw;
+      float* dst = out_s + ((long long)y * a.w + x) * a.Cout + cbase;
+      float o[G];
+#pragma unroll
+      for (int co = 0; co < G; ++co) {
+        o[co] = acc[j][co] + b_s[co];
+        const float l = fmaxf(o[co], CNF_LRELU_SLOPE * o[co]);
+        s1 += l;
+        s2 = fmaf(l, l, s2);
+      }
+      if (vec) {
+#pragma unroll
+        for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
+      } else {
+#pragma unroll
+        for (int co = 0; co < G; ++co) dst[co] = o[co];
+      }
+    }
+  }
+  if (a.stats_out) {
+    double d1, d2;
+    block_sum2(s1, s2, red, d1, d2);
+    if (tid == 0) {
+      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+      atomicAdd(so, d1);
+      atomicAdd(so + 1, d2);
     }
   }
 }
@@ -1293,9 +1514,9 @@ __global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
       if (co < a.c2) {
         const float A = tw_ * tanhf(acc[0][co] + PA[a.b_off + co]);  // M:1198, M:114-116
         const float t = acc[1][co] + PB[a.b_off + co];
-        if (a.mode == HEAD_EMIT) {
+        if (a.mode == HEAD_EMIT || a.mode == HEAD_EMIT_TANH) {
           const long long e = ((long long)b * a.h * a.w + (long long)y * a.w + x) * a.c2 + co;
-          a.outA[e] = A;
+          a.outA[e] = a.mode == HEAD_EMIT ? A : tanhf(acc[0][co] + PA[a.b_off + co]);
           a.outB[e] = t;
         } else {
           float* ptr = a.view.base + comp_off(a.view, a.mask_c, b, y, x, co);
@@ -1584,6 +1805,78 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   }
 }
 
+template <int G, int PX>
+static int launch_gconv4_t(const GconvArgs& a, int NT, size_t smem, cudaStream_t st) {
+  auto kern = gconv4_kernel<G, PX>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  dim3 grid(a.br[0].groups * a.tiles_y * a.tiles_x, a.B, 2);
+  kern<<<grid, NT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int G>
+static int launch_gconv4_g(const GconvArgs& a, int PX, int NT, size_t smem, cudaStream_t st) {
+  switch (PX) {
+    case 1: return launch_gconv4_t<G, 1>(a, NT, smem, st);
+    case 2: return launch_gconv4_t<G, 2>(a, NT, smem, st);
+    case 3: return launch_gconv4_t<G, 3>(a, NT, smem, st);
+    case 4: return launch_gconv4_t<G, 4>(a, NT, smem, st);
+    case 5: return launch_gconv4_t<G, 5>(a, NT, smem, st);
+    case 6: return launch_gconv4_t<G, 6>(a, NT, smem, st);
+    case 7: return launch_gconv4_t<G, 7>(a, NT, smem, st);
+    default: return launch_gconv4_t<G, 8>(a, NT, smem, st);
+  }
+}
+
+// One branch (gin == gout in {1,2,4,8}, ksize 3) with asynchronous staging.  Returns 1 if not eligible.
+static int launch_gconv4_branch(const GconvArgs& g, int bi, cudaStream_t st) {
+  const GconvBranch& br = g.br[bi];
+  const int G = br.gin;
+  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || g.B > 65535) return 1;
+  if ((G >= 4 && g.Cin % 4) || (G == 2 && g.Cin % 2)) return 1;
+  GconvArgs a = g;
+  a.n_br = 1;
+  a.br[0] = br;
+  a.br[0].first_item = 0;
+  const int halo = br.dil;
+  const int GS = G + ((G % 8) == 0 ? 4 : 0);
+  // row bands: three raw tiles (x, gamma, beta) of (TH+2*halo) x (w+2*halo) x GS floats, target <= ~72 KB
+  a.TW = std::min(a.w, 32);
+  a.tiles_x = (a.w + a.TW - 1) / a.TW;
+  static int band_env = -1;
+  if (band_env < 0) { const char* e = getenv("CNF_GC_BAND_KB"); band_env = e ? atoi(e) : 72; }
+  int n_bands = 1;
+  for (;; ++n_bands) {
+    const int thb = (std::min(a.h, 32) + n_bands - 1) / n_bands;
+    const size_t bytes = (size_t)3 * (thb + 2 * halo) * (a.TW + 2 * halo) * GS * 4;
+    if (bytes <= (size_t)band_env * 1024 || thb <= 2) break;
+  }
+  a.TH = (std::min(a.h, 32) + n_bands - 1) / n_bands;
+  a.tiles_y = (a.h + a.TH - 1) / a.TH;
+  const int TP = a.TH * a.TW;
+  int best_px = 8, best_nt = 128, best_waste = 1 << 30;
+  for (int px = 8; px >= 1; --px) {
+    int nt = ((TP + px - 1) / px + 31) / 32 * 32;
+    if (nt < 64) nt = 64;
+    if (nt > 256) continue;
+    const int waste = nt * px - TP;
+    if (waste < best_waste) { best_waste = waste; best_px = px; best_nt = nt; }
+  }
+  const size_t in_sz = (((size_t)(a.TH + 2 * halo) * (a.TW + 2 * halo) * GS) + 3) & ~(size_t)3;
+  const size_t smem = (3 * in_sz + ((9 * G * G + 3) & ~3) + G + 4) * sizeof(float);
+  if (smem > 227 * 1024) return 1;
+  switch (G) {
+    case 1: return launch_gconv4_g<1>(a, best_px, best_nt, smem, st);
+    case 2: return launch_gconv4_g<2>(a, best_px, best_nt, smem, st);
+    case 4: return launch_gconv4_g<4>(a, best_px, best_nt, smem, st);
+    default: return launch_gconv4_g<8>(a, best_px, best_nt, smem, st);
+  }
+}
+
 static int launch_gconv_ffma(GconvArgs a, cudaStream_t st);
 
 static int launch_gconv(GconvArgs a, cudaStream_t st) {
@@ -1594,7 +1887,9 @@ static int launch_gconv(GconvArgs a, cudaStream_t st) {
   GconvArgs rest = a;
   rest.n_br = 0;
   for (int i = 0; i < a.n_br; ++i) {
-    const int rc = tc ? launch_gconv_tc_branch(a, i, st) : launch_gconv3_branch(a, i, st);
+    static int v4 = -1;
+    if (v4 < 0) { const char* e = getenv("CNF_GC_V4"); v4 = (e && e[0] == '1') ? 1 : 0; }   // async-staging variant: correct but slower (opt-in)
+    const int rc = tc ? launch_gconv_tc_branch(a, i, st) : v4 ? launch_gconv4_branch(a, i, st) : launch_gconv3_branch(a, i, st);
     if (rc == 1) rest.br[rest.n_br++] = a.br[i];
     else if (rc != 0) return rc;
   }

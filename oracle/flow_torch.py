@@ -36,8 +36,8 @@ def conv2d_same(x, kernel, bias, dilation=1):
     k = kernel.shape[0]
     assert k % 2 == 1, "oracle restates odd kernel sizes only"
     pad = dilation * (k - 1) // 2
-    w = kernel.permute(3, 2, 0, 1)                           # OIHW
-    y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, stride=1, padding=pad, dilation=dilation)
+    w = kernel.permute(3, 2, 0, 1).contiguous()              # OIHW
+    y = F.conv2d(x.permute(0, 3, 1, 2).contiguous(), w, bias, stride=1, padding=pad, dilation=dilation)
     return y.permute(0, 2, 3, 1)
 
 
