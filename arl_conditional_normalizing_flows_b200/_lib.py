@@ -86,6 +86,9 @@ def _load():
         "cnf_flow_inverse": (I, [P, P, P, P, P, V]),
         "cnf_flow_log_loss": (I, [P, P, P, P, P, P, P, P, P, V]),
         "cnf_prior_loss": (I, [P, P, P, I, D, P, P, P, V]),
+        "cnf_plan_train_workspace_bytes": (I64, [P, I64]),
+        "cnf_flow_loss_and_grad": (I, [P, P, P, P, P, P, P, P, P, P, V]),
+        "cnf_adam_step": (I, [P, P, P, P, I64, D, D, D, D, D, V]),
         "cnf_coupling_forward": (I, [P, P, P, P, P, P, V]),
         "cnf_coupling_backward": (I, [P, P, P, P, P, V]),
         "cnf_coupling_nets": (I, [P, P, P, P, P, P, V]),

@@ -265,8 +265,10 @@ class coupling_layer(Layer):
             return None                                  # biases / beta stay 0
         self.params.copy_(torch.from_numpy(self._host_flat(fill)))
 
-    def weight_views(self):
-        """{'A': {name: tensor view}, 'b': {...}} — Keras-shaped views into the flat device buffer."""
+    def weight_views(self, buf=None):
+        """{'A': {name: tensor view}, 'b': {...}} — Keras-shaped views into the flat device buffer (or into
+        `buf`, a tensor with the same layout, e.g. this layer's slice of the gradient buffer)."""
+        buf = self.params if buf is None else buf
         out = {}
         for n, net in enumerate(("A", "b")):
             base = n * self._net_stride
@@ -275,7 +277,7 @@ class coupling_layer(Layer):
                 if role == 4 and net == "b":
                     continue                             # net b has no tanh scale (M:1190-1204)
                 cnt = int(np.prod(shape))
-                v = self.params[base + off: base + off + cnt]
+                v = buf[base + off: base + off + cnt]
                 d[name] = v.view(()) if role == 4 else v.view(shape)
             out[net] = d
         return out
@@ -621,7 +623,96 @@ class cFlow:
     def test_step(self, xy):
         return self._update_trackers(self.log_loss(xy))
 
+    # -- gradients of log_loss (the tf.GradientTape block of train_step, M:1863-1871) --------------------------
+    def _train_workspace(self, B):
+        need = int(lib.cnf_plan_train_workspace_bytes(self._plan, B))
+        ws = getattr(self, '_train_ws', None)
+        if ws is None or ws.numel() < need or ws.device != self.params.device:
+            self._train_ws = ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
+        return ws
+
+    def loss_and_grad(self, xy):
+        """log_loss(xy) plus dloss/dparams as ONE flat tensor with the layout of self.params (hand-written
+        backward kernels).  Returns ((loss, z_loss, y_loss, detJ_loss), grads)."""
+        xy = self._check_io(xy, "xy")
+        B = xy.shape[0]
+        dev = xy.device
+        zy = torch.empty_like(xy)
+        Bp = (B + 3) & ~3
+        pers = torch.empty((3, Bp), dtype=torch.float32, device=dev)
+        loss4 = torch.empty(4, dtype=torch.float32, device=dev)
+        ll_z, ll_y, ld = pers[0, :B], pers[1, :B], pers[2, :B]
+        if getattr(self, '_grads', None) is None or self._grads.device != self.params.device:
+            self._grads = torch.empty_like(self.params)
+        br = Borrowed()
+        check(lib.cnf_flow_loss_and_grad(self._plan, br(xy), br(self.params), br(self._grads), br(zy), br(ll_z),
+                                         br(ll_y), br(ld), br(loss4), br(self._train_workspace(B)), stream_ptr()))
+        self.last_logdet_per_sample = ld
+        self.last_per_sample = {'ll_z': ll_z, 'll_y': ll_y, 'logdet': ld, 'zy': zy}
+        return (loss4[0], loss4[1], loss4[2], loss4[3]), self._grads
+
+    def grad_views(self, grads=None):
+        """the flat gradient buffer as the same named views get_weights() uses: [{'A': {...}, 'b': {...}}, ...]"""
+        grads = self._grads if grads is None else grads
+        out = []
+        for layer in self.coupling_layers:
+            off = layer.params.storage_offset() - self.params.storage_offset()
+            out.append(layer.weight_views(grads[off: off + layer.params.numel()]))
+        return out
+
     def train_step(self, xy):
-        raise NotImplementedError(
-            "cFlow.train_step: the hand-written backward kernels (SURVEY §8a A11) are not built in this "
-            "round; forward / inverse / log_loss / test_step are.")
+        """cFlow.train_step (M:1850-1880): gradients of log_loss, optimizer.apply_gradients, metric trackers.
+        Data-parallel (torch.distributed initialised): one sum all-reduce of the flat gradient buffer over
+        NCCL, scaled by 1/world_size inside the fused Adam update."""
+        if self.optimizer is None:
+            raise RuntimeError("train_step: call model.compile(optimizer=Adam(...)) first")   # keras raises too
+        four, grads = self.loss_and_grad(xy)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:
+                torch.distributed.all_reduce(grads)
+        self.optimizer.apply_gradients(self.params, grads, grad_scale=1.0 / world)
+        return self._update_trackers(four)
+
+    def fit(self, batches, epochs=1, verbose=0):
+        """thin replacement of the keras fit loop (C:617-636, P:136-145): `batches` is an iterable of xy tensors
+        (re-iterated every epoch).  Returns {'loss': [...], 'z_loss': [...], ...} per epoch, like History.history."""
+        history = {m.name: [] for m in self.metrics}
+        for ep in range(epochs):
+            for m in self.metrics:
+                m.reset_state()
+            logs = None
+            for xy in batches:
+                logs = self.train_step(xy)
+            if logs is None:
+                raise ValueError("fit: empty dataset")
+            for k, v in logs.items():
+                history[k].append(v)
+            if verbose:
+                print(f"epoch {ep + 1}/{epochs} " + " ".join(f"{k}={v:.5f}" for k, v in logs.items()))
+        return history
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate) as the reference compiles it (C:567, P:130): defaults lr 1e-3,
+    beta_1 0.9, beta_2 0.999, epsilon 1e-7, no amsgrad.  One fused kernel over the flat parameter buffer."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate = learning_rate
+        self.beta_1 = beta_1
+        self.beta_2 = beta_2
+        self.epsilon = epsilon
+        self.iterations = 0
+        self._m = None
+        self._v = None
+
+    def apply_gradients(self, params, grads, grad_scale=1.0):
+        if self._m is None or self._m.shape != params.shape or self._m.device != params.device:
+            self._m = torch.zeros_like(params)
+            self._v = torch.zeros_like(params)
+        self.iterations += 1
+        br = Borrowed()
+        check(lib.cnf_adam_step(br(params), br(grads), br(self._m), br(self._v), self.iterations,
+                                float(self.learning_rate), float(self.beta_1), float(self.beta_2),
+                                float(self.epsilon), float(grad_scale), stream_ptr()))

@@ -7,7 +7,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "cnf_internal.h"
 
@@ -215,6 +217,117 @@ int cnf_flow_log_loss(const cnf_plan* p, const DLManagedTensor* xy, const DLMana
   if (X.shape[0] == 0) return fail(CNF_ERR_ARG, "empty batch: the batch means of the loss are undefined");
   TRY(cnf_flow_forward(p, xy, params, zy, logdet, workspace, stream));
   return cnf_prior_loss(zy, xy, logdet, p->x_d, p->lambda_y, ll_z, ll_y, loss4, stream);
+}
+
+// ---- training: forward with saved activations, loss, full backward (cFlow.train_step, M:1850-1880) ----
+namespace {
+struct TrainLayout {
+  int64_t state_bytes, states_off, G_off, ld_off, scratch_off, total;
+  std::vector<int64_t> saved_off;
+};
+TrainLayout train_layout(const cnf_plan* p, int64_t B) {
+  auto al = [](int64_t x) { return (x + 255) & ~int64_t(255); };
+  TrainLayout t;
+  const int n = (int)p->couplings.size();
+  t.state_bytes = al(B * p->H * p->W * p->D * 4);
+  int64_t off = 0;
+  t.states_off = off; off += t.state_bytes * n;
+  t.G_off = off; off += t.state_bytes;
+  t.ld_off = off; off += al(B * 8);
+  int64_t scratch = 0;
+  for (auto* c : p->couplings) scratch = std::max(scratch, coupling_bwd_scratch_bytes(c, B));
+  t.scratch_off = off; off += scratch;
+  for (auto* c : p->couplings) { t.saved_off.push_back(off); off += coupling_saved_bytes(c, B); }
+  t.total = off;
+  return t;
+}
+}  // namespace
+
+int64_t cnf_plan_train_workspace_bytes(const cnf_plan* p, int64_t batch) {
+  if (!p || batch < 0) return -1;
+  return train_layout(p, batch).total;
+}
+
+int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                           DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                           DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream) {
+  if (!p) return fail(CNF_ERR_ARG, "null plan");
+  Ten X, P, Gd, Z, A, Bt, L, F, W;
+  TRY(borrow(xy, "xy", 4, &X));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(grads, "grads", 1, &Gd));
+  TRY(borrow(zy, "zy", 4, &Z));
+  TRY(borrow(ll_z, "ll_z", 1, &A));
+  TRY(borrow(ll_y, "ll_y", 1, &Bt));
+  TRY(borrow(logdet, "logdet", 1, &L));
+  TRY(borrow(loss4, "loss4", 1, &F));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  TRY(check_flow_tensor(p, X, "xy"));
+  TRY(check_flow_tensor(p, Z, "zy"));
+  const int64_t B = X.shape[0];
+  if (B == 0) return fail(CNF_ERR_ARG, "empty batch: the batch means of the loss are undefined");
+  if (Z.shape[0] != B || L.shape[0] != B || A.shape[0] != B || Bt.shape[0] != B || F.shape[0] != 4)
+    return fail(CNF_ERR_SHAPE, "zy must be [B,H,W,D], ll_z/ll_y/logdet [B] and loss4 [4]");
+  if (P.numel < p->param_count || Gd.numel < p->param_count)
+    return fail(CNF_ERR_SHAPE, "params/grads: need %lld floats", (long long)p->param_count);
+  if (X.p == Z.p) return fail(CNF_ERR_ARG, "zy must not alias xy");
+  const TrainLayout T = train_layout(p, B);
+  if (W.bytes < T.total) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)T.total, (long long)W.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)W.p;
+  const int n = (int)p->couplings.size();
+  const long long per = (long long)p->H * p->W * p->D;
+  double* ldacc = (double*)(base + T.ld_off);
+  float* G = (float*)(base + T.G_off);
+  void* scratch = base + T.scratch_off;
+  TRY(cuda_rc((int)cudaMemsetAsync(ldacc, 0, sizeof(double) * B, st), "memset"));
+  TRY(cuda_rc((int)cudaMemsetAsync(Gd.p, 0, sizeof(float) * p->param_count, st), "memset"));
+  std::vector<CouplingSaved> saved;
+  // ---- forward: state[l+1] = layer_l(state[l]); the last state is zy
+  for (int li = 0; li < n; ++li) {
+    const cnf_coupling* c = p->couplings[li];
+    saved.push_back(carve_saved(c, B, base + T.saved_off[li]));
+    CouplingSaved& sv = saved.back();
+    sv.state = (float*)(base + T.states_off + T.state_bytes * li);
+    const float* src = li == 0 ? X.p : saved[li - 1].state;
+    float* dst = li == n - 1 ? Z.p : (float*)(base + T.states_off + T.state_bytes * (li + 1));
+    if (li == 0) TRY(cuda_rc(launch_copy(X.p, sv.state, B * per, stream), "copy"));
+    (void)src;
+    TRY(cuda_rc(launch_copy(sv.state, dst, B * per, stream), "copy"));
+    FlowView v = make_view(dst, p->H, p->W, p->D, p->level[li]);
+    TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], v, c->mask, v, (int)B, HEAD_FWD, ldacc, nullptr, nullptr, nullptr,
+                             stream, &sv), "coupling layer"));
+  }
+  if (n == 0) TRY(cuda_rc(launch_copy(X.p, Z.p, B * per, stream), "copy"));
+  TRY(cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream), "logdet"));
+  TRY(cuda_rc(launch_prior_loss(Z.p, X.p, L.p, (int)B, (int64_t)p->H * p->W, p->D, p->x_d, p->lambda_y, A.p, Bt.p, F.p, stream), "prior loss"));
+  // ---- backward
+  const float invB = 1.0f / (float)B;
+  TRY(cuda_rc(launch_loss_grad(Z.p, X.p, G, B * per, p->D, p->x_d, (float)p->lambda_y, invB, stream), "loss gradient"));
+  int first_layer = 0;   // debug: CNF_BWD_FIRST_LAYER=k stops the backward pass after layer k (scratch keeps its buffers)
+  if (const char* e = getenv("CNF_BWD_FIRST_LAYER")) first_layer = atoi(e);
+  for (int li = n - 1; li >= first_layer; --li) {
+    const cnf_coupling* c = p->couplings[li];
+    FlowView gv = make_view(G, p->H, p->W, p->D, p->level[li]);
+    FlowView sview = make_view(saved[li].state, p->H, p->W, p->D, p->level[li]);
+    TRY(cuda_rc(run_coupling_backward(c, P.p + p->param_off[li], Gd.p + p->param_off[li], saved[li], gv, sview, (int)B,
+                                      invB, scratch, stream), "coupling layer backward"));
+  }
+  return CNF_OK;
+}
+
+int cnf_adam_step(DLManagedTensor* params, const DLManagedTensor* grads, DLManagedTensor* m, DLManagedTensor* v,
+                  int64_t step, double lr, double beta_1, double beta_2, double epsilon, double grad_scale, void* stream) {
+  Ten P, Gd, M, V;
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(grads, "grads", 1, &Gd));
+  TRY(borrow(m, "m", 1, &M));
+  TRY(borrow(v, "v", 1, &V));
+  if (Gd.numel != P.numel || M.numel != P.numel || V.numel != P.numel) return fail(CNF_ERR_SHAPE, "params, grads, m, v must have the same length");
+  if (step < 1) return fail(CNF_ERR_ARG, "step counts from 1");
+  const double lr_t = lr * std::sqrt(1.0 - std::pow(beta_2, (double)step)) / (1.0 - std::pow(beta_1, (double)step));
+  return cuda_rc(launch_adam(P.p, Gd.p, M.p, V.p, P.numel, (float)lr_t, (float)beta_1, (float)beta_2, (float)epsilon,
+                             (float)grad_scale, stream), "adam");
 }
 
 static int coupling_common(const cnf_coupling* c, const DLManagedTensor* in, const DLManagedTensor* params,

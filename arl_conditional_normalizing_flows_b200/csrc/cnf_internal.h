@@ -94,13 +94,39 @@ struct CouplingWorkspace {
   float *X, *Y1, *Y2;
   double* stats;  // [n_ln][2][B][2]
 };
+// Training: every stage of the s/t nets keeps its own buffer so that the backward pass can re-read it.
+struct CouplingSaved {
+  std::vector<float*> X;    // R+1 residual-stream states   [2][B][hw][nk]
+  std::vector<float*> Y1;   // R   1x1 outputs               [2][B][hw][nk]
+  std::vector<float*> Y2;   // R   grouped-conv outputs      [2][B][hw][cat]
+  double* stats;            // [n_ln + 1][2][B][2] forward LayerNorm sums
+  float* TH;                // tanh(raw_A) [B][hw][c2]
+  float* state;             // flow buffer BEFORE this layer [B][H0][W0][D0]
+};
+int64_t coupling_saved_bytes(const cnf_coupling* c, int64_t B);
+// carves `mem` (coupling_saved_bytes) -- `state` is assigned by the caller
+CouplingSaved carve_saved(const cnf_coupling* c, int64_t B, void* mem);
+// scratch of the backward pass of one layer (gradient buffers, per-sample LN-backward sums)
+int64_t coupling_bwd_scratch_bytes(const cnf_coupling* c, int64_t B);
+
 int64_t coupling_ws_bytes(const cnf_coupling* c, int64_t B);
 CouplingWorkspace carve_ws(const cnf_coupling* c, int64_t B, void* ws);
 
 // launchers (kernels.cu); all enqueue on `stream`, return cudaError as int (0 ok)
 int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask,
                  FlowView out_view, int B, int mode, double* logdet_acc, float* outA, float* outB,
-                 void* ws, void* stream);
+                 void* ws, void* stream, const CouplingSaved* sv = nullptr);
+// backward of one coupling layer (bwd_kernels.cu): G is the gradient w.r.t. the layer OUTPUT in the flow
+// buffer layout (updated in place to the gradient w.r.t. the layer INPUT); grads has the layout of params.
+int run_coupling_backward(const cnf_coupling* c, const float* params, float* grads, const CouplingSaved& sv,
+                          FlowView g_view, FlowView s_view, int B, float inv_batch, void* scratch, void* stream);
+int dgrad_pw(const float* params, long long net_stride, long long w_off, const float* dY, float* dA, int B, int hw,
+             int K, int N, void* stream);
+int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B, void* stream);
+int launch_loss_grad(const float* zy, const float* xy, float* G, int64_t n, int D, int x_d, float lambda_y,
+                     float inv_batch, void* stream);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
+                float gscale, void* stream);
 int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, void* ws, void* stream);
 int launch_copy(const float* src, float* dst, int64_t n, void* stream);
 int launch_logdet_finalize(const double* acc, float* out, int B, void* stream);

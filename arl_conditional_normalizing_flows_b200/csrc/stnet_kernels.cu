@@ -1524,6 +1524,8 @@ __global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
           if (a.mode == HEAD_FWD) {
             *ptr = __fadd_rn(__fmul_rn(expf(A), u2), t);                  // M:1307, M:1230-1231
             ld += A;                                                      // M:1323
+            if (a.outA)   // training: keep tanh(raw_A) for the backward pass
+              a.outA[((long long)b * a.h * a.w + (long long)y * a.w + x) * a.c2 + co] = tanhf(acc[0][co] + PA[a.b_off + co]);
           } else {
             *ptr = __fmul_rn(__frcp_rn(expf(A)), __fsub_rn(u2, t));       // M:1379, M:1250-1251
           }
@@ -1976,22 +1978,30 @@ static int launch_head(HeadArgs a, cudaStream_t st) {
 // One coupling layer on `B` samples.  in_view/in_mask: where u1 is gathered from; out_view: where
 // u2 is read and v2 written (the same buffer for the in-place flow).  mode: HeadMode.
 int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
-                 int B, int mode, double* logdet_acc, float* outA, float* outB, void* ws, void* stream) {
+                 int B, int mode, double* logdet_acc, float* outA, float* outB, void* ws, void* stream,
+                 const CouplingSaved* sv) {
   cudaStream_t st = (cudaStream_t)stream;
   if (B <= 0) return 0;
-  CouplingWorkspace W = carve_ws(c, B, ws);
+  CouplingWorkspace W = {};
+  if (!sv) W = carve_ws(c, B, ws);
+  else W.stats = sv->stats;
   const int hw = c->hw(), nk = c->nk, cat = c->cat;
   const int n_ln = c->n_ln();
   const long long slot = 2LL * B * 2;  // doubles per stats slot
   if (n_ln) CU_TRY(cudaMemsetAsync(W.stats, 0, sizeof(double) * slot * n_ln, st));
   auto stats = [&](int i) -> double* { return n_ln ? W.stats + slot * i : nullptr; };
+  // inference: one residual-stream buffer updated in place; training (sv): every stage keeps its own buffer
+  auto Xb = [&](int r) -> float* { return sv ? sv->X[r] : W.X; };
+  auto Y1b = [&](int r) -> float* { return sv ? sv->Y1[r] : W.Y1; };
+  auto Y2b = [&](int r) -> float* { return sv ? sv->Y2[r] : W.Y2; };
+  if (sv && mode == HEAD_FWD) outA = sv->TH;   // tanh(raw_A) for the backward pass
 
   {  // stem
     GemmArgs a = {};
     a.view = in_view; a.mask = in_mask; a.h = c->h; a.w = c->w; a.c1 = c->c1; a.ks = c->ks;
     a.params = params; a.net_stride = c->net_stride; a.w_off = c->stem_w; a.b_off = c->stem_b;
     a.stats_out = stats(0);
-    a.out = W.X; a.out_net_stride = (long long)B * hw * nk;
+    a.out = Xb(0); a.out_net_stride = (long long)B * hw * nk;
     a.B = B; a.hw = hw; a.K = c->ks * c->ks * c->c1; a.N = nk; a.ln = 0;
     CU_TRY((cudaError_t)launch_gemm<true>(a, st));
   }
@@ -1999,18 +2009,18 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
     const ResBlockLayout& L = c->rb[r];
     {  // pw1: X -> Y1
       GemmArgs a = {};
-      a.in = W.X; a.in_net_stride = (long long)B * hw * nk;
+      a.in = Xb(r); a.in_net_stride = (long long)B * hw * nk;
       a.params = params; a.net_stride = c->net_stride; a.w_off = L.pw1_w; a.b_off = L.pw1_b;
       a.g_off = L.ln1_g; a.be_off = L.ln1_b;
       a.stats_in = stats(3 * r); a.stats_out = stats(3 * r + 1);
-      a.out = W.Y1; a.out_net_stride = (long long)B * hw * nk;
+      a.out = Y1b(r); a.out_net_stride = (long long)B * hw * nk;
       a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln;
       CU_TRY((cudaError_t)launch_pw(a, st));
     }
     {  // grouped dilated convs: Y1 -> Y2
       GconvArgs a = {};
-      a.in = W.Y1; a.in_net_stride = (long long)B * hw * nk; a.Cin = nk;
-      a.out = W.Y2; a.out_net_stride = (long long)B * hw * cat; a.Cout = cat;
+      a.in = Y1b(r); a.in_net_stride = (long long)B * hw * nk; a.Cin = nk;
+      a.out = Y2b(r); a.out_net_stride = (long long)B * hw * cat; a.Cout = cat;
       a.params = params; a.net_stride = c->net_stride; a.g_off = L.ln2_g; a.be_off = L.ln2_b;
       a.stats_in = stats(3 * r + 1); a.stats_out = stats(3 * r + 2);
       a.B = B; a.h = c->h; a.w = c->w; a.ln = c->ln; a.ks = c->ks;
@@ -2024,18 +2034,18 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
     }
     {  // pw2 + residual: Y2 (+X) -> X
       GemmArgs a = {};
-      a.in = W.Y2; a.in_net_stride = (long long)B * hw * cat;
+      a.in = Y2b(r); a.in_net_stride = (long long)B * hw * cat;
       a.params = params; a.net_stride = c->net_stride; a.w_off = L.pw2_w; a.b_off = L.pw2_b;
       a.g_off = L.ln3_g; a.be_off = L.ln3_b;
       a.stats_in = stats(3 * r + 2); a.stats_out = stats(3 * r + 3);
-      a.out = W.X; a.res = W.X; a.out_net_stride = (long long)B * hw * nk;
+      a.out = Xb(r + 1); a.res = Xb(r); a.out_net_stride = (long long)B * hw * nk;
       a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln;
       CU_TRY((cudaError_t)launch_pw(a, st));
     }
   }
   {  // head + coupling
     HeadArgs a = {};
-    a.in = W.X; a.in_net_stride = (long long)B * hw * nk;
+    a.in = Xb(c->R); a.in_net_stride = (long long)B * hw * nk;
     a.params = params; a.net_stride = c->net_stride; a.g_off = c->lnf_g; a.be_off = c->lnf_b;
     a.w_off = c->head_w; a.b_off = c->head_b; a.tanh_off = c->tanh_w;
     a.stats_in = stats(3 * c->R);
@@ -2074,6 +2084,46 @@ int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, vo
     a.out = W.Y1; a.res = W.X;     // out-of-place so that X is not accumulated into
   }
   return launch_pw(a, st);
+}
+
+
+// ---- backward-pass uses of the forward kernels (data gradients), called from bwd_kernels.cu ----
+// 1x1 conv: dA[2][B][hw][K] = dY[2][B][hw][N] * W^T   (W is [K][N] at w_off)
+int dgrad_pw(const float* params, long long net_stride, long long w_off, const float* dY, float* dA, int B, int hw,
+             int K, int N, void* stream) {
+  GemmArgs a = {};
+  a.in = dY; a.in_net_stride = (long long)B * hw * N;
+  a.params = params; a.net_stride = net_stride; a.w_off = w_off;
+  a.out = dA; a.out_net_stride = (long long)B * hw * K;
+  a.B = B; a.hw = hw; a.K = N; a.N = K; a.ln = 0;
+  a.raw_in = 1; a.w_trans = 1; a.ldw = N; a.no_bias = 1;
+  return launch_gemm<false>(a, (cudaStream_t)stream);
+}
+
+// grouped dilated convs: dA[2][B][hw][nk] = sum over branches of conv^T(dY[2][B][hw][cat]); returns
+// cudaErrorInvalidConfiguration for group shapes gconv3 does not cover
+int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const ResBlockLayout& L = c->rb[r];
+  const int hw = c->hw(), nk = c->nk, cat = c->cat;
+  CU_TRY(cudaMemsetAsync(dA, 0, sizeof(float) * 2 * (size_t)B * hw * nk, st));
+  GconvArgs a = {};
+  a.in = dY; a.in_net_stride = (long long)B * hw * cat; a.Cin = cat;
+  a.out = dA; a.out_net_stride = (long long)B * hw * nk; a.Cout = nk;
+  a.params = params; a.net_stride = c->net_stride;
+  a.B = B; a.h = c->h; a.w = c->w; a.ln = 0; a.ks = c->ks; a.bwd = 1;
+  a.n_br = (int)L.br.size();
+  for (int i = 0; i < a.n_br; ++i) {
+    const Branch& s = L.br[i];
+    a.br[i].dil = s.dil; a.br[i].groups = s.groups; a.br[i].gin = s.gin; a.br[i].gout = s.gout;
+    a.br[i].in_off = s.out_off; a.br[i].out_off = 0; a.br[i].w_off = s.w_off; a.br[i].b_off = s.b_off;
+  }
+  for (int i = 0; i < a.n_br; ++i) {
+    const int rc = launch_gconv3_branch(a, i, st);
+    if (rc == 1) return (int)cudaErrorInvalidConfiguration;
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 }  // namespace cnf

@@ -129,6 +129,22 @@ int cnf_prior_loss(const DLManagedTensor* zy, const DLManagedTensor* xy, const D
                    int x_d, double lambda_y, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
                    DLManagedTensor* loss4, void* stream);
 
+/* ---- training step: replaces the tf.GradientTape block of cFlow.train_step (M:1863-1871) --------------
+ * forward of log_loss with every s/t-net activation kept, then the hand-written backward pass.
+ * grads [param_count] is OVERWRITTEN with dL/dparams of loss4[0] (same flat layout as params); the other
+ * outputs are those of cnf_flow_log_loss.  workspace: cnf_plan_train_workspace_bytes(plan, B) bytes. */
+int64_t cnf_plan_train_workspace_bytes(const cnf_plan* p, int64_t batch);
+int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                           DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
+                           DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
+                           DLManagedTensor* workspace, void* stream);
+/* optimizer.apply_gradients with keras Adam (M:1874; C:567 / P:130: lr 3e-4, beta 0.9/0.999, eps 1e-7):
+ * one fused update of the flat parameter buffer; `step` counts from 1; grads are multiplied by
+ * grad_scale first (1/world_size after a data-parallel sum all-reduce). */
+int cnf_adam_step(DLManagedTensor* params, const DLManagedTensor* grads, DLManagedTensor* m, DLManagedTensor* v,
+                  int64_t step, double lr, double beta_1, double beta_2, double epsilon, double grad_scale,
+                  void* stream);
+
 /* coupling_layer.forward_and_Jacobian (M:1258-1328) / .backward (M:1333-1394) on one [B,H,W,D]
  * tensor; `out` must not alias `in`.  logdet [B] is ACCUMULATED into (caller zeroes it). */
 int cnf_coupling_forward(const cnf_coupling* c, const DLManagedTensor* u, const DLManagedTensor* params,
