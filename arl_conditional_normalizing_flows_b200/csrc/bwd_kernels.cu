@@ -461,8 +461,35 @@ __global__ void __launch_bounds__(256) wgrad_pw_kernel(const WgradPwArgs a) {
       }
     }
   }
-  if (!worker) return;
   float* gW = a.grads + (long long)net * a.net_stride + a.w_off;
+  float* gB = a.grads + (long long)net * a.net_stride + a.b_off;
+  if (a.teams > 1) {
+    // several teams hold partial sums of the same outputs: combine them in shared memory first
+    __syncthreads();
+    const int KP = a.rows * RK;
+    float* red_w = smem;               // [KP][NS]
+    float* red_b = smem + KP * NS;     // [NS]
+    for (int i = tid; i < KP * NS + NS; i += NT) smem[i] = 0.f;
+    __syncthreads();
+    if (worker) {
+#pragma unroll
+      for (int i = 0; i < RK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(red_w + (tk * RK + i) * NS + tn * 4 + j, acc[i][j]);
+      if (tk == 0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(red_b + tn * 4 + j, bacc[j]);
+    }
+    __syncthreads();
+    for (int i = tid; i < KP * NS; i += NT) {
+      const int k = i / NS, n = i % NS;
+      if (k < kt_len && n < nt_len) atomicAdd(gW + (long long)(k0 + k) * a.N + n0 + n, red_w[i]);
+    }
+    if (kt == 0)
+      for (int n = tid; n < nt_len; n += NT) atomicAdd(gB + n0 + n, red_b[n]);
+    return;
+  }
+  if (!worker) return;
 #pragma unroll
   for (int i = 0; i < RK; ++i) {
     const int k = tk * RK + i;
@@ -474,7 +501,6 @@ __global__ void __launch_bounds__(256) wgrad_pw_kernel(const WgradPwArgs a) {
     }
   }
   if (tk == 0 && kt == 0) {
-    float* gB = a.grads + (long long)net * a.net_stride + a.b_off;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = tn * 4 + j;
@@ -499,7 +525,8 @@ static int launch_wgrad_pw(WgradPwArgs a, cudaStream_t st) {
   const int want_ctas = std::max(1, 148 * 4 / (2 * a.k_tiles * a.n_tiles));
   a.items_per_cta = std::max(4, (a.n_items + want_ctas - 1) / want_ctas);
   const int chunks = (a.n_items + a.items_per_cta - 1) / a.items_per_cta;
-  const size_t smem = (size_t)WG_PT * ((a.rows * RK + 4) + a.cols * 4) * sizeof(float);
+  size_t smem = (size_t)WG_PT * ((a.rows * RK + 4) + a.cols * 4) * sizeof(float);
+  if (a.teams > 1) smem = std::max(smem, (size_t)(a.rows * RK + 1) * a.cols * 4 * sizeof(float));
   dim3 grid(chunks, a.k_tiles * a.n_tiles, 2);
   if (RK == 8) wgrad_pw_kernel<8><<<grid, NT, smem, st>>>(a);
   else wgrad_pw_kernel<4><<<grid, NT, smem, st>>>(a);
@@ -650,6 +677,343 @@ static int launch_wgrad3(Wgrad3Args a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-per-pixel kernels for the 3x3 convs that have a WIDE side (nk channels, spread over the lanes:
+// coalesced row loads/stores) and a NARROW side (c1 or c2 <= 24 channels, broadcast scalars):
+//   wgrad3_wide_kernel   weight + bias gradients of head (wide = LN(lrelu(x_R)) is cin, narrow = d raw is
+//                        cout, neighbour at p - off) and stem (wide = dX0 is cout, narrow = u1c gathered
+//                        through the mask from the saved flow state is cin, neighbour at p + off)
+//   head_dgrad_kernel    d(LN_f output)[p, ci] = sum_tap sum_co draw[p - off, co] W[tap][ci][co]
+//   stem_dgrad_kernel    G[u1 positions] += sum_net sum_tap sum_co dX0[p - off, co] W[tap][ci][co]
+// Each activation row is read exactly once; the kernels are HBM-bound (4*nk bytes per pixel and net).
+// ------------------------------------------------------------------------------------------
+struct Wgrad3WideArgs {
+  const float* wide;
+  long long wide_net_stride;
+  int CW, wide_act;             // wide_act: apply lrelu (+ LayerNorm) while loading (head)
+  const float* narrow;          // dense [2][B][hw][CN] (head) ...
+  long long narrow_net_stride;
+  FlowView view;                // ... or gathered from the flow state through `mask` (stem; same for both nets)
+  int mask, narrow_view, CN, sign;
+  int wide_is_ci;               // head: dW[tap][wide][narrow];  stem: dW[tap][narrow][wide]
+  const float* params;
+  float* grads;
+  long long net_stride, w_off, b_off, g_off, be_off;
+  const double* stats;
+  int B, h, w, ks, ln;
+};
+
+template <int WPL, int NC>
+__global__ void __launch_bounds__(256) wgrad3_wide_kernel(const Wgrad3WideArgs a) {
+  extern __shared__ __align__(16) float red_s[];   // [9][NC][CW]
+  __shared__ float bias_s[256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int net = blockIdx.z, n0 = blockIdx.y * NC;
+  const int nc = min(NC, a.CN - n0);
+  const int hw = a.h * a.w, pad = (a.ks - 1) / 2;
+  const int ch0 = lane * WPL;
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* gam = P + a.g_off;
+  const float* bet = P + a.be_off;
+  for (int i = tid; i < 9 * NC * a.CW; i += 256) red_s[i] = 0.f;
+  bias_s[tid] = 0.f;
+  float acc[9][NC][WPL];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int j = 0; j < WPL; ++j) acc[t][c][j] = 0.f;
+  float bw[WPL], bn[NC];
+#pragma unroll
+  for (int j = 0; j < WPL; ++j) bw[j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) bn[c] = 0.f;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.wide_act && a.ln) ln_coeffs(a.stats, (long long)net * a.B + b, (double)hw * (double)a.CW, mean, rstd);
+    const float* wsrc = a.wide + (long long)net * a.wide_net_stride + (long long)b * hw * a.CW;
+    const float* nsrc = a.narrow_view ? nullptr : a.narrow + (long long)net * a.narrow_net_stride + (long long)b * hw * a.CN;
+    for (int p = wid; p < hw; p += 8) {
+      const int y = p / a.w, x = p - y * a.w;
+      float wv[WPL];
+#pragma unroll
+      for (int j = 0; j < WPL; ++j) {
+        const int ch = ch0 + j;
+        float v = 0.f;
+        if (ch < a.CW) {
+          const long long e = (long long)p * a.CW + ch;
+          v = wsrc[e];
+          if (a.wide_act) {
+            v = lrelu(v);
+            if (a.ln) v = (v - mean) * rstd * gam[e] + bet[e];
+          }
+        }
+        wv[j] = v;
+      }
+      // all 9*NC neighbour scalars are fetched with predicated loads first (independent, in flight together)
+      float nv[9][NC];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + a.sign * (ky - pad);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x + a.sign * (kx - pad);
+          const bool ok = ky < a.ks && kx < a.ks && yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;   // warp-uniform
+          const int yc = ok ? yy : y, xc = ok ? xx : x;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const int cc = c < nc ? n0 + c : n0;
+            const float v = a.narrow_view ? a.view.base[comp_off(a.view, a.mask, b, yc, xc, cc)]
+                                          : nsrc[(long long)(yc * a.w + xc) * a.CN + cc];
+            nv[ky * 3 + kx][c] = (ok && c < nc) ? v : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int j = 0; j < WPL; ++j) acc[t][c][j] = fmaf(nv[t][c], wv[j], acc[t][c][j]);
+      if (pad * 3 + pad < 9) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) bn[c] += nv[4 * (pad != 0)][c];   // centre tap (index 4 for 3x3, 0 for 1x1)
+      }
+#pragma unroll
+      for (int j = 0; j < WPL; ++j) bw[j] += wv[j];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int j = 0; j < WPL; ++j)
+        if (ch0 + j < a.CW) atomicAdd(&red_s[(t * NC + c) * a.CW + ch0 + j], acc[t][c][j]);
+  // bias: head (wide_is_ci) -> sum of the narrow operand, stem -> sum of the wide operand (first narrow chunk only)
+  if (a.wide_is_ci) {
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) atomicAdd(&bias_s[c], bn[c]);
+  } else if (n0 == 0) {
+#pragma unroll
+    for (int j = 0; j < WPL; ++j)
+      if (ch0 + j < a.CW) atomicAdd(&bias_s[ch0 + j], bw[j]);
+  }
+  __syncthreads();
+  float* gW = a.grads + (long long)net * a.net_stride + a.w_off;
+  float* gB = a.grads + (long long)net * a.net_stride + a.b_off;
+  const int taps = a.ks * a.ks;
+  for (int i = tid; i < 9 * NC * a.CW; i += 256) {
+    const int ch = i % a.CW, c = (i / a.CW) % NC, t = i / (a.CW * NC);
+    const int ky = t / 3, kx = t % 3;
+    if (c >= nc || ky >= a.ks || kx >= a.ks) continue;
+    const int tap = ky * a.ks + kx;
+    const long long o = a.wide_is_ci ? ((long long)tap * a.CW + ch) * a.CN + n0 + c : ((long long)tap * a.CN + n0 + c) * a.CW + ch;
+    (void)taps;
+    atomicAdd(gW + o, red_s[i]);
+  }
+  if (a.wide_is_ci) {
+    if (tid < nc) atomicAdd(gB + n0 + tid, bias_s[tid]);
+  } else if (n0 == 0) {
+    if (tid < a.CW) atomicAdd(gB + tid, bias_s[tid]);
+  }
+}
+
+template <int WPL, int NC>
+static int launch_wgrad3_wide_t(const Wgrad3WideArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)9 * NC * a.CW * sizeof(float);
+  const int chunks = (a.CN + NC - 1) / NC;
+  const int gx = std::max(1, std::min(a.B, 148 * 4 / (2 * chunks) + 1));
+  dim3 grid(gx, chunks, 2);
+  wgrad3_wide_kernel<WPL, NC><<<grid, 256, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+// returns 1 when the shape is not covered (caller falls back to wgrad3_small_kernel)
+static int launch_wgrad3_wide(const Wgrad3WideArgs& a, cudaStream_t st) {
+  if (a.ks != 3 && a.ks != 1) return 1;
+  if (a.CW > 256) return 1;
+  if (a.CW <= 32) {
+    if (a.CN >= 4) return launch_wgrad3_wide_t<1, 4>(a, st);
+    if (a.CN >= 2) return launch_wgrad3_wide_t<1, 2>(a, st);
+    return launch_wgrad3_wide_t<1, 1>(a, st);
+  }
+  if (a.CW <= 64) {
+    if (a.CN >= 4) return launch_wgrad3_wide_t<2, 4>(a, st);
+    if (a.CN >= 2) return launch_wgrad3_wide_t<2, 2>(a, st);
+    return launch_wgrad3_wide_t<2, 1>(a, st);
+  }
+  if (a.CW <= 128) {
+    if (a.CN >= 2) return launch_wgrad3_wide_t<4, 2>(a, st);
+    return launch_wgrad3_wide_t<4, 1>(a, st);
+  }
+  return launch_wgrad3_wide_t<8, 1>(a, st);
+}
+
+struct Dgrad3Args {
+  const float* in;      // head: d raw [2][B][hw][CN];  stem: dX0 [2][B][hw][CW]
+  long long in_net_stride;
+  const float* params;
+  long long net_stride, w_off;
+  int B, h, w, CW, CN, ks;
+  float* out;           // head: [2][B][hw][CW]
+  long long out_net_stride;
+  FlowView view;        // stem: gradient buffer, positions of mask(., mask, compress=True)
+  int mask;
+};
+
+// head: CW = nk outputs over the lanes, CN = c2 broadcast inputs.  smem: W as [tap][co][ci].
+template <int WPL>
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const Dgrad3Args a) {
+  extern __shared__ __align__(16) float w_s[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int net = blockIdx.y;
+  const int hw = a.h * a.w, pad = (a.ks - 1) / 2, taps = a.ks * a.ks;
+  const float* W = a.params + (long long)net * a.net_stride + a.w_off;   // [tap][ci = CW][co = CN]
+  for (int i = tid; i < taps * a.CN * a.CW; i += 256) {
+    const int ci = i % a.CW, co = (i / a.CW) % a.CN, tap = i / (a.CW * a.CN);
+    w_s[i] = W[((long long)tap * a.CW + ci) * a.CN + co];
+  }
+  __syncthreads();
+  const int ch0 = lane * WPL;
+  const long long total = (long long)a.B * hw;
+  for (long long it = (long long)blockIdx.x * 8 + wid; it < total; it += (long long)gridDim.x * 8) {
+    const int b = (int)(it / hw), p = (int)(it - (long long)b * hw);
+    const int y = p / a.w, x = p - y * a.w;
+    const float* src = a.in + (long long)net * a.in_net_stride + (long long)b * hw * a.CN;
+    float o[WPL];
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) o[j] = 0.f;
+    for (int co = 0; co < a.CN; ++co) {
+      float dv[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y - (ky - pad);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x - (kx - pad);
+          const bool ok = ky < a.ks && kx < a.ks && yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
+          const float v = src[(long long)((ok ? yy : y) * a.w + (ok ? xx : x)) * a.CN + co];
+          dv[ky * 3 + kx] = ok ? v : 0.f;
+        }
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          if (ky < a.ks && kx < a.ks) {
+            const float* wt = w_s + ((ky * a.ks + kx) * a.CN + co) * a.CW;
+#pragma unroll
+            for (int j = 0; j < WPL; ++j)
+              if (ch0 + j < a.CW) o[j] = fmaf(dv[ky * 3 + kx], wt[ch0 + j], o[j]);
+          }
+        }
+    }
+    float* dst = a.out + (long long)net * a.out_net_stride + it * a.CW;
+#pragma unroll
+    for (int j = 0; j < WPL; ++j)
+      if (ch0 + j < a.CW) dst[ch0 + j] = o[j];
+  }
+}
+
+// stem: CW = nk inputs over the lanes, CN = c1 outputs.  Scatter form: every dX0 row is read ONCE; its 9*c1 dot
+// products with W[tap][ci][:] are reduced across the warp and added (atomics: neighbouring rows hit the same
+// pixels) into the u1 positions of the gradient buffer at q + off(tap).  smem: W [tap][ci][co] of this net.
+template <int WPL>
+__global__ void __launch_bounds__(256) stem_dgrad_kernel(const Dgrad3Args a) {
+  extern __shared__ __align__(16) float w_s[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int net = blockIdx.y;
+  const int hw = a.h * a.w, pad = (a.ks - 1) / 2, taps = a.ks * a.ks;
+  const int per_net = taps * a.CN * a.CW;
+  for (int i = tid; i < per_net; i += 256) w_s[i] = a.params[(long long)net * a.net_stride + a.w_off + i];
+  __syncthreads();
+  const int ch0 = lane * WPL;
+  const long long total = (long long)a.B * hw;
+  const float* src = a.in + (long long)net * a.in_net_stride;
+  for (long long it = (long long)blockIdx.x * 8 + wid; it < total; it += (long long)gridDim.x * 8) {
+    const int b = (int)(it / hw), p = (int)(it - (long long)b * hw);
+    const int y = p / a.w, x = p - y * a.w;
+    float dv[WPL];
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) dv[j] = ch0 + j < a.CW ? src[it * a.CW + ch0 + j] : 0.f;
+    for (int ci = 0; ci < a.CN; ++ci) {
+      float part[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float sacc = 0.f;
+        if (t < taps) {
+          const float* wt = w_s + (t * a.CN + ci) * a.CW;
+#pragma unroll
+          for (int j = 0; j < WPL; ++j)
+            if (ch0 + j < a.CW) sacc = fmaf(dv[j], wt[ch0 + j], sacc);
+        }
+        part[t] = sacc;
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) part[t] = warp_sum(part[t]);
+      // dX0[q] * W[tap] contributes to du1 at q + off(tap):  da[q', ci] = sum_tap dy[q' - off(tap)] W[tap]
+      if (lane < taps) {
+        float mine = part[0];
+#pragma unroll
+        for (int t = 1; t < 9; ++t) mine = lane == t ? part[t] : mine;
+        const int ky = lane / a.ks, kx = lane - ky * a.ks;
+        const int yy = y + (ky - pad), xx = x + (kx - pad);
+        if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
+          atomicAdd(a.view.base + comp_off(a.view, a.mask, b, yy, xx, ci), mine);
+      }
+    }
+  }
+}
+
+static int launch_head_dgrad(const Dgrad3Args& a, cudaStream_t st) {
+  const size_t smem = (size_t)a.ks * a.ks * a.CN * a.CW * sizeof(float);
+  if (a.CW > 256 || smem > 160 * 1024 || (a.ks != 3 && a.ks != 1)) return 1;
+  const long long total = (long long)a.B * a.h * a.w;
+  dim3 grid((unsigned)std::min<long long>((total + 7) / 8, 148 * 8), 2);
+#define CNF_LAUNCH_HD(WPL)                                                                                     \
+  {                                                                                                            \
+    static size_t configured = 0;                                                                              \
+    if (smem > configured && smem > 48 * 1024) {                                                               \
+      CU_TRY(cudaFuncSetAttribute(head_dgrad_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                       \
+    }                                                                                                          \
+    head_dgrad_kernel<WPL><<<grid, 256, smem, st>>>(a);                                                        \
+  }
+  if (a.CW <= 32) CNF_LAUNCH_HD(1)
+  else if (a.CW <= 64) CNF_LAUNCH_HD(2)
+  else if (a.CW <= 128) CNF_LAUNCH_HD(4)
+  else CNF_LAUNCH_HD(8)
+#undef CNF_LAUNCH_HD
+  return (int)cudaGetLastError();
+}
+
+static int launch_stem_dgrad(const Dgrad3Args& a, cudaStream_t st) {
+  const size_t smem = (size_t)a.ks * a.ks * a.CN * a.CW * sizeof(float);
+  if (a.CW > 256 || smem > 160 * 1024 || (a.ks != 3 && a.ks != 1)) return 1;
+  const long long total = (long long)a.B * a.h * a.w;
+  dim3 grid((unsigned)std::min<long long>((total + 7) / 8, 148 * 8), 2);
+#define CNF_LAUNCH_SD(WPL)                                                                                     \
+  {                                                                                                            \
+    static size_t configured = 0;                                                                              \
+    if (smem > configured && smem > 48 * 1024) {                                                               \
+      CU_TRY(cudaFuncSetAttribute(stem_dgrad_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                       \
+    }                                                                                                          \
+    stem_dgrad_kernel<WPL><<<grid, 256, smem, st>>>(a);                                                        \
+  }
+  if (a.CW <= 32) CNF_LAUNCH_SD(1)
+  else if (a.CW <= 64) CNF_LAUNCH_SD(2)
+  else if (a.CW <= 128) CNF_LAUNCH_SD(4)
+  else CNF_LAUNCH_SD(8)
+#undef CNF_LAUNCH_SD
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Grouped dilated 3x3 weight gradient of ONE dilation branch (F:387-413, F:565-590):
 //   dW[g][ky][kx][ci][co] += sum_{b,q} a2[b, q + d*off(ky,kx), g*G + ci] dy[b, q, out_off + g*G + co]
 // a2 = LN2(lrelu(y1)) applied while staging.  Thread = (channel c = g*G + ci, ky): 3 x G accumulators.
@@ -668,8 +1032,8 @@ struct WgradGcArgs {
   int TH, TW, tiles_y, tiles_x, SB, teams;
 };
 
-template <int G>
-__global__ void __launch_bounds__(768) wgrad_gconv_kernel(const WgradGcArgs a) {
+template <int G, int KYS>   // KYS = 3: a thread owns all 9 taps of its channel; KYS = 1: one kernel row (wide groups)
+__global__ void __launch_bounds__(KYS == 3 ? 256 : 768) wgrad_gconv_kernel(const WgradGcArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, NT = blockDim.x;
   const int net = blockIdx.z;
@@ -680,26 +1044,27 @@ __global__ void __launch_bounds__(768) wgrad_gconv_kernel(const WgradGcArgs a) {
   const int th = min(a.TH, a.h - y0), tw = min(a.TW, a.w - x0);
   const int d = a.dil;
   const int SH = a.TH + 2 * d, SW = a.TW + 2 * d;
-  float* a_s = smem;                        // [SH][SW][Cb]
-  float* d_s = smem + SH * SW * Cb;         // [TH][TW][Cb]
+  float* a_s = smem;                                   // [SH][SW][Cb]
+  float* d_s = smem + ((SH * SW * Cb + 3) & ~3);       // [TH][TW][Cb]
   const float* P = a.params + (long long)net * a.net_stride;
   const float* gam = P + a.g_off;
   const float* bet = P + a.be_off;
-  const int tpt = 3 * Cb;
+  const int tpt = (3 / KYS) * Cb;
   const int team = tid / tpt, t = tid % tpt;
   const bool worker = team < a.teams;
-  const int c = t % Cb, ky = t / Cb;
+  const int c = t % Cb, ky0 = t / Cb;                  // ky0 = 0 when KYS == 3
   const int g = c / G;
+  const bool vec = (Cb % 4 == 0) && (a.nk % 4 == 0) && (a.cat % 4 == 0) && (a.out_off % 4 == 0);
 
-  float acc[3][G];
+  float acc[KYS * 3][G];
   float bacc[G];
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < KYS * 3; ++k)
 #pragma unroll
     for (int j = 0; j < G; ++j) acc[k][j] = 0.f;
 #pragma unroll
   for (int j = 0; j < G; ++j) bacc[j] = 0.f;
-  const bool do_bias = worker && ky == 0 && (c % G) == 0;
+  const bool do_bias = worker && ky0 == 0 && (c % G) == 0;
 
   const int b0 = sb * a.SB, b1 = min(a.B, b0 + a.SB);
   for (int b = b0; b < b1; ++b) {
@@ -708,39 +1073,82 @@ __global__ void __launch_bounds__(768) wgrad_gconv_kernel(const WgradGcArgs a) {
     const float* xs = a.x + (long long)net * a.x_net_stride + (long long)b * a.h * a.w * a.nk;
     const float* ds = a.dy + (long long)net * a.dy_net_stride + (long long)b * a.h * a.w * a.cat + a.out_off;
     __syncthreads();
-    for (int idx = tid; idx < SH * SW * Cb; idx += NT) {
-      const int ch = idx % Cb, pix = idx / Cb;
-      const int gy = y0 - d + pix / SW, gx = x0 - d + pix % SW;
-      float v = 0.f;
-      if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) {
-        const long long e = ((long long)gy * a.w + gx) * a.nk + ch;
-        v = lrelu(xs[e]);
-        if (a.ln) v = (v - mean) * rstd * gam[e] + bet[e];
+    if (vec) {
+      const int q = Cb >> 2;
+      for (int idx = tid; idx < SH * SW * q; idx += NT) {
+        const int cq = idx % q, pix = idx / q;
+        const int sy = pix / SW, sx = pix - sy * SW;
+        const int gy = y0 - d + sy, gx = x0 - d + sx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) {
+          const long long e = ((long long)gy * a.w + gx) * a.nk + 4 * cq;
+          v = ld4(xs + e);
+          v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w);
+          if (a.ln) {
+            const float4 gg = ld4(gam + e), be = ld4(bet + e);
+            v.x = (v.x - mean) * rstd * gg.x + be.x;
+            v.y = (v.y - mean) * rstd * gg.y + be.y;
+            v.z = (v.z - mean) * rstd * gg.z + be.z;
+            v.w = (v.w - mean) * rstd * gg.w + be.w;
+          }
+        }
+        st4(a_s + pix * Cb + 4 * cq, v);
       }
-      a_s[idx] = v;
-    }
-    for (int idx = tid; idx < a.TH * a.TW * Cb; idx += NT) {
-      const int ch = idx % Cb, pix = idx / Cb;
-      const int py = pix / a.TW, px = pix % a.TW;
-      float v = 0.f;
-      if (py < th && px < tw) v = ds[((long long)(y0 + py) * a.w + x0 + px) * a.cat + ch];
-      d_s[idx] = v;
+      for (int idx = tid; idx < a.TH * a.TW * q; idx += NT) {
+        const int cq = idx % q, pix = idx / q;
+        const int py = pix / a.TW, px = pix - py * a.TW;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (py < th && px < tw) v = ld4(ds + ((long long)(y0 + py) * a.w + x0 + px) * a.cat + 4 * cq);
+        st4(d_s + pix * Cb + 4 * cq, v);
+      }
+    } else {
+      for (int idx = tid; idx < SH * SW * Cb; idx += NT) {
+        const int ch = idx % Cb, pix = idx / Cb;
+        const int gy = y0 - d + pix / SW, gx = x0 - d + pix % SW;
+        float v = 0.f;
+        if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) {
+          const long long e = ((long long)gy * a.w + gx) * a.nk + ch;
+          v = lrelu(xs[e]);
+          if (a.ln) v = (v - mean) * rstd * gam[e] + bet[e];
+        }
+        a_s[idx] = v;
+      }
+      for (int idx = tid; idx < a.TH * a.TW * Cb; idx += NT) {
+        const int ch = idx % Cb, pix = idx / Cb;
+        const int py = pix / a.TW, px = pix % a.TW;
+        float v = 0.f;
+        if (py < th && px < tw) v = ds[((long long)(y0 + py) * a.w + x0 + px) * a.cat + ch];
+        d_s[idx] = v;
+      }
     }
     __syncthreads();
     if (worker) {
       const int np = th * tw;
       for (int p = team; p < np; p += a.teams) {
-        const int py = p / tw, px = p % tw;
+        const int py = p / tw, px = p - py * tw;
         const float* dp = d_s + (py * a.TW + px) * Cb + g * G;
         float dv[G];
+        if (G % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) dv[j] = dp[j];
-        const float* ap = a_s + ((py + ky * d) * SW + px) * Cb + c;
+          for (int j = 0; j < G; j += 4) {
+            const float4 t4 = ld4(dp + j);
+            dv[j] = t4.x; dv[j + 1] = t4.y; dv[j + 2] = t4.z; dv[j + 3] = t4.w;
+          }
+        } else if (G == 2) {
+          const float2 t2 = *reinterpret_cast<const float2*>(dp);
+          dv[0] = t2.x; dv[G - 1] = t2.y;
+        } else {
+          dv[0] = dp[0];
+        }
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float av = ap[kx * d * Cb];
+        for (int kyi = 0; kyi < KYS; ++kyi) {
+          const float* ap = a_s + ((py + (ky0 + kyi) * d) * SW + px) * Cb + c;
 #pragma unroll
-          for (int j = 0; j < G; ++j) acc[kx][j] = fmaf(av, dv[j], acc[kx][j]);
+          for (int kx = 0; kx < 3; ++kx) {
+            const float av = ap[kx * d * Cb];
+#pragma unroll
+            for (int j = 0; j < G; ++j) acc[kyi * 3 + kx][j] = fmaf(av, dv[j], acc[kyi * 3 + kx][j]);
+          }
         }
         if (do_bias) {
 #pragma unroll
@@ -749,41 +1157,55 @@ __global__ void __launch_bounds__(768) wgrad_gconv_kernel(const WgradGcArgs a) {
       }
     }
   }
-  if (!worker) return;
-  const int ci = c % G;
-  float* gW = a.grads + (long long)net * a.net_stride + a.w_off;   // packed [group][ky][kx][gin][gout]
+  // reduce the teams through shared memory (the staging tiles are dead), then one global atomic per output and CTA
+  __syncthreads();
+  const int n_out = Cb * 9 * G;                        // packed [group][ky][kx][gin][gout] == [c / G][tap][c % G][co]
+  float* red_w = smem;
+  float* red_b = smem + n_out;
+  for (int i = tid; i < n_out + Cb; i += NT) smem[i] = 0.f;
+  __syncthreads();
+  if (worker) {
+    const int ci = c % G;
 #pragma unroll
-  for (int kx = 0; kx < 3; ++kx)
+    for (int kyi = 0; kyi < KYS; ++kyi)
 #pragma unroll
-    for (int j = 0; j < G; ++j)
-      atomicAdd(gW + (((long long)g * 9 + ky * 3 + kx) * G + ci) * G + j, acc[kx][j]);
-  if (do_bias) {
-    float* gB = a.grads + (long long)net * a.net_stride + a.b_off;
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-    for (int j = 0; j < G; ++j) atomicAdd(gB + g * G + j, bacc[j]);
+        for (int j = 0; j < G; ++j)
+          atomicAdd(red_w + ((g * 9 + (ky0 + kyi) * 3 + kx) * G + ci) * G + j, acc[kyi * 3 + kx][j]);
+    if (do_bias) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) atomicAdd(red_b + g * G + j, bacc[j]);
+    }
   }
+  __syncthreads();
+  float* gW = a.grads + (long long)net * a.net_stride + a.w_off;
+  float* gB = a.grads + (long long)net * a.net_stride + a.b_off;
+  for (int i = tid; i < n_out; i += NT) atomicAdd(gW + i, red_w[i]);
+  for (int i = tid; i < Cb; i += NT) atomicAdd(gB + i, red_b[i]);
 }
 
-template <int G>
+template <int G, int KYS>
 static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   const int Cb = a.groups * G, d = a.dil;
-  const int tpt = 3 * Cb;
-  if (tpt > 768) return (int)cudaErrorInvalidConfiguration;
+  const int tpt = (3 / KYS) * Cb;
+  const int max_nt = KYS == 3 ? 256 : 768;
+  if (tpt > max_nt) return 1;
   a.TW = std::min(a.w, 32);
   a.TH = std::min(a.h, 32);
-  auto bytes = [&](int th) { return (size_t)((th + 2 * d) * (a.TW + 2 * d) + th * a.TW) * Cb * sizeof(float); };
+  auto bytes = [&](int th) { return (size_t)((((th + 2 * d) * (a.TW + 2 * d) * Cb + 3) & ~3) + th * a.TW * Cb) * sizeof(float); };
   while (a.TH > 1 && bytes(a.TH) > 72 * 1024) --a.TH;
   if (bytes(a.TH) > 220 * 1024) return (int)cudaErrorInvalidConfiguration;
   a.tiles_y = (a.h + a.TH - 1) / a.TH;
   a.tiles_x = (a.w + a.TW - 1) / a.TW;
   const int tiles = a.tiles_y * a.tiles_x;
-  a.teams = std::max(1, std::min(a.TH * a.TW, 384 / tpt));
+  a.teams = std::max(1, std::min(a.TH * a.TW, (KYS == 3 ? 256 : 384) / tpt));
   const int NT = std::max(64, ((tpt * a.teams + 31) / 32) * 32);
   const int want = std::max(1, 148 * 6 / (2 * tiles));
   a.SB = std::max(1, (a.B + want - 1) / want);
   const int sbs = (a.B + a.SB - 1) / a.SB;
-  const size_t smem = bytes(a.TH);
-  auto kern = wgrad_gconv_kernel<G>;
+  const size_t smem = std::max(bytes(a.TH), (size_t)(Cb * 9 * G + Cb) * sizeof(float));
+  auto kern = wgrad_gconv_kernel<G, KYS>;
   static size_t configured = 0;
   if (smem > configured && smem > 48 * 1024) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -794,13 +1216,23 @@ static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+template <int G>
+static int launch_wgrad_gconv_g(const WgradGcArgs& a, cudaStream_t st) {
+  if (G <= 8) {
+    const int rc = launch_wgrad_gconv_t<G, 3>(a, st);
+    if (rc != 1) return rc;
+  }
+  const int rc = launch_wgrad_gconv_t<G, 1>(a, st);
+  return rc == 1 ? (int)cudaErrorInvalidConfiguration : rc;
+}
+
 static int launch_wgrad_gconv(const WgradGcArgs& a, int G, cudaStream_t st) {
   switch (G) {
-    case 1: return launch_wgrad_gconv_t<1>(a, st);
-    case 2: return launch_wgrad_gconv_t<2>(a, st);
-    case 4: return launch_wgrad_gconv_t<4>(a, st);
-    case 8: return launch_wgrad_gconv_t<8>(a, st);
-    case 16: return launch_wgrad_gconv_t<16>(a, st);
+    case 1: return launch_wgrad_gconv_g<1>(a, st);
+    case 2: return launch_wgrad_gconv_g<2>(a, st);
+    case 4: return launch_wgrad_gconv_g<4>(a, st);
+    case 8: return launch_wgrad_gconv_g<8>(a, st);
+    case 16: return launch_wgrad_gconv_g<16>(a, st);
     default: return (int)cudaErrorInvalidConfiguration;
   }
 }
@@ -963,15 +1395,32 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
     a.params = params; a.grads = grads; a.net_stride = ns; a.w_off = c->head_w; a.b_off = c->head_b;
     a.g_off = c->lnf_g; a.be_off = c->lnf_b; a.stats = stats(3 * R);
     a.B = B; a.h = c->h; a.w = c->w; a.CI = nk; a.CO = c2; a.ks = c->ks; a.ln = c->ln;
-    CU_TRY(launch_wgrad3(a, st));
-    Conv3tArgs t = {};
-    t.in = DR; t.in_net_stride = (long long)B * hw * c2;
-    t.params = params; t.net_stride = ns; t.w_off = c->head_w;
-    t.B = B; t.h = c->h; t.w = c->w; t.CI = nk; t.CO = c2; t.ks = c->ks; t.mode = 0;
-    t.out = GA; t.out_net_stride = (long long)B * hw * nk;
-    const long long total = 2LL * B * hw * nk;
-    conv3t_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t);
-    CU_TRY(cudaGetLastError());
+    Wgrad3WideArgs ww = {};
+    ww.wide = sv.X[R]; ww.wide_net_stride = (long long)B * hw * nk; ww.CW = nk; ww.wide_act = 1;
+    ww.narrow = DR; ww.narrow_net_stride = (long long)B * hw * c2; ww.CN = c2; ww.sign = -1; ww.wide_is_ci = 1;
+    ww.params = params; ww.grads = grads; ww.net_stride = ns; ww.w_off = c->head_w; ww.b_off = c->head_b;
+    ww.g_off = c->lnf_g; ww.be_off = c->lnf_b; ww.stats = stats(3 * R);
+    ww.B = B; ww.h = c->h; ww.w = c->w; ww.ks = c->ks; ww.ln = c->ln;
+    int rc = launch_wgrad3_wide(ww, st);
+    if (rc == 1) rc = launch_wgrad3(a, st);
+    CU_TRY(rc);
+    Dgrad3Args dg = {};
+    dg.in = DR; dg.in_net_stride = (long long)B * hw * c2;
+    dg.params = params; dg.net_stride = ns; dg.w_off = c->head_w;
+    dg.B = B; dg.h = c->h; dg.w = c->w; dg.CW = nk; dg.CN = c2; dg.ks = c->ks;
+    dg.out = GA; dg.out_net_stride = (long long)B * hw * nk;
+    rc = launch_head_dgrad(dg, st);
+    if (rc == 1) {
+      Conv3tArgs t = {};
+      t.in = DR; t.in_net_stride = (long long)B * hw * c2;
+      t.params = params; t.net_stride = ns; t.w_off = c->head_w;
+      t.B = B; t.h = c->h; t.w = c->w; t.CI = nk; t.CO = c2; t.ks = c->ks; t.mode = 0;
+      t.out = GA; t.out_net_stride = (long long)B * hw * nk;
+      const long long total = 2LL * B * hw * nk;
+      conv3t_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t);
+      rc = (int)cudaGetLastError();
+    }
+    CU_TRY(rc);
     CU_TRY(ln_backward(GA, sv.X[R], GX, params, grads, ns, c->lnf_g, c->lnf_b, stats(3 * R), bst, B, (long long)hw * nk,
                        c->ln, 0, st));
   }
@@ -1028,15 +1477,31 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
     a.dy = GX; a.dy_net_stride = (long long)B * hw * nk;
     a.params = params; a.grads = grads; a.net_stride = ns; a.w_off = c->stem_w; a.b_off = c->stem_b;
     a.B = B; a.h = c->h; a.w = c->w; a.CI = c->c1; a.CO = nk; a.ks = c->ks; a.ln = 0;
-    CU_TRY(launch_wgrad3(a, st));
-    Conv3tArgs t = {};
-    t.in = GX; t.in_net_stride = (long long)B * hw * nk;
-    t.params = params; t.net_stride = ns; t.w_off = c->stem_w;
-    t.B = B; t.h = c->h; t.w = c->w; t.CI = c->c1; t.CO = nk; t.ks = c->ks; t.mode = 1;
-    t.view = g_view; t.mask = c->mask;
-    const long long total = (long long)B * hw * c->c1;
-    conv3t_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t);
-    CU_TRY(cudaGetLastError());
+    Wgrad3WideArgs ww = {};
+    ww.wide = GX; ww.wide_net_stride = (long long)B * hw * nk; ww.CW = nk; ww.wide_act = 0;
+    ww.view = s_view; ww.mask = c->mask; ww.narrow_view = 1; ww.CN = c->c1; ww.sign = +1; ww.wide_is_ci = 0;
+    ww.params = params; ww.grads = grads; ww.net_stride = ns; ww.w_off = c->stem_w; ww.b_off = c->stem_b;
+    ww.B = B; ww.h = c->h; ww.w = c->w; ww.ks = c->ks; ww.ln = 0;
+    int rc = launch_wgrad3_wide(ww, st);
+    if (rc == 1) rc = launch_wgrad3(a, st);
+    CU_TRY(rc);
+    Dgrad3Args dg = {};
+    dg.in = GX; dg.in_net_stride = (long long)B * hw * nk;
+    dg.params = params; dg.net_stride = ns; dg.w_off = c->stem_w;
+    dg.B = B; dg.h = c->h; dg.w = c->w; dg.CW = nk; dg.CN = c->c1; dg.ks = c->ks;
+    dg.view = g_view; dg.mask = c->mask;
+    rc = launch_stem_dgrad(dg, st);
+    if (rc == 1) {
+      Conv3tArgs t = {};
+      t.in = GX; t.in_net_stride = (long long)B * hw * nk;
+      t.params = params; t.net_stride = ns; t.w_off = c->stem_w;
+      t.B = B; t.h = c->h; t.w = c->w; t.CI = c->c1; t.CO = nk; t.ks = c->ks; t.mode = 1;
+      t.view = g_view; t.mask = c->mask;
+      const long long total = (long long)B * hw * c->c1;
+      conv3t_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t);
+      rc = (int)cudaGetLastError();
+    }
+    CU_TRY(rc);
   }
   return 0;
 }
