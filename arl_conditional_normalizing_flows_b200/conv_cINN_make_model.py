@@ -663,16 +663,13 @@ class cFlow:
     def train_step(self, xy):
         """cFlow.train_step (M:1850-1880): gradients of log_loss, optimizer.apply_gradients, metric trackers.
         Data-parallel (torch.distributed initialised): one sum all-reduce of the flat gradient buffer over
-        NCCL, scaled by 1/world_size inside the fused Adam update."""
+        NCCL (sharding.allreduce_mean_gradients); the reported metrics are this rank's shard's."""
         if self.optimizer is None:
             raise RuntimeError("train_step: call model.compile(optimizer=Adam(...)) first")   # keras raises too
+        from .sharding import allreduce_mean_gradients
         four, grads = self.loss_and_grad(xy)
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            if world > 1:
-                torch.distributed.all_reduce(grads)
-        self.optimizer.apply_gradients(self.params, grads, grad_scale=1.0 / world)
+        allreduce_mean_gradients(grads, xy.shape[0])
+        self.optimizer.apply_gradients(self.params, grads)
         return self._update_trackers(four)
 
     def fit(self, batches, epochs=1, verbose=0):

@@ -310,6 +310,14 @@ def run_ours(args):
     law_gbs = 12 * ul.numel() / (ms_law * 1e-3) / 1e9
     del ul, sl, tl_, vl
 
+    # ---- training step: loss_and_grad + gradient all-reduce (NCCL, N>1) + fused Adam on the same
+    # batch shape.  Reported in `config` beside the headline metric; run last because it updates the weights.
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam
+    model.compile(optimizer=Adam(3e-4))
+    Kt = max(1, min(K, 10))
+    ms_train = timed(lambda i: model.train_step(xs_d[i % NBUF]), Kt, 2)
+    train_ws_gib = model._train_ws.numel() / 2 ** 30
+
     n_coupling = len(model.coupling_layers)
     launches_per_dir = sum(2 + 3 * l._info.R for l in model.coupling_layers)
     launches_step = (launches_per_dir + 3) + launches_per_dir     # fwd (+logdet, prior, finalize) + inverse
@@ -328,7 +336,12 @@ def run_ours(args):
                        "sample_images_per_s": B * world * K / (ms_samp * 1e-3),
                        "coupling_law_kernel": {"shape": [512, 128, 128, 4], "ms": ms_law, "GB/s": law_gbs,
                                                "frac_of_hbm_peak": law_gbs / hbm_peak, "bytes_per_element": 12},
-                       "parallelism": f"batch-sharded x{world}, no collective"},
+                       "train_step": {"images_per_s": B * world * Kt / (ms_train * 1e-3), "ms_per_step": ms_train / Kt,
+                                      "steps": Kt, "what": "cFlow.train_step: forward with saved activations, hand-written "
+                                      "backward, flat-gradient all-reduce (NCCL when N>1), fused Adam; batch "
+                                      f"{B}/GPU", "activation_workspace_GiB": train_ws_gib},
+                       "parallelism": f"batch-sharded x{world}; eval/sampling: no collective; training: one gradient "
+                                      "all-reduce per step"},
             "e2e": {"value": imgs * K / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": 2 * B * H * W * D * 4, "d2h_bytes_per_step": (4 + 3 * B) * 4 + B * H * W * D * 4},
             "gpu_launches": launches_step * K,

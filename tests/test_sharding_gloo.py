@@ -13,7 +13,8 @@ from oracle.flow_torch import FlowOracle
 from oracle.weights import init_weights, synth_inputs
 
 pytest.importorskip("arl_conditional_normalizing_flows_b200")
-from arl_conditional_normalizing_flows_b200.sharding import shard_bounds, global_loss  # noqa: E402
+from arl_conditional_normalizing_flows_b200.sharding import (allreduce_mean_gradients, global_loss,  # noqa: E402
+                                                             shard_bounds)
 
 CFG = dict(io_shape=[8, 8, 3], x_d=2, squeeze_factor_block_list=[1, 0], ResNeXt_block_list=[1, 1],
            num_kernels_list=[16, 8], cardinality_list=[2, 2])
@@ -67,3 +68,52 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- data-parallel training: one all-reduce of the flat gradient buffer -----------------------
+def _flat(grads):
+    return np.concatenate([np.asarray(g[net][k], np.float64).reshape(-1) for g in grads for net in ('A', 'b')
+                           for k in sorted(g[net])])
+
+
+def _grad_worker(rank, world, port, B, q):
+    from oracle.grad_torch import loss_and_grads
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    o = FlowOracle(**CFG, dtype=torch.float64)
+    o.set_weights(init_weights(o.plan, 'rand', seed=3))
+    x = synth_inputs('noise:8x8x3', B, seed=4).astype(np.float64)
+    lo, hi = shard_bounds(B, rank, world)
+    _, grads = loss_and_grads(o, x[lo:hi])
+    flat = torch.from_numpy(_flat(grads))
+    allreduce_mean_gradients(flat, hi - lo)
+    q.put((rank, flat.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [6, 5])      # even and uneven shards
+def test_two_rank_gradient_allreduce_equals_full_batch_gradient(B):
+    from oracle.grad_torch import loss_and_grads
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = FlowOracle(**CFG, dtype=torch.float64)
+    o.set_weights(init_weights(o.plan, 'rand', seed=3))
+    _, want = loss_and_grads(o, synth_inputs('noise:8x8x3', B, seed=4).astype(np.float64))
+    want = _flat(want)
+    for _, got in res:
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    np.testing.assert_array_equal(res[0][1], res[1][1])      # every rank applies the identical update
