@@ -5,6 +5,8 @@
 // M:1800-1848.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "cnf_internal.h"
 #include "device_utils.cuh"
 
@@ -95,6 +97,94 @@ __global__ void __launch_bounds__(256) coupling_law_kernel(const float* __restri
   }
 }
 
+// Fast paths (the shapes the flow produces): 4 consecutive channels of one pixel per thread, no integer
+// division by runtime values on the channel masks (even D: the compressed index of element e is e >> 1),
+// 128-bit loads of u and 64/128-bit loads of s and t, LAW_U independent items per thread in flight.
+constexpr int LAW_U = 4;
+
+template <int MASK>   // 2 or 3, D % 4 == 0
+__global__ void __launch_bounds__(256) coupling_law_chan_kernel(const float4* __restrict__ u, const float2* __restrict__ s,
+                                                                const float2* __restrict__ t, float4* __restrict__ v,
+                                                                float* __restrict__ logdet, int n4, int inverse) {
+  __shared__ float red[64];
+  const int b = blockIdx.y;
+  const float4* ub = u + (long long)b * n4;
+  const float2* sb = s + (long long)b * n4;
+  const float2* tb = t + (long long)b * n4;
+  float4* vb = v + (long long)b * n4;
+  float4 x[LAW_U];
+  float2 sv[LAW_U], tv[LAW_U];
+  int idx[LAW_U];
+#pragma unroll
+  for (int k = 0; k < LAW_U; ++k) {
+    idx[k] = (blockIdx.x * LAW_U + k) * 256 + threadIdx.x;
+    if (idx[k] < n4) {
+      x[k] = __ldcs(ub + idx[k]);
+      sv[k] = __ldcs(sb + idx[k]);
+      tv[k] = __ldcs(tb + idx[k]);
+    }
+  }
+  float ld = 0.f;
+#pragma unroll
+  for (int k = 0; k < LAW_U; ++k) {
+    if (idx[k] < n4) {
+      float4 o = x[k];
+      if (MASK == 2) {   // even channels pass through, odd channels are transformed
+        o.y = law_apply(o.y, sv[k].x, tv[k].x, inverse);
+        o.w = law_apply(o.w, sv[k].y, tv[k].y, inverse);
+      } else {
+        o.x = law_apply(o.x, sv[k].x, tv[k].x, inverse);
+        o.z = law_apply(o.z, sv[k].y, tv[k].y, inverse);
+      }
+      ld += sv[k].x + sv[k].y;
+      __stcs(vb + idx[k], o);
+    }
+  }
+  if (logdet) {
+    double d1, d2;
+    block_sum2(ld, 0.f, red, d1, d2);
+    if (threadIdx.x == 0) atomicAdd(logdet + b, (float)d1);
+  }
+}
+
+// checkerboard masks, D % 4 == 0: a float4 lies inside one pixel, so it is either copied or transformed whole
+__global__ void __launch_bounds__(256) coupling_law_cb_kernel(const float4* __restrict__ u, const float* __restrict__ s,
+                                                              const float* __restrict__ t, float4* __restrict__ v,
+                                                              float* __restrict__ logdet, LawGeom g, int n4, int ns_per) {
+  __shared__ float red[64];
+  const int b = blockIdx.y;
+  const float4* ub = u + (long long)b * n4;
+  const float* sb = s + (long long)b * ns_per;
+  const float* tb = t + (long long)b * ns_per;
+  float4* vb = v + (long long)b * n4;
+  const int q = g.D >> 2;
+  float ld = 0.f;
+#pragma unroll
+  for (int k = 0; k < LAW_U; ++k) {
+    const int i = (blockIdx.x * LAW_U + k) * 256 + threadIdx.x;
+    if (i >= n4) continue;
+    float4 o = __ldcs(ub + i);
+    const int px = i / q, cq = i - px * q;
+    const int y = px / g.W, x = px - y * g.W;
+    if (((y + x) & 1) != g.mask) {
+      const int si = (((y >> 1) * g.w) + (x >> 1)) * g.c2 + (y & 1) * g.D + 4 * cq;
+      const float4 sv = __ldcs(reinterpret_cast<const float4*>(sb + si));
+      const float4 tv = __ldcs(reinterpret_cast<const float4*>(tb + si));
+      o.x = law_apply(o.x, sv.x, tv.x, g.inverse);
+      o.y = law_apply(o.y, sv.y, tv.y, g.inverse);
+      o.z = law_apply(o.z, sv.z, tv.z, g.inverse);
+      o.w = law_apply(o.w, sv.w, tv.w, g.inverse);
+      ld += (sv.x + sv.y) + (sv.z + sv.w);
+    }
+    __stcs(vb + i, o);
+  }
+  if (logdet) {
+    double d1, d2;
+    block_sum2(ld, 0.f, red, d1, d2);
+    if (threadIdx.x == 0) atomicAdd(logdet + b, (float)d1);
+  }
+}
+
 int launch_coupling_law(const float* u, const float* s, const float* t, float* v, float* logdet, int B, int H,
                         int W, int D, int mask, int inverse, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -105,6 +195,19 @@ int launch_coupling_law(const float* u, const float* s, const float* t, float* v
   else { g.h = H; g.w = W; g.c2 = mc == 2 ? (D + 1) / 2 : D / 2; }
   const int n_per = H * W * D, ns_per = g.h * g.w * g.c2;
   if (logdet) CU_TRY(cudaMemsetAsync(logdet, 0, sizeof(float) * B, st));
+  if (D % 4 == 0 && B <= 65535 && ((uintptr_t)s & 15) == 0 && ((uintptr_t)t & 15) == 0) {
+    const int n4 = n_per / 4;
+    dim3 grid((n4 + 256 * LAW_U - 1) / (256 * LAW_U), B);
+    const float4* u4 = reinterpret_cast<const float4*>(u);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    if (mask == 2)
+      coupling_law_chan_kernel<2><<<grid, 256, 0, st>>>(u4, reinterpret_cast<const float2*>(s), reinterpret_cast<const float2*>(t), v4, logdet, n4, inverse);
+    else if (mask == 3)
+      coupling_law_chan_kernel<3><<<grid, 256, 0, st>>>(u4, reinterpret_cast<const float2*>(s), reinterpret_cast<const float2*>(t), v4, logdet, n4, inverse);
+    else
+      coupling_law_cb_kernel<<<grid, 256, 0, st>>>(u4, s, t, v4, logdet, g, n4, ns_per);
+    return (int)cudaGetLastError();
+  }
   const bool vec = (n_per % 4) == 0;
   const int work = vec ? n_per / 4 : n_per;
   int bx = (work + 256 * 4 - 1) / (256 * 4);  // ~4 items per thread

@@ -305,7 +305,7 @@ def test_edge_cases(dev):
 # ---------------------------------------------------------------------------------------------------
 # standalone fused coupling-law kernel
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [[8, 8, 3], [28, 28, 2], [6, 10, 5], [32, 32, 4]])
+@pytest.mark.parametrize("shape", [[8, 8, 3], [28, 28, 2], [6, 10, 5], [32, 32, 4], [12, 20, 8]])
 @pytest.mark.parametrize("m", [0, 1, 2, 3])
 def test_coupling_law_kernel(dev, shape, m):
     from arl_conditional_normalizing_flows_b200 import _lib
