@@ -1773,13 +1773,17 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   a.tiles_y = (a.h + a.TH - 1) / a.TH;
   a.tiles_x = (a.w + a.TW - 1) / a.TW;
   const int TP = a.TH * a.TW;
-  int best_px = 8, best_nt = 128, best_waste = 1 << 30;
+  // pixels per thread: thread slots nt*px (idle slots still issue), each tap re-reads the group's weights once per
+  // thread, so the per-pixel cost falls like (1 + alpha/px); 32-thread samples are allowed (two samples share a CTA)
+  static float alpha = -1.f;
+  if (alpha < 0.f) { const char* e = getenv("CNF_GC_ALPHA"); alpha = e ? (float)atof(e) : 2.0f; }
+  int best_px = 8, best_nt = 128;
+  float best_cost = 1e30f;
   for (int px = 8; px >= 1; --px) {
     int nt = ((TP + px - 1) / px + 31) / 32 * 32;
-    if (nt < 64) nt = 64;
     if (nt > 256) continue;
-    const int waste = nt * px - TP;
-    if (waste < best_waste) { best_waste = waste; best_px = px; best_nt = nt; }
+    const float cost = (float)nt * px * (1.f + alpha / px);
+    if (cost < best_cost) { best_cost = cost; best_px = px; best_nt = nt; }
   }
   const int halo = br.dil;
   const int GS = G + ((G % 8) == 0 ? 4 : 0);
@@ -1789,6 +1793,7 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   static int s_env = -1;
   if (s_env < 0) { const char* e = getenv("CNF_GC_S"); s_env = e ? atoi(e) : 2; }
   const bool two = s_env >= 2 && a.B >= 2 && (2 * in_sz + tail) * sizeof(float) <= 110 * 1024 && 2 * best_nt <= 320;
+  if (!two && best_nt < 64) best_nt = 64;
   const size_t smem = ((two ? 2 : 1) * in_sz + tail) * sizeof(float);
   if (smem > 227 * 1024) return 1;
   if (two) {
