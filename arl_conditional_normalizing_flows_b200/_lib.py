@@ -94,6 +94,7 @@ def _load():
         "cnf_coupling_nets": (I, [P, P, P, P, P, P, V]),
         "cnf_coupling_law": (I, [P, P, P, I, I, P, P, V]),
         "cnf_debug_pw_conv": (I, [P, P, P, I64, I, V]),
+        "cnf_debug_read_clocks": (I, [POINTER(c_int64), I]),
         "cnf_mask": (I, [P, I, I, P, V]),
         "cnf_decompress_mask": (I, [P, I, P, V]),
         "cnf_space_to_depth": (I, [P, P, V]),

@@ -407,6 +407,10 @@ int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLMa
   return cuda_rc(run_pw_only(c, P.p, (int)batch, which, W.p, stream), "1x1 conv");
 }
 
+int cnf_debug_read_clocks(long long* out, int n) {
+  return cuda_rc(read_tc3_clocks(out, n), "debug clocks");
+}
+
 int cnf_coupling_law(const DLManagedTensor* u, const DLManagedTensor* s, const DLManagedTensor* t, int which_mask,
                      int inverse, DLManagedTensor* v, DLManagedTensor* logdet, void* stream) {
   Ten U, S, T, V, L;

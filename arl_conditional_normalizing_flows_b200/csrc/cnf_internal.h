@@ -127,6 +127,7 @@ int launch_loss_grad(const float* zy, const float* xy, float* G, int64_t n, int 
                      float inv_batch, void* stream);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                 float gscale, void* stream);
+int read_tc3_clocks(long long* out, int n);
 int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, void* ws, void* stream);
 int launch_copy(const float* src, float* dst, int64_t n, void* stream);
 int launch_logdet_finalize(const double* acc, float* out, int B, void* stream);

@@ -48,6 +48,7 @@ struct GemmArgs {
   int B, hw, K, N, KC, ln;
   // backward-pass uses of gemm_kernel: raw_in = no LReLU/LN on A; w_trans = B[k][n] = W[n*ldw + k]; no_bias
   int raw_in, w_trans, ldw, no_bias;
+  int dbg;   // timing experiments only (CNF_PW_DBG): 1 skip epilogue stores, 2 skip cp.async, 4 skip MMAs, 8 skip transform math
 };
 
 template <int TN, int NQ, int RM, bool STEM>
@@ -1629,12 +1630,12 @@ static int launch_pw_tc2_t(const GemmArgs& a, cudaStream_t st) {
 }
 
 // warp-specialised persistent tcgen05 1x1 conv; returns 1 when the resident-W image does not fit
-template <int N>
-static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
+template <int N, int TW, int NST>
+static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   const int nchunks = (a.K + 31) / 32;
-  const size_t smem = ((size_t)4 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
-  if (smem > 220 * 1024) return 1;
-  auto kern = pw_tc3_kernel<N>;
+  const size_t smem = ((size_t)NST * 2 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
+  if (smem > 225 * 1024) return 1;
+  auto kern = pw_tc3_kernel<N, TW, NST>;
   static size_t configured = 0;
   static int n_sm = 0;
   if (smem > configured) {
@@ -1646,8 +1647,22 @@ static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
   }
   const int tiles_p = (a.hw + 31) / 32, tiles_s = (a.B + 3) / 4;
   const int grid = std::min(2 * tiles_p * tiles_s, n_sm & ~1);
-  kern<<<grid, 416, smem, st>>>(a, tiles_p, tiles_s);
+  GemmArgs b = a;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CNF_PW_DBG"); dbg = e ? atoi(e) : 0; } b.dbg = dbg; }
+  kern<<<grid, (TW + 1 + 8 + 4) * 32, smem, st>>>(b, tiles_p, tiles_s);
   return (int)cudaGetLastError();
+}
+
+// more operand stages decouple the transform warps from the MMA round trip; use as many as shared memory allows
+template <int N>
+static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
+  static int nst = -1;
+  if (nst < 0) { const char* e = getenv("CNF_PW_NST"); nst = e ? atoi(e) : 4; }
+  int rc = 1;
+  if (nst >= 4) rc = launch_pw_tc3_tw<N, 8, 4>(a, st);
+  if (rc == 1 && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3>(a, st);
+  if (rc == 1) rc = launch_pw_tc3_tw<N, 8, 2>(a, st);
+  return rc;
 }
 
 static bool use_tensor_cores() {
@@ -2060,6 +2075,11 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
     CU_TRY((cudaError_t)launch_head(a, st));
   }
   return 0;
+}
+
+int read_tc3_clocks(long long* out, int n) {
+  CU_TRY(cudaDeviceSynchronize());
+  return (int)cudaMemcpyFromSymbol(out, g_tc3_clk, sizeof(long long) * std::min(n, 8192));
 }
 
 // Measurement hook (cnf_debug_pw_conv): one 1x1-conv launch of residual block 0 on the current workspace.

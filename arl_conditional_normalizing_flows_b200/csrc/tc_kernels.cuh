@@ -590,9 +590,34 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int N>
-__global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
-  constexpr int NTT = 256;                     // transform threads
+// timing instrumentation (CNF_PW_DBG bit 128): CTA 0 records clock64() at the hand-off points of its first chunks
+__device__ long long g_tc3_clk[8192];
+#define TC3_STAMP(role, idx, slot)                                                                     \
+  do {                                                                                                 \
+    if ((a.dbg & 128) && blockIdx.x == 0 && (idx) < 64) g_tc3_clk[((role) * 64 + (idx)) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+// the calling thread's earlier cp.async operations arrive on the mbarrier when they complete (no pending-count increment)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void st8(float* p, const float* v) {   // 256-bit store (sm_100: STG.E.256), p 32-byte aligned
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld8(const float* p, float* v) {   // 256-bit load
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
+template <int N, int TW, int NST>   // TW transform warps: 8 (4 samples per thread) or 16 (2 per thread); NST operand stages
+__global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
+  constexpr int NTT = 256;                     // 16-byte units per sample and K-chunk (32 rows x 8 quads)
+  constexpr int NTH = TW * 32;                 // transform threads
+  constexpr int SPT = 4 * 256 / NTH;           // samples per transform thread
   constexpr int S = 4, PT = 32, M = 128;
   constexpr int KC = 32;
   constexpr int DEPTH = 3;
@@ -601,12 +626,14 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
   constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
   extern __shared__ __align__(128) float tc3_smem[];
   const int nchunks = (a.K + KC - 1) / KC;
-  float* opsA = tc3_smem;                      // [2 stages][hi, lo][A_ST]
-  float* raw = opsA + 4 * A_ST;                // [DEPTH][6][NTT] float4
+  float* opsA = tc3_smem;                      // [NST stages][hi, lo][A_ST]
+  float* raw = opsA + NST * 2 * A_ST;                // [DEPTH][6][NTT] float4
   float* Bres = raw + DEPTH * RAW;             // [nchunks][hi, lo][B_ST]
-  __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_tfull[2], bar_tempty[2];
+  constexpr int PWARPS = 4, NPT = PWARPS * 32;  // producer (copy) warps / threads
+  constexpr int EWARPS = 8;                     // epilogue warps: two per TMEM lane quarter, half of the columns each
+  __shared__ __align__(8) uint64_t bar_full[NST], bar_free[NST], bar_tfull[2], bar_tempty[2], raw_full[DEPTH], raw_free[DEPTH];
   __shared__ uint32_t tmem_slot;
-  __shared__ float mr[2][S][2];
+  __shared__ __align__(8) float mr[2][S][2];
   __shared__ __align__(16) float bias_s[N];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -618,21 +645,27 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
   const float* P = a.params + (long long)net * a.net_stride;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_full[i], NTT);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&bar_full[i], TW);             // one arrival per transform warp
       mbar_init(&bar_free[i], 1);
+    }
+    for (int i = 0; i < DEPTH; ++i) {
+      mbar_init(&raw_full[i], NPT);            // every producer thread's copies of the chunk have landed
+      mbar_init(&raw_free[i], TW);             // every transform warp has read the slot
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 128);
+      mbar_init(&bar_tempty[i], EWARPS);       // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (wid == 8) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (wid == TW) tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid < N) bias_s[tid] = P[a.b_off + tid];
   // resident B operand (all threads help)
   {
     const float* Wg = P + a.w_off;
     const int bnr = lane & 7, bkr = lane >> 3;
-    for (int it = wid; it < nchunks * (N / 8) * (KC / 4); it += 13) {
+    for (int it = wid; it < ((a.dbg & 64) ? 0 : nchunks * (N / 8) * (KC / 4)); it += TW + 1 + EWARPS + PWARPS) {
       const int c = it / ((N / 8) * (KC / 4)), r = it % ((N / 8) * (KC / 4));
       const int ng = r % (N / 8), kq = r / (N / 8);
       const int n = ng * 8 + bnr, k = c * KC + kq * 4 + bkr;
@@ -651,113 +684,92 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (wid < 8) {
+  if (wid < TW) {
     // =============================== transform warps ===============================
-    const float* src_n = a.in + (long long)net * a.in_net_stride;
-    const float* gam = P + a.g_off;
-    const float* bet = P + a.be_off;
-    const int ar = lane & 7, akq = (lane >> 3) + 4 * (wid >> 2);
-    const int ap = 8 * (wid & 3) + ar;
-    int pf_tl = 0, pf_c = 0, pf_r = cta;
-    int pf_s0 = (pf_r / tiles_p) * S, pf_p0 = (pf_r % tiles_p) * PT;
-    int pf_slot = 0;
-    auto issue = [&]() {
-      if (pf_tl < my_tiles) {
-        const int k0 = pf_c * KC, kc = min(KC, a.K - k0);
-        const int gp = pf_p0 + ap;
-        if (akq * 4 < kc && gp < a.hw) {
-          float* dst = raw + pf_slot * RAW;
-          const long long e = (long long)gp * a.K + k0 + akq * 4;
-          const int ns = min(S, a.B - pf_s0);
-#pragma unroll
-          for (int s = 0; s < S; ++s)
-            if (s < ns) cp_async16_cg(dst + (s * NTT + tid) * 4, src_n + ((long long)(pf_s0 + s) * a.hw) * a.K + e);
-          if (a.ln) {
-            cp_async16_ca(dst + (4 * NTT + tid) * 4, gam + e);
-            cp_async16_ca(dst + (5 * NTT + tid) * 4, bet + e);
-          }
-        }
-        if (++pf_c == nchunks) {
-          pf_c = 0;
-          ++pf_tl;
-          pf_r += ncta;
-          pf_s0 = (pf_r / tiles_p) * S;
-          pf_p0 = (pf_r % tiles_p) * PT;
-        }
-      }
-      pf_slot = pf_slot + 1 == DEPTH ? 0 : pf_slot + 1;
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int i = 0; i < DEPTH; ++i) issue();
-
+    const int wl = wid & 7, sh0 = (wid >> 3) * SPT;   // warp inside its group of 8; first sample this thread handles
+    const int ar = lane & 7, akq = (lane >> 3) + 4 * (wl >> 2);
+    const int ap = 8 * (wl & 3) + ar;
+    // unit (row ap, quad akq) was written by a producer thread at the swizzled position below (bank-conflict-free
+    // for 8 lanes = 8 rows of one quad)
+    const int runit = ap * 8 + (akq ^ (ap & 7));
     int gi = 0, slot = 0, r = cta;
-    // LayerNorm coefficients: the (sum, sumsq) pair of tile tl+1 is loaded while tile tl is transformed, so the
-    // L2 round trip never sits between a tile's barrier and its first chunk
+    // LayerNorm coefficients: every thread keeps (rstd, -mean*rstd) of its own samples in registers; the (sum, sumsq)
+    // pairs of tile tl+1 are loaded while tile tl is transformed (no shared copy, no barrier between tiles)
     const float inv_n = 1.0f / ((float)a.hw * (float)a.K);
-    double st_s = 0.0, st_q = 0.0;
-    auto load_stats = [&](int rr) {
-      const int s0n = (rr / tiles_p) * S;
-      if (a.ln && tid < S && s0n + tid < a.B) {
-        const double* sp = a.stats_in + 2 * ((long long)net * a.B + s0n + tid);
-        st_s = sp[0];
-        st_q = sp[1];
-      }
-    };
-    auto store_coeffs = [&](int par) {
-      if (tid < S) {
-        float sc = 1.f, shf = 0.f;
-        if (a.ln) {
-          const float m_ = (float)st_s * inv_n;
-          const float var = fmaxf(fmaf(-m_, m_, (float)st_q * inv_n), 0.f);
-          sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
-          shf = -m_ * sc;
+    double st_s[SPT], st_q[SPT];
+    // tile index r = tq * tiles_p + tp is advanced by ncta without divisions
+    const int dq = ncta / tiles_p, dp = ncta - dq * tiles_p;
+    int tq = cta / tiles_p, tp = cta - tq * tiles_p;
+    auto load_stats = [&](int tq_next) {
+      const int s0n = tq_next * S;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        st_s[j] = 0.0; st_q[j] = 1.0;
+        if (a.ln && s0n + sh0 + j < a.B) {
+          const double* sp = a.stats_in + 2 * ((long long)net * a.B + s0n + sh0 + j);
+          st_s[j] = sp[0];
+          st_q[j] = sp[1];
         }
-        mr[par][tid][0] = sc;
-        mr[par][tid][1] = shf;
       }
     };
-    if (my_tiles > 0) {
-      load_stats(cta);
-      store_coeffs(0);
-    }
+    if (my_tiles > 0) load_stats(tq);
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
-      const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+      const int s0 = tq * S, p0 = tp * PT;
       const int ns = min(S, a.B - s0);
-      named_bar_sync(1, NTT);                      // publishes mr[tl & 1] (written before this barrier)
-      if (tl + 1 < my_tiles) load_stats(r + ncta);  // in flight during this tile
+      tq += dq; tp += dp;
+      if (tp >= tiles_p) { tp -= tiles_p; ++tq; }
+      float2 cf[SPT];
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence: four ~200-instruction dependent chains per tile sat on
+        // the critical path between tiles (measured 1400 cycles); the difference is ~1e-7 relative
+        const float m_ = (float)st_s[j] * inv_n;
+        const float var = fmaxf(fmaf(-m_, m_, (float)st_q[j] * inv_n), 0.f);
+        const float sc = rsqrtf(var + (float)CNF_LN_EPS);
+        cf[j] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
+      }
+      if (tid == 0) TC3_STAMP(0, gi, 1);
+      if (tl + 1 < my_tiles) load_stats(tq);        // in flight during this tile
+      if (tid == 0) TC3_STAMP(0, gi, 2);
       const bool pv = (p0 + ap) < a.hw;
       for (int c = 0; c < nchunks; ++c, ++gi) {
-        const int stage = gi & 1;
+        const int stage = gi % NST;
         float* As_hi = opsA + stage * 2 * A_ST;
         float* As_lo = As_hi + A_ST;
         const int kc = min(KC, a.K - c * KC);
-        cp_async_wait<DEPTH - 1>();
-        if (gi >= 2) mbar_wait(&bar_free[stage], ((gi >> 1) - 1) & 1);
-        if (akq * 4 < kc) {
+        if (tid == 0) TC3_STAMP(0, gi, 0);
+        mbar_wait(&raw_full[slot], (gi / DEPTH) & 1);   // the producer warps' copies of chunk gi have landed
+        if (tid == 0) TC3_STAMP(0, gi, 3);
+        if (gi >= NST) mbar_wait(&bar_free[stage], ((gi / NST) - 1) & 1);
+        if (tid == 0) TC3_STAMP(0, gi, 4);
+        if (akq * 4 < kc && !(a.dbg & 32)) {
+          // every shared-memory read of this chunk is issued up front into its own registers (no branches between
+          // them: slots that were not copied hold stale bits and are discarded by the selects below), so the
+          // LDS latencies overlap instead of forming one dependent chain per sample
           const float* src = raw + slot * RAW;
-          float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pv && a.ln) {
-            g = ld4(src + (4 * NTT + tid) * 4);
-            be = ld4(src + (5 * NTT + tid) * 4);
-          }
+          float4 xv[SPT];
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (pv && s < ns) {
-              const float4 xv = ld4(src + (s * NTT + tid) * 4);
-              const float sc = mr[tl & 1][s][0], sh = mr[tl & 1][s][1];
-              v[0] = fmaxf(xv.x, CNF_LRELU_SLOPE * xv.x);
-              v[1] = fmaxf(xv.y, CNF_LRELU_SLOPE * xv.y);
-              v[2] = fmaxf(xv.z, CNF_LRELU_SLOPE * xv.z);
-              v[3] = fmaxf(xv.w, CNF_LRELU_SLOPE * xv.w);
-              if (a.ln) {
-                v[0] = fmaf(fmaf(v[0], sc, sh), g.x, be.x);
-                v[1] = fmaf(fmaf(v[1], sc, sh), g.y, be.y);
-                v[2] = fmaf(fmaf(v[2], sc, sh), g.z, be.z);
-                v[3] = fmaf(fmaf(v[3], sc, sh), g.w, be.w);
-              }
-            }
+          for (int j = 0; j < SPT; ++j) xv[j] = ld4(src + ((sh0 + j) * NTT + runit) * 4);
+          float4 g = ld4(src + (4 * NTT + runit) * 4), be = ld4(src + (5 * NTT + runit) * 4);
+          const bool use_ln = pv && a.ln;
+          g.x = use_ln ? g.x : 1.f; g.y = use_ln ? g.y : 1.f; g.z = use_ln ? g.z : 1.f; g.w = use_ln ? g.w : 1.f;
+          be.x = use_ln ? be.x : 0.f; be.y = use_ln ? be.y : 0.f; be.z = use_ln ? be.z : 0.f; be.w = use_ln ? be.w : 0.f;
+#pragma unroll
+          for (int j = 0; j < SPT; ++j) {
+            const int s = sh0 + j;
+            const bool ok = pv && s < ns && !(a.dbg & 8);
+            const float sc = cf[j].x, sh = cf[j].y;
+            float v[4];
+            v[0] = fmaxf(xv[j].x, CNF_LRELU_SLOPE * xv[j].x);
+            v[1] = fmaxf(xv[j].y, CNF_LRELU_SLOPE * xv[j].y);
+            v[2] = fmaxf(xv[j].z, CNF_LRELU_SLOPE * xv[j].z);
+            v[3] = fmaxf(xv[j].w, CNF_LRELU_SLOPE * xv[j].w);
+            v[0] = fmaf(fmaf(v[0], sc, sh), g.x, be.x);
+            v[1] = fmaf(fmaf(v[1], sc, sh), g.y, be.y);
+            v[2] = fmaf(fmaf(v[2], sc, sh), g.z, be.z);
+            v[3] = fmaf(fmaf(v[3], sc, sh), g.w, be.w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ok ? v[i] : 0.f;
             float h[4], l[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) tf32_split(v[i], h[i], l[i]);
@@ -766,15 +778,58 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
             st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
           }
         }
-        issue();
+        if (tid == 0) TC3_STAMP(0, gi, 5);
+        fence_async_smem();          // my generic-proxy writes -> async proxy ...
+        __syncwarp();                // ... for every lane of the warp, then ONE arrival per warp signals the MMA warp
+        if (tid == 0) TC3_STAMP(0, gi, 6);
+        if (lane == 0) {
+          mbar_arrive(&raw_free[slot]);              // the ring slot may be refilled
+          mbar_arrive(&bar_full[stage]);
+        }
         slot = slot + 1 == DEPTH ? 0 : slot + 1;
-        fence_async_smem();          // my generic-proxy writes -> async proxy, then signal the MMA warp
-        mbar_arrive(&bar_full[stage]);
+        if (tid == 0) TC3_STAMP(0, gi, 7);
       }
-      if (tl + 1 < my_tiles) store_coeffs((tl + 1) & 1);   // other parity: nobody reads it during tile tl
     }
-    cp_async_wait<0>();
-  } else if (wid == 8) {
+  } else if (wid >= TW + 1 + EWARPS) {
+    // =============================== producer (copy) warps ===============================
+    // 8 consecutive lanes fetch the 8 16-byte pieces of ONE 128-byte row segment (one L2 line -> one shared-memory
+    // wavefront); the piece (row, q) lands in unit row*8 + (q ^ (row & 7)).  Each producer thread owns 2 of the 256
+    // units of a chunk; completion is signalled through raw_full[slot] (cp.async.mbarrier.arrive.noinc).
+    const float* src_n = a.in + (long long)net * a.in_net_stride;
+    const float* gam = P + a.g_off;
+    const float* bet = P + a.be_off;
+    const int pt = tid - (TW + 1 + EWARPS) * 32;
+    int idx = 0, pslot = 0, r = cta;
+    for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
+      const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+      const int ns = min(S, a.B - s0);
+      for (int c = 0; c < nchunks; ++c, ++idx) {
+        if (idx >= DEPTH) mbar_wait(&raw_free[pslot], ((idx / DEPTH) - 1) & 1);
+        const int k0 = c * KC, kc = min(KC, a.K - k0);
+        float* dst = raw + pslot * RAW;
+#pragma unroll
+        for (int h = 0; h < NTT / NPT; ++h) {
+          const int u = pt + h * NPT;
+          const int cq = u & 7, crow = u >> 3;
+          const int gp = p0 + crow;
+          if (cq * 4 < kc && gp < a.hw && !(a.dbg & 2)) {
+            const int cunit = crow * 8 + (cq ^ (crow & 7));
+            const long long e = (long long)gp * a.K + k0 + cq * 4;
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (s < ns) cp_async16_cg(dst + (s * NTT + cunit) * 4, src_n + ((long long)(s0 + s) * a.hw) * a.K + e);
+            if (a.ln) {
+              cp_async16_ca(dst + (4 * NTT + cunit) * 4, gam + e);
+              cp_async16_ca(dst + (5 * NTT + cunit) * 4, bet + e);
+            }
+          }
+        }
+        cp_async_mbar_arrive_noinc(&raw_full[pslot]);
+        pslot = pslot + 1 == DEPTH ? 0 : pslot + 1;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (wid == TW) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(N);
@@ -787,13 +842,15 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
         tc_fence_after();
         const uint32_t d_addr = tmem_d + buf * N;
         for (int c = 0; c < nchunks; ++c, ++gi) {
-          const int stage = gi & 1;
+          const int stage = gi % NST;
           const int kc = min(KC, a.K - c * KC);
-          mbar_wait(&bar_full[stage], (gi >> 1) & 1);
+          TC3_STAMP(1, gi, 0);
+          mbar_wait(&bar_full[stage], (gi / NST) & 1);
+          TC3_STAMP(1, gi, 1);
           tc_fence_after();
           const uint32_t a_hi = a_base + stage * 2 * A_ST * 4, a_lo = a_hi + A_ST * 4;
           const uint32_t b_hi = b_base + c * 2 * B_ST * 4, b_lo = b_hi + B_ST * 4;
-          for (int ks = 0; ks < kc / 8; ++ks) {
+          for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : kc / 8); ++ks) {
             const uint32_t adv = ks * 2 * LBO;
             const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
             const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
@@ -801,60 +858,70 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
             umma_tf32(d_addr, dal, dbh, idesc, 1);
             umma_tf32(d_addr, dah, dbl, idesc, 1);
           }
+          TC3_STAMP(1, gi, 2);
           umma_commit(&bar_free[stage]);
           if (c == nchunks - 1) umma_commit(&bar_tfull[buf]);
+          TC3_STAMP(1, gi, 3);
         }
       }
     }
-  } else {
+  } else if (wid < TW + 1 + EWARPS) {
     // =============================== epilogue warps ===============================
-    const int quarter = wid & 3;                 // TMEM lane quarter this warp may access == sample index (PT == 32)
+    // warp e: TMEM lane quarter (wid & 3) == sample index (PT == 32), column half e >> 2.  The accumulator values are
+    // pulled into registers and the TMEM buffer is released BEFORE bias / residual / statistics / 256-bit stores.
+    constexpr int NH = N >= 32 ? N / 2 : N;      // columns per epilogue warp
+    const int quarter = wid & 3, half = (wid - (TW + 1)) >> 2;
+    const bool has_cols = N >= 32 || half == 0;
+    const int c0 = N >= 32 ? half * NH : 0;
     int r = cta;
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
       const int buf = tl & 1;
       const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
       const int ns = min(S, a.B - s0);
       const int egp = p0 + lane;
-      const bool erow = egp < a.hw && quarter < ns;
-      const long long row = ((long long)(s0 + quarter) * a.hw + egp) * a.N;
+      const bool erow = egp < a.hw && quarter < ns && has_cols;
+      const long long row = ((long long)(s0 + quarter) * a.hw + egp) * a.N + c0;
       float* out_r = a.out + (long long)net * a.out_net_stride + row;
       const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
-      float4 rr[N / 4];                            // residual row: in flight while the MMAs of this tile run
+      float rr[NH];                                // residual row segment: in flight while the MMAs of this tile run
       if (res_r && erow) {
 #pragma unroll
-        for (int j = 0; j < N / 4; ++j) rr[j] = ld4(res_r + 4 * j);
+        for (int j = 0; j < NH; j += 8) ld8(res_r + j, rr + j);
       }
+      if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 0);
       mbar_wait(&bar_tfull[buf], (tl >> 1) & 1);
+      if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 1);
       tc_fence_after();
-      float s1 = 0.f, s2 = 0.f;
+      float v[NH];
+      if (has_cols && !(a.dbg & 16)) {
 #pragma unroll
-      for (int cb = 0; cb < N; cb += 16) {
-        float v[16];
-        tmem_ld<16>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + cb), v);
-        if (erow) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 bb = ld4(bias_s + cb + j);
-            float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
-            if (res_r) {
-              const float4 q4 = rr[(cb + j) / 4];
-              o0 += q4.x; o1 += q4.y; o2 += q4.z; o3 += q4.w;
-            }
-            st4(out_r + cb + j, make_float4(o0, o1, o2, o3));
-            float l;
-            l = fmaxf(o0, CNF_LRELU_SLOPE * o0); s1 += l; s2 = fmaf(l, l, s2);
-            l = fmaxf(o1, CNF_LRELU_SLOPE * o1); s1 += l; s2 = fmaf(l, l, s2);
-            l = fmaxf(o2, CNF_LRELU_SLOPE * o2); s1 += l; s2 = fmaf(l, l, s2);
-            l = fmaxf(o3, CNF_LRELU_SLOPE * o3); s1 += l; s2 = fmaf(l, l, s2);
-          }
-        }
+        for (int cb = 0; cb < NH; cb += 16)
+          tmem_ld<16>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0 + cb), v + cb);
       }
       tc_fence_before();
-      mbar_arrive(&bar_tempty[buf]);             // accumulator buffer may be overwritten
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[buf]);   // accumulator buffer may be overwritten
+      if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 2);
+      float s1 = 0.f, s2 = 0.f;
+      if (erow && !(a.dbg & 16)) {
+#pragma unroll
+        for (int j = 0; j < NH; j += 8) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] = v[j + i] + bias_s[c0 + j + i];
+            if (res_r) o[i] += rr[j + i];
+            const float l = fmaxf(o[i], CNF_LRELU_SLOPE * o[i]);
+            s1 += l;
+            s2 = fmaf(l, l, s2);
+          }
+          if (!(a.dbg & 1)) st8(out_r + j, o);
+        }
+      }
       if (a.stats_out) {
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-        if (lane == 0 && quarter < ns) {
+        if (lane == 0 && quarter < ns && has_cols) {
           double* so = a.stats_out + 2 * ((long long)net * a.B + s0 + quarter);
           atomicAdd(so, (double)s1);
           atomicAdd(so + 1, (double)s2);
@@ -864,7 +931,7 @@ __global__ void __launch_bounds__(416, 1) pw_tc3_kernel(const GemmArgs a, const 
   }
   tc_fence_before();
   __syncthreads();
-  if (wid == 8) tmem_dealloc(tmem_d, TMEM_COLS);
+  if (wid == TW) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
 }  // namespace cnf

@@ -165,6 +165,9 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1_compresse
 int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace,
                       int64_t batch, int which, void* stream);
 
+/* timing instrumentation of the 1x1-conv kernel (CNF_PW_DBG=128): clock64() stamps of CTA 0, [role][chunk][8] */
+int cnf_debug_read_clocks(long long* out, int n);
+
 /* fused standalone coupling law + mask addressing + per-sample log-det (M:1215-1253, M:1307-1326):
  * v = mask(u,m,False) + decompress(exp(s)*u2c + t, m_bar)   (inverse: (u2c - t) / exp(s)).
  * u, v are [B,H,W,D]; s, t are [B,h,w,c2] in the compressed layout of the complement mask;
