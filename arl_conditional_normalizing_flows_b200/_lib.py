@@ -8,7 +8,7 @@ There is NO fallback: if the shared library is missing, importing this module ra
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, byref, c_char, c_char_p, c_double, c_int, c_int64, c_void_p,
+from ctypes import (POINTER, Structure, byref, c_char, c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p,
                     py_object)
 
 import torch
@@ -99,6 +99,11 @@ def _load():
         "cnf_decompress_mask": (I, [P, I, P, V]),
         "cnf_space_to_depth": (I, [P, P, V]),
         "cnf_depth_to_space": (I, [P, P, V]),
+        "cnf_down": (I, [P, I, P, V]),
+        "cnf_up": (I, [P, I, P, V]),
+        "cnf_sr_preprocess": (I, [P, I, I, I, P, V]),
+        "cnf_logit_scale": (I, [P, D, I, P, V]),
+        "cnf_instance_noise": (I, [P, D, c_uint64, c_uint64, P, V]),
         "cnf_toy_param_count": (I64, [I, I, I]),
         "cnf_toy_layer_offset": (I64, [I, I, I]),
         "cnf_toy_call": (I, [P, P, IP, I, I, I, I, P, P, V]),

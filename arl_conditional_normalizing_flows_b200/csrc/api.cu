@@ -497,6 +497,65 @@ int cnf_depth_to_space(const DLManagedTensor* in, DLManagedTensor* out, void* st
   return cuda_rc(launch_space_to_depth(I.p, O.p, B, 2 * h, 2 * w, C4 / 4, 1, stream), "depth_to_space");
 }
 
+// ---- data helpers on either side of the flow --------------------------------
+int cnf_down(const DLManagedTensor* img, int levels, DLManagedTensor* out, void* stream) {
+  Ten I, O;
+  TRY(borrow(img, "img", 4, &I));
+  TRY(borrow(out, "out", 4, &O));
+  if (levels < 1 || levels > 4) return fail(CNF_ERR_ARG, "down: levels must be 1..4 (got %d)", levels);
+  const int B = (int)I.shape[0], H = (int)I.shape[1], W = (int)I.shape[2], D = (int)I.shape[3];
+  if (O.shape[0] != B || O.shape[1] != (H >> levels) || O.shape[2] != (W >> levels) || O.shape[3] != D)
+    return fail(CNF_ERR_SHAPE, "out: expected [%d,%d,%d,%d]", B, H >> levels, W >> levels, D);
+  return cuda_rc(launch_down(I.p, O.p, B, H, W, D, levels, stream), "down");
+}
+
+int cnf_up(const DLManagedTensor* img, int levels, DLManagedTensor* out, void* stream) {
+  Ten I, O;
+  TRY(borrow(img, "img", 4, &I));
+  TRY(borrow(out, "out", 4, &O));
+  if (levels < 1 || levels > 4) return fail(CNF_ERR_ARG, "up: levels must be 1..4 (got %d)", levels);
+  const int B = (int)I.shape[0], H = (int)I.shape[1], W = (int)I.shape[2], D = (int)I.shape[3];
+  if (O.shape[0] != B || O.shape[1] != ((int64_t)H << levels) || O.shape[2] != ((int64_t)W << levels) || O.shape[3] != D)
+    return fail(CNF_ERR_SHAPE, "out: expected [%d,%d,%d,%d]", B, H << levels, W << levels, D);
+  return cuda_rc(launch_up(I.p, O.p, B, H, W, D, levels, stream), "up");
+}
+
+int cnf_sr_preprocess(const DLManagedTensor* hires, int levels_x, int levels_y, int residual, DLManagedTensor* xy,
+                      void* stream) {
+  Ten I, O;
+  TRY(borrow(hires, "hires", 4, &I));
+  TRY(borrow(xy, "xy", 4, &O));
+  if (levels_x < 0 || levels_y <= levels_x || levels_y > 4)
+    return fail(CNF_ERR_ARG, "sr_preprocess: need 0 <= levels_x < levels_y <= 4 (got %d, %d)", levels_x, levels_y);
+  const int B = (int)I.shape[0], H = (int)I.shape[1], W = (int)I.shape[2], D = (int)I.shape[3];
+  if ((H % (1 << levels_y)) || (W % (1 << levels_y)))
+    return fail(CNF_ERR_ARG, "sr_preprocess: H and W must be divisible by %d", 1 << levels_y);
+  if (O.shape[0] != B || O.shape[1] != (H >> levels_x) || O.shape[2] != (W >> levels_x) || O.shape[3] != 2 * D)
+    return fail(CNF_ERR_SHAPE, "xy: expected [%d,%d,%d,%d]", B, H >> levels_x, W >> levels_x, 2 * D);
+  return cuda_rc(launch_sr_preprocess(I.p, O.p, B, H, W, D, levels_x, levels_y, residual, stream), "sr_preprocess");
+}
+
+int cnf_logit_scale(const DLManagedTensor* x, double a, int inverse, DLManagedTensor* out, void* stream) {
+  Ten I, O;
+  TRY(borrow(x, "x", -1, &I));
+  TRY(borrow(out, "out", -1, &O));
+  if (!(a > 0.0 && a < 0.5)) return fail(CNF_ERR_ARG, "logit_scale: the fudge factor a must be in (0, 0.5)");
+  if (O.numel != I.numel) return fail(CNF_ERR_SHAPE, "out: expected %lld elements", (long long)I.numel);
+  return cuda_rc(launch_logit(I.p, O.p, I.numel, a, inverse, stream), "logit_scale");
+}
+
+int cnf_instance_noise(const DLManagedTensor* x, double alpha, uint64_t seed, uint64_t offset, DLManagedTensor* out,
+                       void* stream) {
+  Ten I, O;
+  TRY(borrow(out, "out", -1, &O));
+  if (x) {
+    TRY(borrow(x, "x", -1, &I));
+    if (O.numel != I.numel) return fail(CNF_ERR_SHAPE, "out: expected %lld elements", (long long)I.numel);
+  }
+  return cuda_rc(launch_instance_noise(x ? I.p : nullptr, O.p, O.numel, x ? alpha : 0.0, seed, offset, stream),
+                 "instance_noise");
+}
+
 // ---- toy ------------------------------------------------------------------------------------
 static long long toy_net_size_h(int I, int num_layers) {
   return 2LL * I + I + (long long)num_layers * ((long long)I * I + I) + 2LL * I + 4;

@@ -140,6 +140,14 @@ int launch_mask(const float* uv, float* out, int B, int H, int W, int D, int mas
 int launch_decompress(const float* uvc, float* out, int B, int H, int W, int D, int mask, void* stream);
 int launch_space_to_depth(const float* in, float* out, int B, int H, int W, int C, int inverse,
                           void* stream);
+// data_kernels.cu: input / output side helpers (F:74-318, F:635-676)
+int launch_down(const float* in, float* out, int B, int H, int W, int D, int L, void* stream);
+int launch_up(const float* in, float* out, int B, int H, int W, int D, int L, void* stream);
+int launch_sr_preprocess(const float* hires, float* out, int B, int H, int W, int D, int lx, int ly, int residual,
+                         void* stream);
+int launch_logit(const float* x, float* out, long long n, double a, int inverse, void* stream);
+int launch_instance_noise(const float* x, float* out, long long n, double alpha, unsigned long long seed,
+                          unsigned long long offset, void* stream);
 int launch_toy(const float* u, const float* params, const int* mask_idx_host, int n_layers_c, int width,
                int num_layers, int direction, float* v, float* logdet, int B, void* stream);
 int launch_toy_loss(const float* zy, const float* xy, const float* logdet, int B, int x_d, double lambda_y,

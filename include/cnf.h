@@ -184,6 +184,29 @@ int cnf_decompress_mask(const DLManagedTensor* uv_compressed, int which_mask, DL
 int cnf_space_to_depth(const DLManagedTensor* in, DLManagedTensor* out, void* stream);
 int cnf_depth_to_space(const DLManagedTensor* in, DLManagedTensor* out, void* stream);
 
+/* ---- data helpers on either side of the flow (conv_cINN_base_functions.py), SURVEY 8f-2/8f-3 ----
+ * The reference runs these as tf.data maps on the host; here each is one HBM-bound kernel on device tensors.
+ * cnf_down: `levels` nested 2x2 average pools (F:74-127: down(down(..)) = mean of means; trailing odd rows /
+ *   columns cropped).  img [B,H,W,D] -> out [B,H>>levels,W>>levels,D].
+ * cnf_up: `levels` nested 2x2 pixel repeats (F:129-164).  img [B,H,W,D] -> out [B,H<<levels,W<<levels,D].
+ * cnf_sr_preprocess: preprocess_dataset_SR (F:233-279) fused: x = down^levels_x(hires),
+ *   y = up^(levels_y-levels_x)(down^levels_y(hires)), x -= y if residual, xy = concat(x, y).
+ *   'SR2,1' = (0,1); 'SR4,2' = (1,2); SURVEY config 4 (8x8 condition for 64x64) = (0,3).
+ *   hires [B,H,W,D] -> xy [B,H>>levels_x,W>>levels_x,2D].
+ * cnf_logit_scale: inverse = 0: preprocess_dataset_class with LOGITS (F:174-231),
+ *   x -> (logit(a + (1-a) b x) - logit(a)) / (logit(1-a) - logit(a)), b = (1-2a)/(1-a);
+ *   inverse = 1: de_logitify (F:287-318).  Any shape; out may alias x.
+ * cnf_instance_noise: out = alpha x + (1 - alpha) N(0,1) (instance_noise, F:635-653); x == NULL: out = N(0,1)
+ *   (renew_noise, F:660-676).  Counter-based Philox4x32-10 + Box-Muller: elements 4q..4q+3 come from counter
+ *   q + offset under key `seed`, so a (seed, offset) pair reproduces the same noise on any grid / device count. */
+int cnf_down(const DLManagedTensor* img, int levels, DLManagedTensor* out, void* stream);
+int cnf_up(const DLManagedTensor* img, int levels, DLManagedTensor* out, void* stream);
+int cnf_sr_preprocess(const DLManagedTensor* hires, int levels_x, int levels_y, int residual, DLManagedTensor* xy,
+                      void* stream);
+int cnf_logit_scale(const DLManagedTensor* x, double a, int inverse, DLManagedTensor* out, void* stream);
+int cnf_instance_noise(const DLManagedTensor* x, double alpha, uint64_t seed, uint64_t offset, DLManagedTensor* out,
+                       void* stream);
+
 /* ---- toy dense cINN: cINN_affine.call / log_loss (T:248-451), coupling_layer MLPs (T:29-97) --
  * u, v are [B,3]; params is the flat buffer laid out by cnf_toy_param_count(); mask_indices[n]
  * (host ints) is the layer order; direction follows the TOY convention (-1: xy->zy with log-det,
