@@ -1,0 +1,447 @@
+// Fused grouped dilated 3x3 convs of one residual block (F:364-413, F:577-590): ALL dilation branches in one
+// persistent, double-buffered launch.  Included by stnet_kernels.cu after tc_kernels.cuh (cp.async helpers).
+//
+// Work decomposition: a CTA owns one OCTET of input channels (8 consecutive channels of the 1x1-conv output) of one
+// net and walks over batch items (S samples each).  Branch d reads the first nk/d channels (Q3), so octet o feeds
+// every branch with nk/d > 8 o: the d = 1 group(s) of the octet, and -- for the low octets -- the d = 2, 4, ... groups
+// that read the same channels.  The activation octet is therefore fetched from HBM/L2 ONCE for all branches
+// (the per-branch kernels fetched it once per branch), gamma/beta of the octet and the octet's weights stay resident in
+// shared memory for the whole launch, and the next item's raw rows stream in with cp.async while the current item is
+// transformed (LReLU + LayerNorm, in place) and convolved.  Octets that feed more branches get proportionally more CTAs
+// (host-side split, launch_gconv_oct).
+//
+// Compute: a thread owns 4 pixels x the full octet (8 in, 8 out); the weights are block-diagonal with G x G blocks
+// (G = group width in {1, 2, 4, 8}), so a pixel-tap costs 8 G FFMA from two 128-bit shared loads.  Lanes 4..7 of every
+// group of 8 read the two channel quads in swapped order ("flip"): lanes i and i + 4 sit 128 bytes apart (same banks),
+// so the swap makes the 8-lane phases of the 128-bit loads conflict-free without padding the tile.
+#pragma once
+
+namespace cnf {
+
+constexpr int OCT_MAX = 32;   // octets per tensor (nk <= 256)
+constexpr int OCT_PX = 4;
+
+struct OctBranch {
+  int dil, G, noct, out_off;  // noct = branch channels / 8; out_off = first channel of the branch in the concat
+  long long w_off, b_off;
+  int w_smem;                 // float offset of this branch's weights inside the weight area
+};
+
+struct OctArgs {
+  const float* in;
+  float* out;
+  long long in_net_stride, out_net_stride;
+  const float* params;
+  long long net_stride, g_off, be_off;
+  const double* stats_in;
+  double* stats_out;
+  int B, h, w, Cin, Cout, ln;
+  int S, halo, SW, SHW, n_items, n_oct, nsps;   // nsps = pixel slots per sample = ceil(h w / 4)
+  int tps;                                      // threads per sample: nsps rounded up to whole warps (nsps itself if < 32)
+  int n_br;
+  OctBranch br[CNF_MAX_BRANCHES];
+  unsigned char cta_first[OCT_MAX + 1];         // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
+};
+
+__host__ __device__ inline int oct_w_floats(int G) { return 9 * 2 * (4 * G + 4); }   // [tap][half][4 rows x G + pad 4]
+
+// one branch of one item: 9 taps of block-diagonal 8x8 weights on this thread's 4 pixels, then bias, store, statistics
+template <int G>
+__device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const float* __restrict__ wb,
+                                           const float* __restrict__ bias, const int (&poff)[OCT_PX], int flip, int dil,
+                                           int SW, float* __restrict__ dst, int Cout, const bool (&pv)[OCT_PX],
+                                           float& s1, float& s2) {
+  constexpr int HS = 4 * G + 4;                 // floats between the two weight halves of a tap
+  float acc[OCT_PX][8];
+#pragma unroll
+  for (int j = 0; j < OCT_PX; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  // running pointers instead of per-tap index arithmetic: xa[j] walks the 3x3 taps of pixel j (first-loaded quad), the
+  // other quad sits d2 floats away; wq[hq] walks the weight rows of the quad loaded hq-th
+  const float* xa[OCT_PX];
+#pragma unroll
+  for (int j = 0; j < OCT_PX; ++j) xa[j] = xb + poff[j] + flip * 4 - (SW + 1) * dil * 8;
+  const int d2 = 4 - 8 * flip;
+  const int dx = dil * 8, dy = (SW - 3) * dil * 8;
+  const float* wq[2] = {wb + flip * HS, wb + (1 - flip) * HS};
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    float4 xq[OCT_PX][2];
+#pragma unroll
+    for (int j = 0; j < OCT_PX; ++j) {
+      xq[j][0] = ld4(xa[j]);                    // logical quad `flip`
+      xq[j][1] = ld4(xa[j] + d2);               // logical quad `1 - flip`
+      xa[j] += (tap == 2 || tap == 5) ? dx + dy : dx;
+    }
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+      const float* wr = wq[hq];                  // rows of the logical quad hq ^ flip
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float wv[G];
+        if constexpr (G == 8) {
+          const float4 a = ld4(wr + i * 8), b = ld4(wr + i * 8 + 4);
+          wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+          wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
+        } else if constexpr (G == 4) {
+          const float4 a = ld4(wr + i * 4);
+          wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+        } else if constexpr (G == 2) {
+          const float2 a = *reinterpret_cast<const float2*>(wr + i * 2);
+          wv[0] = a.x; wv[1] = a.y;
+        } else {
+          wv[0] = wr[i];
+        }
+#pragma unroll
+        for (int j = 0; j < OCT_PX; ++j) {
+          const float xv = i == 0 ? xq[j][hq].x : i == 1 ? xq[j][hq].y : i == 2 ? xq[j][hq].z : xq[j][hq].w;
+          if constexpr (G == 8) {
+#pragma unroll
+            for (int co = 0; co < 8; ++co) acc[j][co] = fmaf(xv, wv[co], acc[j][co]);
+          } else {
+            // outputs of this quad's groups live in acc[j][hq * 4 ..]: channel (i / G) * G + co of the quad
+            constexpr int GG = G < 4 ? G : 4;
+            const int base = hq * 4 + (i / GG) * GG;
+#pragma unroll
+            for (int co = 0; co < GG; ++co) acc[j][base + co] = fmaf(xv, wv[co], acc[j][base + co]);
+          }
+        }
+      }
+    }
+    wq[0] += 2 * HS;
+    wq[1] += 2 * HS;
+  }
+  // acc[j][0..7]: G == 8 -> channels 0..7; G < 8 -> [quad hq][4] with logical quad hq ^ flip
+  float bq[2][4];
+#pragma unroll
+  for (int hq = 0; hq < 2; ++hq) {
+    const int lq = G == 8 ? hq : (hq ^ flip);
+    const float4 b = ld4(bias + lq * 4);
+    bq[hq][0] = b.x; bq[hq][1] = b.y; bq[hq][2] = b.z; bq[hq][3] = b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < OCT_PX; ++j) {
+    if (!pv[j]) continue;
+    float* d = dst + (long long)j * Cout;       // caller passes dst of pixel 0 with pixel stride folded into Cout arg
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+      float o[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        o[c] = acc[j][hq * 4 + c] + bq[hq][c];
+        const float l = lrelu(o[c]);
+        s1 += l;
+        s2 = fmaf(l, l, s2);
+      }
+      const int lq = G == 8 ? hq : (hq ^ flip);
+      st4(d + lq * 4, make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
+  extern __shared__ __align__(16) float oct_smem[];
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int net = blockIdx.y;
+  const int hw = a.h * a.w;
+  // which octet, and this CTA's rank among the CTAs of the octet
+  int o = 0;
+  while (o + 1 < a.n_oct && (int)blockIdx.x >= (int)a.cta_first[o + 1]) ++o;
+  const int rank = blockIdx.x - a.cta_first[o], nshare = a.cta_first[o + 1] - a.cta_first[o];
+
+  const int xsz = a.S * a.SHW * 8;                          // floats per x buffer
+  float* xbuf = oct_smem;                                   // [2][S][SHW][8]
+  float* gb = xbuf + 2 * xsz;                               // [2][hw][8] gamma, beta of the octet
+  float* w_s = gb + (a.ln ? 2 * hw * 8 : 0);                // per branch [9][2][4G+4]
+  int wtot = 0;
+  for (int b = 0; b < a.n_br; ++b) wtot += oct_w_floats(a.br[b].G);
+  float* b_s = w_s + wtot;                                  // [n_br][8]
+  float* mr = b_s + a.n_br * 8;                             // [2][S][2]  (rstd, -mean rstd) per buffer parity
+  float* red = mr + 4 * a.S;                                // [NT][2] per-thread, or [NT/32][4] per-warp partial sums
+  unsigned short* pt = reinterpret_cast<unsigned short*>(red + 2 * NT);    // [hw] pixel offset inside a sample tile
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  const float* src_n = a.in + (long long)net * a.in_net_stride + o * 8;
+  float* out_n = a.out + (long long)net * a.out_net_stride + o * 8;
+
+  // ---- one-time setup: zero tiles (the halo stays zero for the whole launch), tables, weights, gamma/beta ----
+  for (int i = tid; i < 2 * xsz / 4; i += NT) st4(xbuf + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int p = tid; p < hw; p += NT) {
+    const int y = p / a.w, x = p - y * a.w;
+    pt[p] = (unsigned short)((y + a.halo) * a.SW + x + a.halo);
+  }
+  for (int b = 0; b < a.n_br; ++b) {
+    const OctBranch& br = a.br[b];
+    if (o >= br.noct) continue;
+    const int G = br.G, HS = 4 * G + 4;
+    float* wd = w_s + br.w_smem;
+    const float* wsrc = P + br.w_off + (long long)o * (8 / G) * 9 * G * G;   // groups o*8/G .. of [group][tap][ci][co]
+    for (int i = tid; i < 9 * 8 * G; i += NT) {
+      const int co = i % G, ci = (i / G) % 8, tap = i / (8 * G);
+      const int grp = ci / G, cig = ci - grp * G;
+      wd[tap * 2 * HS + (ci >> 2) * HS + (ci & 3) * G + co] = wsrc[((grp * 9 + tap) * G + cig) * G + co];
+    }
+    if (tid < 8) b_s[b * 8 + tid] = P[br.b_off + o * 8 + tid];
+  }
+  if (a.ln) {
+    const float* gam = P + a.g_off + o * 8;
+    const float* bet = P + a.be_off + o * 8;
+    for (int i = tid; i < hw * 2; i += NT) {
+      const int p = i >> 1, qd = (i & 1) * 4;
+      st4(gb + p * 8 + qd, ld4(gam + (long long)p * a.Cin + qd));
+      st4(gb + hw * 8 + p * 8 + qd, ld4(bet + (long long)p * a.Cin + qd));
+    }
+  }
+
+  // this thread's pixels (same for every item): sample q, slots sl + j nsps
+  // (a sample's threads are whole warps, so its reduction order -- and therefore every bit of the result -- does not
+  // depend on the batch size or on the sample's position inside the item)
+  const int q = tid / a.tps, sl = tid - q * a.tps;
+  const bool tactive = q < a.S && sl < a.nsps;
+  const int flip = (lane >> 2) & 1;
+  int poff[OCT_PX];
+  bool pin[OCT_PX];
+#pragma unroll
+  for (int j = 0; j < OCT_PX; ++j) {
+    const int p = sl + j * a.nsps;
+    pin[j] = tactive && p < hw;
+    const int pc = min(p, hw - 1);
+    const int y = pc / a.w, x = pc - y * a.w;
+    poff[j] = ((tactive ? q : 0) * a.SHW + (y + a.halo) * a.SW + x + a.halo) * 8;
+  }
+  const float inv_n = 1.0f / ((float)hw * (float)a.Cin);
+  auto coeffs = [&](int item, int par) {   // LayerNorm coefficients of the samples of `item` -> mr[par]
+    if (tid < a.S) {
+      float sc = 1.f, sh = 0.f;
+      const int s = item * a.S + tid;
+      if (a.ln && s < a.B) {
+        const double* sp = a.stats_in + 2 * ((long long)net * a.B + s);
+        const float m = (float)sp[0] * inv_n;
+        const float var = fmaxf(fmaf(-m, m, (float)sp[1] * inv_n), 0.f);
+        sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
+        sh = -m * sc;
+      }
+      mr[(par * a.S + tid) * 2] = sc;
+      mr[(par * a.S + tid) * 2 + 1] = sh;
+    }
+  };
+  auto issue = [&](int item, int par) {    // cp.async the raw octet rows of `item` into buffer `par`
+    const int b0 = item * a.S, ns = min(a.S, a.B - b0);
+    float* xb = xbuf + par * xsz;
+    for (int s = 0; s < ns; ++s) {
+      const float* src = src_n + (long long)(b0 + s) * hw * a.Cin;
+      float* dst = xb + s * a.SHW * 8;
+      for (int i = tid; i < hw * 2; i += NT) {
+        const int p = i >> 1, qd = (i & 1) * 4;
+        cp_async16_cg(dst + pt[p] * 8 + qd, src + (long long)p * a.Cin + qd);
+      }
+    }
+  };
+  __syncthreads();                         // pt[] and the zero fill are visible before the first copies land
+  int item = rank;
+  if (item < a.n_items) {
+    issue(item, 0);
+    coeffs(item, 0);
+  }
+  cp_async_commit();
+
+  for (int it = 0; item < a.n_items; ++it, item += nshare) {
+    const int par = it & 1;
+    const int next = item + nshare;
+    if (next < a.n_items) issue(next, par ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();                    // this thread's copies of `item` have landed
+    __syncthreads();                       // ... and everybody else's; mr[par] is visible
+    const int b0 = item * a.S, ns = min(a.S, a.B - b0);
+    float* xb = xbuf + par * xsz;
+    // ---- LReLU + LayerNorm in place on the interior pixels (4 float4 units per thread in flight) ----
+    for (int s = 0; s < ns; ++s) {
+      const float sc = mr[(par * a.S + s) * 2], sh = mr[(par * a.S + s) * 2 + 1];
+      float* xs = xb + s * a.SHW * 8;
+      for (int i0 = tid; i0 < hw * 2; i0 += 4 * NT) {
+        float4 v[4], g[4], be[4];
+        float* px[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = min(i0 + u * NT, hw * 2 - 1);
+          const int p = i >> 1, qd = (i & 1) * 4;
+          px[u] = xs + pt[p] * 8 + qd;
+          v[u] = ld4(px[u]);
+          if (a.ln) {
+            g[u] = ld4(gb + p * 8 + qd);
+            be[u] = ld4(gb + hw * 8 + p * 8 + qd);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 t = v[u];
+          t.x = lrelu(t.x); t.y = lrelu(t.y); t.z = lrelu(t.z); t.w = lrelu(t.w);
+          if (a.ln) {
+            t.x = fmaf(fmaf(t.x, sc, sh), g[u].x, be[u].x);
+            t.y = fmaf(fmaf(t.y, sc, sh), g[u].y, be[u].y);
+            t.z = fmaf(fmaf(t.z, sc, sh), g[u].z, be[u].z);
+            t.w = fmaf(fmaf(t.w, sc, sh), g[u].w, be[u].w);
+          }
+          if (i0 + u * NT < hw * 2) st4(px[u], t);
+        }
+      }
+    }
+    if (next < a.n_items) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
+    __syncthreads();
+    // ---- the branches that read this octet ----
+    const bool live = tactive && q < ns;
+    bool pv[OCT_PX];
+#pragma unroll
+    for (int j = 0; j < OCT_PX; ++j) pv[j] = live && pin[j];
+    float s1 = 0.f, s2 = 0.f;
+    if (tactive) {
+      // pixel j of this thread: global pixel index (b0 + q) hw + sl + j nsps
+      float* dst0 = out_n + ((long long)(b0 + min(q, a.S - 1)) * hw + min(sl, a.nsps - 1)) * a.Cout;
+      const int jstride = a.nsps * a.Cout;       // floats between this thread's consecutive pixels
+      for (int b = 0; b < a.n_br; ++b) {
+        const OctBranch& br = a.br[b];
+        if (o >= br.noct) continue;
+        const float* wb = w_s + br.w_smem;
+        float* d = dst0 + br.out_off;
+        switch (br.G) {
+          case 8: oct_branch<8>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
+          case 4: oct_branch<4>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
+          case 2: oct_branch<2>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
+          default: oct_branch<1>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
+        }
+      }
+    }
+    // statistics of LReLU(out): fixed-order reduction (bit-reproducible run to run), fp64 across CTAs
+    if (a.stats_out) {
+      if (a.nsps >= 32) {
+        const float a1 = warp_sum(s1), a2 = warp_sum(s2);       // the warp belongs to one sample
+        if (lane == 0) {
+          red[2 * (tid >> 5)] = a1;
+          red[2 * (tid >> 5) + 1] = a2;
+        }
+      } else {
+        red[2 * tid] = s1;
+        red[2 * tid + 1] = s2;
+      }
+    }
+    __syncthreads();                       // everyone is done with xb (the next iteration refills it); red is complete
+    if (a.stats_out && tid < 2 * a.S && (tid >> 1) < ns) {
+      const int s = tid >> 1, which = tid & 1;
+      double t = 0.0;
+      const int cnt = a.nsps >= 32 ? (a.tps >> 5) : a.nsps;      // partial sums of sample s: per warp or per thread
+      for (int k = 0; k < cnt; ++k) t += (double)red[2 * (s * cnt + k) + which];
+      atomicAdd(a.stats_out + 2 * ((long long)net * a.B + b0 + s) + which, t);
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// Host side: eligibility, shared-memory budget, CTA split.  Returns 1 if the shape is not covered (caller falls back to
+// the per-branch kernels), 0 on success, a cudaError otherwise.
+static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("CNF_GC_OCT"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled || g.bwd || g.ks != 3 || g.n_br < 1) return 1;
+  if ((g.Cin % 4) || (g.Cout % 4)) return 1;
+  OctArgs a{};
+  a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
+  a.params = g.params; a.net_stride = g.net_stride; a.g_off = g.g_off; a.be_off = g.be_off;
+  a.stats_in = g.stats_in; a.stats_out = g.stats_out;
+  a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
+  a.n_br = g.n_br;
+  int halo = 0, n_oct = 0, wtot = 0;
+  for (int i = 0; i < g.n_br; ++i) {
+    const GconvBranch& b = g.br[i];
+    const int G = b.gin, ch = b.groups * b.gin;
+    if (b.gin != b.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || (ch % 8) || b.in_off != 0 || (b.out_off % 4)) return 1;
+    if (ch > g.Cin) return 1;
+    OctBranch& ob = a.br[i];
+    ob.dil = b.dil; ob.G = G; ob.noct = ch / 8; ob.out_off = b.out_off; ob.w_off = b.w_off; ob.b_off = b.b_off;
+    ob.w_smem = wtot;
+    wtot += oct_w_floats(G);
+    halo = std::max(halo, b.dil);
+    n_oct = std::max(n_oct, ob.noct);
+  }
+  if (n_oct > OCT_MAX || n_oct < 1) return 1;
+  const int hw = g.h * g.w;
+  a.halo = halo; a.SW = g.w + 2 * halo; a.SHW = (g.h + 2 * halo) * a.SW; a.n_oct = n_oct;
+  if ((long long)a.SHW >= 65536 / 1) return 1;                 // pt[] is 16 bit
+  a.nsps = (hw + OCT_PX - 1) / OCT_PX;
+  a.tps = a.nsps < 32 ? a.nsps : (a.nsps + 31) / 32 * 32;
+  // samples per item: as many as keep <= 512 threads busy and fit the shared-memory budget
+  const size_t budget = 227 * 1024 - 1024;
+  auto smem_for = [&](int S) {
+    size_t f = (size_t)2 * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * 512;
+    return f * sizeof(float) + (((size_t)hw * 2 + 15) & ~(size_t)15);
+  };
+  if (a.tps > 512 || smem_for(1) > budget) return 1;
+  static int nsm = 0;
+  if (!nsm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 2) nsm = 148;
+  }
+  // walk down from the largest S (<= 512 threads, fits shared memory) until every CTA slot has >= 3 items to pipeline,
+  // but keep at least ~96 busy threads per CTA
+  int S = 0, NT = 0, slots = 0;
+  static int s_cap = 0;
+  if (!s_cap) { const char* e = getenv("CNF_OCT_S"); s_cap = e ? std::max(1, atoi(e)) : 512; }
+  for (int s = std::max(1, std::min(std::min(512 / a.tps, s_cap), g.B)); s >= 1; --s) {
+    if (smem_for(s) > budget) continue;
+    if (S && s * a.tps < 96) break;
+    S = s;
+    NT = std::min(512, (s * a.tps + 31) / 32 * 32);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, (227 * 1024) / (smem_for(s) + 1024)), 65536 / (NT * 128)));
+    slots = std::min(255, nsm / 2 * per_sm);
+    if (((g.B + s - 1) / s) * n_oct >= 3 * slots) break;
+  }
+  a.S = S;
+  a.n_items = (g.B + S - 1) / S;
+  // CTA split: half of the slots per net; octet o gets CTAs in proportion to its FFMA work
+  int per_net = std::max(n_oct, slots);
+  if (per_net > n_oct * a.n_items) per_net = std::max(n_oct, n_oct * a.n_items);
+  float work[OCT_MAX];
+  int nc[OCT_MAX];
+  for (int o = 0; o < n_oct; ++o) {
+    work[o] = 24.f;                                            // staging / transform overhead in the same units
+    for (int i = 0; i < g.n_br; ++i)
+      if (o < a.br[i].noct) work[o] += 8.f * a.br[i].G + 6.f;  // FFMA per pixel-tap + epilogue share
+    nc[o] = 1;
+  }
+  for (int left = per_net - n_oct; left > 0; --left) {         // greedy: relieve the octet with the longest schedule
+    int best = 0;
+    float worst = -1.f;
+    for (int o = 0; o < n_oct; ++o) {
+      const float t = work[o] * (float)((a.n_items + nc[o] - 1) / nc[o]);
+      if (t > worst) { worst = t; best = o; }
+    }
+    if ((a.n_items + nc[best] - 1) / nc[best] <= 1) break;
+    ++nc[best];
+  }
+  int tot = 0;
+  for (int o = 0; o < n_oct; ++o) { a.cta_first[o] = (unsigned char)tot; tot += nc[o]; }
+  a.cta_first[n_oct] = (unsigned char)tot;
+  if (tot > 255) return 1;
+  const size_t smem = smem_for(S);
+  static int verbose = -1;
+  if (verbose < 0) { const char* e = getenv("CNF_OCT_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  if (verbose > 0) {
+    --verbose;
+    fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d\n", g.B, g.h, g.w, g.Cin,
+            g.Cout, S, NT, a.n_items, n_oct, tot, smem, halo);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gconv_oct_kernel<448>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  if (NT <= 448) gconv_oct_kernel<448><<<dim3(tot, 2), NT, smem, st>>>(a);
+  else gconv_oct_kernel<512><<<dim3(tot, 2), NT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace cnf

@@ -1901,11 +1901,20 @@ static int launch_gconv4_branch(const GconvArgs& g, int bi, cudaStream_t st) {
 
 static int launch_gconv_ffma(GconvArgs a, cudaStream_t st);
 
+}  // namespace cnf
+#include "gconv_oct.cuh"
+namespace cnf {
+
 static int launch_gconv(GconvArgs a, cudaStream_t st) {
   const bool tc = use_tensor_cores_gconv();
   static int v2 = -1;
   if (v2 < 0) { const char* e = getenv("CNF_GC_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
   if (v2) return launch_gconv_ffma(a, st);
+  if (!tc) {
+    // all dilation branches in one persistent launch (gconv_oct.cuh); shapes it does not cover fall through
+    const int rc = launch_gconv_oct(a, st);
+    if (rc != 1) return rc;
+  }
   GconvArgs rest = a;
   rest.n_br = 0;
   for (int i = 0; i < a.n_br; ++i) {
