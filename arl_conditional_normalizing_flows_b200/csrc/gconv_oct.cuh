@@ -39,11 +39,31 @@ struct OctArgs {
   int S, halo, SW, SHW, n_items, n_oct, nsps;   // nsps = pixel slots per sample = ceil(h w / 4)
   int tps;                                      // threads per sample: nsps rounded up to whole warps (nsps itself if < 32)
   int n_br;
+  int dbg;                                      // CNF_OCT_DBG: 1 skip branches, 2 skip transform, 4 skip copies, 8 skip stores, 16 skip coeffs
   OctBranch br[CNF_MAX_BRANCHES];
   unsigned char cta_first[OCT_MAX + 1];         // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
 };
 
 __host__ __device__ inline int oct_w_floats(int G) { return 9 * 2 * (4 * G + 4); }   // [tap][half][4 rows x G + pad 4]
+
+// d.xy += a.xy * b.xy: one FFMA2 (sm_100 packed fp32 FMA).  A three-register FFMA issues every other cycle per scheduler
+// on this part, FFMA2 does two FMAs in the same slot, so the packed form is what reaches the fp32 peak.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+
+// position of weight (ci, co) of a tap inside its quad half (ci & 4 selects the half): input channels are taken in PAIRS
+// (2k, 2k+1) so that (x[2k], x[2k+1]) * (w[2k][co], w[2k+1][co]) is one FFMA2 into an (even-ci, odd-ci) accumulator pair
+__host__ __device__ inline int oct_w_pos(int G, int ci, int co) {
+  const int c4 = ci & 3;
+  if (G == 1) return c4;                                  // depthwise: (w[2k], w[2k+1]) multiplies (x[2k], x[2k+1])
+  if (G == 2) return ((c4 >> 1) * 2 + co) * 2 + (c4 & 1);  // quad = 2 groups, each one ci pair
+  return ((c4 >> 1) * G + co) * 2 + (c4 & 1);              // G = 4 (quad = the group) or 8 (group = both quads)
+}
 
 // one branch of one item: 9 taps of block-diagonal 8x8 weights on this thread's 4 pixels, then bias, store, statistics
 template <int G>
@@ -52,11 +72,14 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
                                            int SW, float* __restrict__ dst, int Cout, const bool (&pv)[OCT_PX],
                                            float& s1, float& s2) {
   constexpr int HS = 4 * G + 4;                 // floats between the two weight halves of a tap
-  float acc[OCT_PX][8];
+  // G >= 2: acc[j][c] = (sum over even ci, sum over odd ci) of output channel c (G == 8) or of channel c of the quads in
+  // load order (G < 8).  G == 1: acc[j][k] = the two depthwise channels 2k, 2k+1 (load order), k < 4.
+  constexpr int NA = G == 1 ? 4 : 8;
+  float2 acc[OCT_PX][NA];
 #pragma unroll
   for (int j = 0; j < OCT_PX; ++j)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+    for (int c = 0; c < NA; ++c) acc[j][c] = make_float2(0.f, 0.f);
   // running pointers instead of per-tap index arithmetic: xa[j] walks the 3x3 taps of pixel j (first-loaded quad), the
   // other quad sits d2 floats away; wq[hq] walks the weight rows of the quad loaded hq-th
   const float* xa[OCT_PX];
@@ -76,35 +99,38 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
     }
 #pragma unroll
     for (int hq = 0; hq < 2; ++hq) {
-      const float* wr = wq[hq];                  // rows of the logical quad hq ^ flip
+      const float* wr = wq[hq];                  // weights of the logical quad hq ^ flip
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float wv[G];
-        if constexpr (G == 8) {
-          const float4 a = ld4(wr + i * 8), b = ld4(wr + i * 8 + 4);
-          wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
-          wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
-        } else if constexpr (G == 4) {
-          const float4 a = ld4(wr + i * 4);
-          wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+      for (int k = 0; k < 2; ++k) {              // ci pair (2k, 2k+1) of the quad
+        if constexpr (G == 8 || G == 4) {
+          constexpr int NCO = G;
+          float2 wv[NCO];
+#pragma unroll
+          for (int c = 0; c < NCO; c += 2) {
+            const float4 t = ld4(wr + (k * NCO + c) * 2);
+            wv[c] = make_float2(t.x, t.y);
+            wv[c + 1] = make_float2(t.z, t.w);
+          }
+#pragma unroll
+          for (int j = 0; j < OCT_PX; ++j) {
+            const float2 xp = k == 0 ? make_float2(xq[j][hq].x, xq[j][hq].y) : make_float2(xq[j][hq].z, xq[j][hq].w);
+#pragma unroll
+            for (int c = 0; c < NCO; ++c) ffma2(acc[j][(G == 8 ? 0 : hq * 4) + c], xp, wv[c]);
+          }
         } else if constexpr (G == 2) {
-          const float2 a = *reinterpret_cast<const float2*>(wr + i * 2);
-          wv[0] = a.x; wv[1] = a.y;
+          const float4 t = ld4(wr + k * 4);       // group k of the quad: (w[0][0], w[1][0], w[0][1], w[1][1])
+#pragma unroll
+          for (int j = 0; j < OCT_PX; ++j) {
+            const float2 xp = k == 0 ? make_float2(xq[j][hq].x, xq[j][hq].y) : make_float2(xq[j][hq].z, xq[j][hq].w);
+            ffma2(acc[j][hq * 4 + k * 2], xp, make_float2(t.x, t.y));
+            ffma2(acc[j][hq * 4 + k * 2 + 1], xp, make_float2(t.z, t.w));
+          }
         } else {
-          wv[0] = wr[i];
-        }
+          const float2 t = *reinterpret_cast<const float2*>(wr + k * 2);
 #pragma unroll
-        for (int j = 0; j < OCT_PX; ++j) {
-          const float xv = i == 0 ? xq[j][hq].x : i == 1 ? xq[j][hq].y : i == 2 ? xq[j][hq].z : xq[j][hq].w;
-          if constexpr (G == 8) {
-#pragma unroll
-            for (int co = 0; co < 8; ++co) acc[j][co] = fmaf(xv, wv[co], acc[j][co]);
-          } else {
-            // outputs of this quad's groups live in acc[j][hq * 4 ..]: channel (i / G) * G + co of the quad
-            constexpr int GG = G < 4 ? G : 4;
-            const int base = hq * 4 + (i / GG) * GG;
-#pragma unroll
-            for (int co = 0; co < GG; ++co) acc[j][base + co] = fmaf(xv, wv[co], acc[j][base + co]);
+          for (int j = 0; j < OCT_PX; ++j) {
+            const float2 xp = k == 0 ? make_float2(xq[j][hq].x, xq[j][hq].y) : make_float2(xq[j][hq].z, xq[j][hq].w);
+            ffma2(acc[j][hq * 2 + k], xp, t);
           }
         }
       }
@@ -112,7 +138,7 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
     wq[0] += 2 * HS;
     wq[1] += 2 * HS;
   }
-  // acc[j][0..7]: G == 8 -> channels 0..7; G < 8 -> [quad hq][4] with logical quad hq ^ flip
+  // channel order of the results: G == 8 -> channels 0..7; G < 8 -> [quad hq][4] with logical quad hq ^ flip
   float bq[2][4];
 #pragma unroll
   for (int hq = 0; hq < 2; ++hq) {
@@ -129,8 +155,11 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
       float o[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        o[c] = acc[j][hq * 4 + c] + bq[hq][c];
-        const float l = lrelu(o[c]);
+        float v;
+        if constexpr (G == 1) v = (c & 1) ? acc[j][hq * 2 + (c >> 1)].y : acc[j][hq * 2 + (c >> 1)].x;
+        else v = acc[j][hq * 4 + c].x + acc[j][hq * 4 + c].y;
+        o[c] = v + bq[hq][c];
+        const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
         s1 += l;
         s2 = fmaf(l, l, s2);
       }
@@ -181,7 +210,7 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
     for (int i = tid; i < 9 * 8 * G; i += NT) {
       const int co = i % G, ci = (i / G) % 8, tap = i / (8 * G);
       const int grp = ci / G, cig = ci - grp * G;
-      wd[tap * 2 * HS + (ci >> 2) * HS + (ci & 3) * G + co] = wsrc[((grp * 9 + tap) * G + cig) * G + co];
+      wd[tap * 2 * HS + (ci >> 2) * HS + oct_w_pos(G, ci, co)] = wsrc[((grp * 9 + tap) * G + cig) * G + co];
     }
     if (tid < 8) b_s[b * 8 + tid] = P[br.b_off + o * 8 + tid];
   }
@@ -250,14 +279,14 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
   for (int it = 0; item < a.n_items; ++it, item += nshare) {
     const int par = it & 1;
     const int next = item + nshare;
-    if (next < a.n_items) issue(next, par ^ 1);
+    if (next < a.n_items && !(a.dbg & 4)) issue(next, par ^ 1);
     cp_async_commit();
     cp_async_wait<1>();                    // this thread's copies of `item` have landed
     __syncthreads();                       // ... and everybody else's; mr[par] is visible
     const int b0 = item * a.S, ns = min(a.S, a.B - b0);
     float* xb = xbuf + par * xsz;
     // ---- LReLU + LayerNorm in place on the interior pixels (4 float4 units per thread in flight) ----
-    for (int s = 0; s < ns; ++s) {
+    for (int s = 0; s < ((a.dbg & 2) ? 0 : ns); ++s) {
       const float sc = mr[(par * a.S + s) * 2], sh = mr[(par * a.S + s) * 2 + 1];
       float* xs = xb + s * a.SHW * 8;
       for (int i0 = tid; i0 < hw * 2; i0 += 4 * NT) {
@@ -288,15 +317,15 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
         }
       }
     }
-    if (next < a.n_items) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
+    if (next < a.n_items && !(a.dbg & 16)) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
     __syncthreads();
     // ---- the branches that read this octet ----
     const bool live = tactive && q < ns;
     bool pv[OCT_PX];
 #pragma unroll
-    for (int j = 0; j < OCT_PX; ++j) pv[j] = live && pin[j];
+    for (int j = 0; j < OCT_PX; ++j) pv[j] = live && pin[j] && !(a.dbg & 8);
     float s1 = 0.f, s2 = 0.f;
-    if (tactive) {
+    if (tactive && !(a.dbg & 1)) {
       // pixel j of this thread: global pixel index (b0 + q) hw + sl + j nsps
       float* dst0 = out_n + ((long long)(b0 + min(q, a.S - 1)) * hw + min(sl, a.nsps - 1)) * a.Cout;
       const int jstride = a.nsps * a.Cout;       // floats between this thread's consecutive pixels
@@ -351,6 +380,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   a.stats_in = g.stats_in; a.stats_out = g.stats_out;
   a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
   a.n_br = g.n_br;
+  { static int d = -1; if (d < 0) { const char* e = getenv("CNF_OCT_DBG"); d = e ? atoi(e) : 0; } a.dbg = d; }
   int halo = 0, n_oct = 0, wtot = 0;
   for (int i = 0; i < g.n_br; ++i) {
     const GconvBranch& b = g.br[i];
