@@ -10,10 +10,13 @@
 // transformed (LReLU + LayerNorm, in place) and convolved.  Octets that feed more branches get proportionally more CTAs
 // (host-side split, launch_gconv_oct).
 //
-// Compute: a thread owns 4 pixels x the full octet (8 in, 8 out); the weights are block-diagonal with G x G blocks
-// (G = group width in {1, 2, 4, 8}), so a pixel-tap costs 8 G FFMA from two 128-bit shared loads.  Lanes 4..7 of every
-// group of 8 read the two channel quads in swapped order ("flip"): lanes i and i + 4 sit 128 bytes apart (same banks),
-// so the swap makes the 8-lane phases of the 128-bit loads conflict-free without padding the tile.
+// Compute: a thread owns a COLUMN SEGMENT of 4 output pixels spaced `dil` rows apart x the full octet (8 in, 8 out).  For
+// each kx it loads the 6 input rows the segment's 3 ky taps touch ONCE (6 x 128-bit shared loads per channel quad) and
+// reuses them from registers for the three ky taps, so every staged pixel is read 4.5x instead of 9x.  The weights are
+// block-diagonal with G x G blocks (G = group width in {1, 2, 4, 8}) and are read with warp-uniform (broadcast) addresses.
+// Input channels are consumed in pairs with packed FFMA2 into (even-ci, odd-ci) accumulator pairs.  Lanes of a warp are
+// consecutive columns; the two channel quads of a pixel are stored swapped when bit 2 of the pixel index is set, which
+// makes every 8-lane phase of the 128-bit loads conflict-free without padding the tile.
 #pragma once
 
 namespace cnf {
@@ -23,6 +26,7 @@ constexpr int OCT_PX = 4;
 
 struct OctBranch {
   int dil, G, noct, out_off;  // noct = branch channels / 8; out_off = first channel of the branch in the concat
+  int nsr;                    // column segments (4 rows spaced dil apart) per row residue class: ceil(ceil(h / dil) / 4)
   long long w_off, b_off;
   int w_smem;                 // float offset of this branch's weights inside the weight area
 };
@@ -36,9 +40,10 @@ struct OctArgs {
   const double* stats_in;
   double* stats_out;
   int B, h, w, Cin, Cout, ln;
-  int S, halo, SW, SHW, n_items, n_oct, nsps;   // nsps = pixel slots per sample = ceil(h w / 4)
+  int S, halo, SW, SHW, n_items, n_oct, nsps;   // nsps = column-segment slots per sample (max over the branches)
   int tps;                                      // threads per sample: nsps rounded up to whole warps (nsps itself if < 32)
   int n_br;
+  int nbuf;                                     // 2: cp.async double buffering inside the CTA; 1: single buffer, two CTAs per SM overlap
   int dbg;                                      // CNF_OCT_DBG: 1 skip branches, 2 skip transform, 4 skip copies, 8 skip stores, 16 skip coeffs
   OctBranch br[CNF_MAX_BRANCHES];
   unsigned char cta_first[OCT_MAX + 1];         // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
@@ -58,114 +63,180 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 
 // position of weight (ci, co) of a tap inside its quad half (ci & 4 selects the half): input channels are taken in PAIRS
 // (2k, 2k+1) so that (x[2k], x[2k+1]) * (w[2k][co], w[2k+1][co]) is one FFMA2 into an (even-ci, odd-ci) accumulator pair
+#ifndef OCT_PACKED
+#define OCT_PACKED 0   // 1: FFMA2 with (even-ci, odd-ci) accumulator pairs; 0: scalar FFMA (half the accumulator registers)
+#endif
 __host__ __device__ inline int oct_w_pos(int G, int ci, int co) {
   const int c4 = ci & 3;
+  if (!OCT_PACKED) return c4 * G + co;                    // rows of G outputs per input channel
   if (G == 1) return c4;                                  // depthwise: (w[2k], w[2k+1]) multiplies (x[2k], x[2k+1])
   if (G == 2) return ((c4 >> 1) * 2 + co) * 2 + (c4 & 1);  // quad = 2 groups, each one ci pair
   return ((c4 >> 1) * G + co) * 2 + (c4 & 1);              // G = 4 (quad = the group) or 8 (group = both quads)
 }
 
-// one branch of one item: 9 taps of block-diagonal 8x8 weights on this thread's 4 pixels, then bias, store, statistics
+// byte-free helper: float offset of (pixel P, logical quad hq) inside a swizzled tile
+__device__ __forceinline__ int oct_xoff(int P, int hq) { return P * 8 + ((hq ^ ((P >> 2) & 1)) << 2); }
+
+// one branch of one item for this thread's column segment: output pixels (y0 + j dil, x), j < 4.  P0 = tile pixel index of
+// (y0 - dil, x - dil) (first input row, kx = 0); rows are rstep = dil * SW pixels apart; pixel indices are clamped to Pmax
+// (segments that stick out of the image read in-bounds garbage that is never stored).
 template <int G>
 __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const float* __restrict__ wb,
-                                           const float* __restrict__ bias, const int (&poff)[OCT_PX], int flip, int dil,
-                                           int SW, float* __restrict__ dst, int Cout, const bool (&pv)[OCT_PX],
-                                           float& s1, float& s2) {
-  constexpr int HS = 4 * G + 4;                 // floats between the two weight halves of a tap
-  // G >= 2: acc[j][c] = (sum over even ci, sum over odd ci) of output channel c (G == 8) or of channel c of the quads in
-  // load order (G < 8).  G == 1: acc[j][k] = the two depthwise channels 2k, 2k+1 (load order), k < 4.
+                                           const float* __restrict__ bias, int P0, int Pmax, int rstep, int dil,
+                                           float* __restrict__ dst, long long jstride, int vmask, float& s1, float& s2) {
+  constexpr int HS = 4 * G + 4;                 // floats per (tap, quad) weight block (4 of them padding)
+#if !OCT_PACKED
+  {
+    float acc[OCT_PX][8];
+#pragma unroll
+    for (int j = 0; j < OCT_PX; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+#pragma unroll 1
+    for (int kx = 0; kx < 3; ++kx) {
+      int Pm[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) Pm[m] = min(P0 + kx * dil + m * rstep, Pmax);
+#pragma unroll
+      for (int hq = 0; hq < 2; ++hq) {
+        float4 xw[6];                              // logical quad hq of the 6 input rows
+#pragma unroll
+        for (int m = 0; m < 6; ++m) xw[m] = ld4(xb + oct_xoff(Pm[m], hq));
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* wr = wb + ((ky * 3 + kx) * 2 + hq) * HS;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {            // input channel hq * 4 + i
+            float wv[G];
+            if constexpr (G == 8) {
+              const float4 t0 = ld4(wr + i * 8), t1 = ld4(wr + i * 8 + 4);
+              wv[0] = t0.x; wv[1] = t0.y; wv[2] = t0.z; wv[3] = t0.w; wv[4] = t1.x; wv[5] = t1.y; wv[6] = t1.z; wv[7] = t1.w;
+            } else if constexpr (G == 4) {
+              const float4 t0 = ld4(wr + i * 4);
+              wv[0] = t0.x; wv[1] = t0.y; wv[2] = t0.z; wv[3] = t0.w;
+            } else if constexpr (G == 2) {
+              const float2 t0 = *reinterpret_cast<const float2*>(wr + i * 2);
+              wv[0] = t0.x; wv[1] = t0.y;
+            } else {
+              wv[0] = wr[i];
+            }
+#pragma unroll
+            for (int j = 0; j < OCT_PX; ++j) {
+              const float4 xr = xw[j + ky];
+              const float xv = i == 0 ? xr.x : i == 1 ? xr.y : i == 2 ? xr.z : xr.w;
+              constexpr int GG = G < 4 ? G : 4;
+              const int base = G == 8 ? 0 : hq * 4 + (i / GG) * GG;
+#pragma unroll
+              for (int c = 0; c < G; ++c) acc[j][base + c] = fmaf(xv, wv[c], acc[j][base + c]);
+            }
+          }
+        }
+      }
+    }
+    float bq[8];
+    {
+      const float4 b0 = ld4(bias), b1 = ld4(bias + 4);
+      bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < OCT_PX; ++j) {
+      if (!((vmask >> j) & 1)) continue;
+      float* d = dst + j * jstride;
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        o[c] = acc[j][c] + bq[c];
+        const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
+        s1 += l;
+        s2 = fmaf(l, l, s2);
+      }
+      st4(d, make_float4(o[0], o[1], o[2], o[3]));
+      st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
+    }
+    return;
+  }
+#endif
+  // G >= 2: acc[j][c] = (sum over even ci, sum over odd ci) of output channel c.  G == 1: acc[j][k] = channels 2k, 2k+1.
   constexpr int NA = G == 1 ? 4 : 8;
   float2 acc[OCT_PX][NA];
 #pragma unroll
   for (int j = 0; j < OCT_PX; ++j)
 #pragma unroll
     for (int c = 0; c < NA; ++c) acc[j][c] = make_float2(0.f, 0.f);
-  // running pointers instead of per-tap index arithmetic: xa[j] walks the 3x3 taps of pixel j (first-loaded quad), the
-  // other quad sits d2 floats away; wq[hq] walks the weight rows of the quad loaded hq-th
-  const float* xa[OCT_PX];
-#pragma unroll
-  for (int j = 0; j < OCT_PX; ++j) xa[j] = xb + poff[j] + flip * 4 - (SW + 1) * dil * 8;
-  const int d2 = 4 - 8 * flip;
-  const int dx = dil * 8, dy = (SW - 3) * dil * 8;
-  const float* wq[2] = {wb + flip * HS, wb + (1 - flip) * HS};
 #pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    float4 xq[OCT_PX][2];
+  for (int kx = 0; kx < 3; ++kx) {
+    int Pm[6];
 #pragma unroll
-    for (int j = 0; j < OCT_PX; ++j) {
-      xq[j][0] = ld4(xa[j]);                    // logical quad `flip`
-      xq[j][1] = ld4(xa[j] + d2);               // logical quad `1 - flip`
-      xa[j] += (tap == 2 || tap == 5) ? dx + dy : dx;
-    }
+    for (int m = 0; m < 6; ++m) Pm[m] = min(P0 + kx * dil + m * rstep, Pmax);
 #pragma unroll
     for (int hq = 0; hq < 2; ++hq) {
-      const float* wr = wq[hq];                  // weights of the logical quad hq ^ flip
+      float4 xw[6];                              // logical quad hq of the 6 input rows
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {              // ci pair (2k, 2k+1) of the quad
-        if constexpr (G == 8 || G == 4) {
-          constexpr int NCO = G;
-          float2 wv[NCO];
+      for (int m = 0; m < 6; ++m) xw[m] = ld4(xb + oct_xoff(Pm[m], hq));
 #pragma unroll
-          for (int c = 0; c < NCO; c += 2) {
-            const float4 t = ld4(wr + (k * NCO + c) * 2);
-            wv[c] = make_float2(t.x, t.y);
-            wv[c + 1] = make_float2(t.z, t.w);
-          }
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* wr = wb + ((ky * 3 + kx) * 2 + hq) * HS;
 #pragma unroll
-          for (int j = 0; j < OCT_PX; ++j) {
-            const float2 xp = k == 0 ? make_float2(xq[j][hq].x, xq[j][hq].y) : make_float2(xq[j][hq].z, xq[j][hq].w);
+        for (int k = 0; k < 2; ++k) {            // ci pair (2k, 2k+1) of the quad
+          if constexpr (G == 8 || G == 4) {
+            float2 wv[G];
 #pragma unroll
-            for (int c = 0; c < NCO; ++c) ffma2(acc[j][(G == 8 ? 0 : hq * 4) + c], xp, wv[c]);
-          }
-        } else if constexpr (G == 2) {
-          const float4 t = ld4(wr + k * 4);       // group k of the quad: (w[0][0], w[1][0], w[0][1], w[1][1])
+            for (int c = 0; c < G; c += 2) {
+              const float4 t = ld4(wr + (k * G + c) * 2);
+              wv[c] = make_float2(t.x, t.y);
+              wv[c + 1] = make_float2(t.z, t.w);
+            }
 #pragma unroll
-          for (int j = 0; j < OCT_PX; ++j) {
-            const float2 xp = k == 0 ? make_float2(xq[j][hq].x, xq[j][hq].y) : make_float2(xq[j][hq].z, xq[j][hq].w);
-            ffma2(acc[j][hq * 4 + k * 2], xp, make_float2(t.x, t.y));
-            ffma2(acc[j][hq * 4 + k * 2 + 1], xp, make_float2(t.z, t.w));
-          }
-        } else {
-          const float2 t = *reinterpret_cast<const float2*>(wr + k * 2);
+            for (int j = 0; j < OCT_PX; ++j) {
+              const float4 xr = xw[j + ky];
+              const float2 xp = k == 0 ? make_float2(xr.x, xr.y) : make_float2(xr.z, xr.w);
 #pragma unroll
-          for (int j = 0; j < OCT_PX; ++j) {
-            const float2 xp = k == 0 ? make_float2(xq[j][hq].x, xq[j][hq].y) : make_float2(xq[j][hq].z, xq[j][hq].w);
-            ffma2(acc[j][hq * 2 + k], xp, t);
+              for (int c = 0; c < G; ++c) ffma2(acc[j][(G == 8 ? 0 : hq * 4) + c], xp, wv[c]);
+            }
+          } else if constexpr (G == 2) {
+            const float4 t = ld4(wr + k * 4);     // group k of the quad: (w[0][0], w[1][0], w[0][1], w[1][1])
+#pragma unroll
+            for (int j = 0; j < OCT_PX; ++j) {
+              const float4 xr = xw[j + ky];
+              const float2 xp = k == 0 ? make_float2(xr.x, xr.y) : make_float2(xr.z, xr.w);
+              ffma2(acc[j][hq * 4 + k * 2], xp, make_float2(t.x, t.y));
+              ffma2(acc[j][hq * 4 + k * 2 + 1], xp, make_float2(t.z, t.w));
+            }
+          } else {
+            const float2 t = *reinterpret_cast<const float2*>(wr + k * 2);
+#pragma unroll
+            for (int j = 0; j < OCT_PX; ++j) {
+              const float4 xr = xw[j + ky];
+              const float2 xp = k == 0 ? make_float2(xr.x, xr.y) : make_float2(xr.z, xr.w);
+              ffma2(acc[j][hq * 2 + k], xp, t);
+            }
           }
         }
       }
     }
-    wq[0] += 2 * HS;
-    wq[1] += 2 * HS;
   }
-  // channel order of the results: G == 8 -> channels 0..7; G < 8 -> [quad hq][4] with logical quad hq ^ flip
-  float bq[2][4];
-#pragma unroll
-  for (int hq = 0; hq < 2; ++hq) {
-    const int lq = G == 8 ? hq : (hq ^ flip);
-    const float4 b = ld4(bias + lq * 4);
-    bq[hq][0] = b.x; bq[hq][1] = b.y; bq[hq][2] = b.z; bq[hq][3] = b.w;
+  float bq[8];
+  {
+    const float4 b0 = ld4(bias), b1 = ld4(bias + 4);
+    bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
   }
 #pragma unroll
   for (int j = 0; j < OCT_PX; ++j) {
-    if (!pv[j]) continue;
-    float* d = dst + (long long)j * Cout;       // caller passes dst of pixel 0 with pixel stride folded into Cout arg
+    if (!((vmask >> j) & 1)) continue;
+    float* d = dst + j * jstride;
+    float o[8];
 #pragma unroll
-    for (int hq = 0; hq < 2; ++hq) {
-      float o[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float v;
-        if constexpr (G == 1) v = (c & 1) ? acc[j][hq * 2 + (c >> 1)].y : acc[j][hq * 2 + (c >> 1)].x;
-        else v = acc[j][hq * 4 + c].x + acc[j][hq * 4 + c].y;
-        o[c] = v + bq[hq][c];
-        const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
-        s1 += l;
-        s2 = fmaf(l, l, s2);
-      }
-      const int lq = G == 8 ? hq : (hq ^ flip);
-      st4(d + lq * 4, make_float4(o[0], o[1], o[2], o[3]));
+    for (int c = 0; c < 8; ++c) {
+      float v;
+      if constexpr (G == 1) v = (c & 1) ? acc[j][c >> 1].y : acc[j][c >> 1].x;
+      else v = acc[j][c].x + acc[j][c].y;
+      o[c] = v + bq[c];
+      const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
+      s1 += l;
+      s2 = fmaf(l, l, s2);
     }
+    st4(d, make_float4(o[0], o[1], o[2], o[3]));
+    st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
   }
 }
 
@@ -182,7 +253,7 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
 
   const int xsz = a.S * a.SHW * 8;                          // floats per x buffer
   float* xbuf = oct_smem;                                   // [2][S][SHW][8]
-  float* gb = xbuf + 2 * xsz;                               // [2][hw][8] gamma, beta of the octet
+  float* gb = xbuf + a.nbuf * xsz;                               // [2][hw][8] gamma, beta of the octet
   float* w_s = gb + (a.ln ? 2 * hw * 8 : 0);                // per branch [9][2][4G+4]
   int wtot = 0;
   for (int b = 0; b < a.n_br; ++b) wtot += oct_w_floats(a.br[b].G);
@@ -196,7 +267,7 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
   float* out_n = a.out + (long long)net * a.out_net_stride + o * 8;
 
   // ---- one-time setup: zero tiles (the halo stays zero for the whole launch), tables, weights, gamma/beta ----
-  for (int i = tid; i < 2 * xsz / 4; i += NT) st4(xbuf + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int i = tid; i < a.nbuf * xsz / 4; i += NT) st4(xbuf + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   for (int p = tid; p < hw; p += NT) {
     const int y = p / a.w, x = p - y * a.w;
     pt[p] = (unsigned short)((y + a.halo) * a.SW + x + a.halo);
@@ -224,22 +295,11 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
     }
   }
 
-  // this thread's pixels (same for every item): sample q, slots sl + j nsps
+  // this thread: sample q of the item, slot sl of the sample (the slot -> column-segment map depends on the branch)
   // (a sample's threads are whole warps, so its reduction order -- and therefore every bit of the result -- does not
   // depend on the batch size or on the sample's position inside the item)
   const int q = tid / a.tps, sl = tid - q * a.tps;
   const bool tactive = q < a.S && sl < a.nsps;
-  const int flip = (lane >> 2) & 1;
-  int poff[OCT_PX];
-  bool pin[OCT_PX];
-#pragma unroll
-  for (int j = 0; j < OCT_PX; ++j) {
-    const int p = sl + j * a.nsps;
-    pin[j] = tactive && p < hw;
-    const int pc = min(p, hw - 1);
-    const int y = pc / a.w, x = pc - y * a.w;
-    poff[j] = ((tactive ? q : 0) * a.SHW + (y + a.halo) * a.SW + x + a.halo) * 8;
-  }
   const float inv_n = 1.0f / ((float)hw * (float)a.Cin);
   auto coeffs = [&](int item, int par) {   // LayerNorm coefficients of the samples of `item` -> mr[par]
     if (tid < a.S) {
@@ -264,24 +324,32 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
       float* dst = xb + s * a.SHW * 8;
       for (int i = tid; i < hw * 2; i += NT) {
         const int p = i >> 1, qd = (i & 1) * 4;
-        cp_async16_cg(dst + pt[p] * 8 + qd, src + (long long)p * a.Cin + qd);
+        cp_async16_cg(dst + oct_xoff(s * a.SHW + pt[p], i & 1) - s * a.SHW * 8, src + (long long)p * a.Cin + qd);
       }
     }
   };
   __syncthreads();                         // pt[] and the zero fill are visible before the first copies land
   int item = rank;
-  if (item < a.n_items) {
+  const bool dbl = a.nbuf == 2;
+  if (dbl && item < a.n_items) {
     issue(item, 0);
     coeffs(item, 0);
   }
   cp_async_commit();
 
   for (int it = 0; item < a.n_items; ++it, item += nshare) {
-    const int par = it & 1;
+    const int par = dbl ? (it & 1) : 0;
     const int next = item + nshare;
-    if (next < a.n_items && !(a.dbg & 4)) issue(next, par ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();                    // this thread's copies of `item` have landed
+    if (dbl) {
+      if (next < a.n_items && !(a.dbg & 4)) issue(next, par ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();                  // this thread's copies of `item` have landed
+    } else {
+      if (!(a.dbg & 4)) issue(item, 0);    // single buffer: the SM's other CTA computes while these copies fly
+      cp_async_commit();
+      coeffs(item, 0);
+      cp_async_wait<0>();
+    }
     __syncthreads();                       // ... and everybody else's; mr[par] is visible
     const int b0 = item * a.S, ns = min(a.S, a.B - b0);
     float* xb = xbuf + par * xsz;
@@ -296,7 +364,7 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
         for (int u = 0; u < 4; ++u) {
           const int i = min(i0 + u * NT, hw * 2 - 1);
           const int p = i >> 1, qd = (i & 1) * 4;
-          px[u] = xs + pt[p] * 8 + qd;
+          px[u] = xb + oct_xoff(s * a.SHW + pt[p], i & 1);
           v[u] = ld4(px[u]);
           if (a.ln) {
             g[u] = ld4(gb + p * 8 + qd);
@@ -317,28 +385,34 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
         }
       }
     }
-    if (next < a.n_items && !(a.dbg & 16)) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
+    if (dbl && next < a.n_items && !(a.dbg & 16)) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
     __syncthreads();
     // ---- the branches that read this octet ----
-    const bool live = tactive && q < ns;
-    bool pv[OCT_PX];
-#pragma unroll
-    for (int j = 0; j < OCT_PX; ++j) pv[j] = live && pin[j] && !(a.dbg & 8);
+    const bool live = tactive && q < ns && !(a.dbg & 1);
     float s1 = 0.f, s2 = 0.f;
-    if (tactive && !(a.dbg & 1)) {
-      // pixel j of this thread: global pixel index (b0 + q) hw + sl + j nsps
-      float* dst0 = out_n + ((long long)(b0 + min(q, a.S - 1)) * hw + min(sl, a.nsps - 1)) * a.Cout;
-      const int jstride = a.nsps * a.Cout;       // floats between this thread's consecutive pixels
+    if (live) {
+      const int Pmax = (q + 1) * a.SHW - 1;
       for (int b = 0; b < a.n_br; ++b) {
         const OctBranch& br = a.br[b];
         if (o >= br.noct) continue;
+        // slot -> (column x, row residue r mod dil, segment k): rows y0 + j dil with y0 = r + 4 k dil
+        const int d = br.dil;
+        const int t = sl / a.w, x = sl - t * a.w;
+        const int r = t / br.nsr, k = t - r * br.nsr;
+        const int y0 = r + 4 * k * d;
+        if (r >= d || y0 >= a.h) continue;
+        int vmask = 0;
+#pragma unroll
+        for (int j = 0; j < OCT_PX; ++j) vmask |= (y0 + j * d < a.h && !(a.dbg & 8)) ? (1 << j) : 0;
+        const int P0 = q * a.SHW + (y0 - d + a.halo) * a.SW + x - d + a.halo;
         const float* wb = w_s + br.w_smem;
-        float* d = dst0 + br.out_off;
+        float* dptr = out_n + ((long long)(b0 + q) * hw + (long long)y0 * a.w + x) * a.Cout + br.out_off;
+        const long long jstride = (long long)d * a.w * a.Cout;
         switch (br.G) {
-          case 8: oct_branch<8>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
-          case 4: oct_branch<4>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
-          case 2: oct_branch<2>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
-          default: oct_branch<1>(xb, wb, b_s + b * 8, poff, flip, br.dil, a.SW, d, jstride, pv, s1, s2); break;
+          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
+          case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
+          case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
+          default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
         }
       }
     }
@@ -398,12 +472,20 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   const int hw = g.h * g.w;
   a.halo = halo; a.SW = g.w + 2 * halo; a.SHW = (g.h + 2 * halo) * a.SW; a.n_oct = n_oct;
   if ((long long)a.SHW >= 65536 / 1) return 1;                 // pt[] is 16 bit
-  a.nsps = (hw + OCT_PX - 1) / OCT_PX;
+  a.nsps = 0;
+  for (int i = 0; i < g.n_br; ++i) {
+    const int d = a.br[i].dil;
+    a.br[i].nsr = ((g.h + d - 1) / d + OCT_PX - 1) / OCT_PX;
+    a.nsps = std::max(a.nsps, g.w * d * a.br[i].nsr);
+  }
   a.tps = a.nsps < 32 ? a.nsps : (a.nsps + 31) / 32 * 32;
   // samples per item: as many as keep <= 512 threads busy and fit the shared-memory budget
   const size_t budget = 227 * 1024 - 1024;
+  static int nbuf_env = 0;
+  if (!nbuf_env) { const char* e = getenv("CNF_OCT_NBUF"); nbuf_env = (e && e[0] == '1') ? 1 : 2; }
+  a.nbuf = nbuf_env;
   auto smem_for = [&](int S) {
-    size_t f = (size_t)2 * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * 512;
+    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * 512;
     return f * sizeof(float) + (((size_t)hw * 2 + 15) & ~(size_t)15);
   };
   if (a.tps > 512 || smem_for(1) > budget) return 1;
@@ -418,7 +500,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   int S = 0, NT = 0, slots = 0;
   static int s_cap = 0;
   if (!s_cap) { const char* e = getenv("CNF_OCT_S"); s_cap = e ? std::max(1, atoi(e)) : 512; }
-  for (int s = std::max(1, std::min(std::min(512 / a.tps, s_cap), g.B)); s >= 1; --s) {
+  for (int s = std::max(1, std::min(std::min(512 / a.tps, a.nbuf == 1 ? 1 : s_cap), g.B)); s >= 1; --s) {
     if (smem_for(s) > budget) continue;
     if (S && s * a.tps < 96) break;
     S = s;
@@ -459,8 +541,8 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (verbose < 0) { const char* e = getenv("CNF_OCT_VERBOSE"); verbose = e ? atoi(e) : 0; }
   if (verbose > 0) {
     --verbose;
-    fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d\n", g.B, g.h, g.w, g.Cin,
-            g.Cout, S, NT, a.n_items, n_oct, tot, smem, halo);
+    fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d nbuf=%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d\n", g.B, g.h, g.w, g.Cin,
+            g.Cout, a.nbuf, S, NT, a.n_items, n_oct, tot, smem, halo);
   }
   static bool attr_set = false;
   if (!attr_set) {
