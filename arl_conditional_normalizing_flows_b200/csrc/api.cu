@@ -401,7 +401,7 @@ int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLMa
   Ten P, W;
   TRY(borrow(params, "params", 1, &P));
   TRY(borrow(workspace, "workspace", 1, &W, true));
-  if (batch < 1 || which < 0 || which > 1) return fail(CNF_ERR_ARG, "batch >= 1 and which in {0,1} required");
+  if (batch < 1 || which < 0 || which > 2) return fail(CNF_ERR_ARG, "batch >= 1 and which in {0,1,2} required");
   if (P.numel < 2 * c->net_stride) return fail(CNF_ERR_SHAPE, "params too small");
   if (W.bytes < cnf_coupling_workspace_bytes(c, batch)) return fail(CNF_ERR_WORKSPACE, "workspace too small");
   return cuda_rc(run_pw_only(c, P.p, (int)batch, which, W.p, stream), "1x1 conv");

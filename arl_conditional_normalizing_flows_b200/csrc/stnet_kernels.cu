@@ -2106,6 +2106,21 @@ int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, vo
   // the statistics outputs go to the spare slot (index n_ln) so that repeated launches do not disturb the layer
   double* spare = c->n_ln() ? W.stats + slot * c->n_ln() : nullptr;
   if (spare) CU_TRY(cudaMemsetAsync(spare, 0, sizeof(double) * slot, st));
+  if (which == 2) {  // the grouped dilated convs of block 0: Y1 -> Y2 (Y2 is simply rewritten with the same values)
+    GconvArgs g = {};
+    g.in = W.Y1; g.in_net_stride = (long long)B * hw * nk; g.Cin = nk;
+    g.out = W.Y2; g.out_net_stride = (long long)B * hw * cat; g.Cout = cat;
+    g.params = params; g.net_stride = c->net_stride; g.g_off = L.ln2_g; g.be_off = L.ln2_b;
+    g.stats_in = c->n_ln() ? W.stats + slot : nullptr; g.stats_out = spare;
+    g.B = B; g.h = c->h; g.w = c->w; g.ln = c->ln; g.ks = c->ks;
+    g.n_br = (int)L.br.size();
+    for (int i = 0; i < g.n_br; ++i) {
+      const Branch& s = L.br[i];
+      g.br[i].dil = s.dil; g.br[i].groups = s.groups; g.br[i].gin = s.gin; g.br[i].gout = s.gout;
+      g.br[i].out_off = s.out_off; g.br[i].w_off = s.w_off; g.br[i].b_off = s.b_off;
+    }
+    return launch_gconv(g, st);
+  }
   if (which == 0) {
     a.in = W.X; a.in_net_stride = (long long)B * hw * nk; a.K = nk;
     a.w_off = L.pw1_w; a.b_off = L.pw1_b; a.g_off = L.ln1_g; a.be_off = L.ln1_b;

@@ -246,8 +246,9 @@ def run_ours(args):
     ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
     ms_e2e = timed(step_e2e, K, 2)
 
-    # ---- dominant kernel (profiles/: ~40 % of the step): the 1x1 convolution of the 28x28x64 channel layers,
-    # tcgen05 3xTF32 (pw_tc3_kernel<64>), timed ALONE with CUDA events on the stream it is launched on.
+    # ---- dominant kernel (profiles/r01h_summary.md: ~55 % of the step): the fused grouped dilated 3x3 convs of the 28x28x64
+    # channel layers (gconv_oct_kernel, all dilation branches in one launch), timed ALONE with CUDA events on the stream it
+    # is launched on; the 1x1-conv kernel (pw_tc3_kernel<64>, tcgen05 3xTF32) is timed the same way and reported beside it.
     layer = model.coupling_layers[2]        # block 0, mask 2: h,w,nk = 28,28,64
     info = layer._info
     hw, nk, cat = info.h * info.w, info.nk, info.cat
@@ -271,19 +272,33 @@ def run_ours(args):
 
     ms_pw1 = time_pw(0)
     ms_pw2 = time_pw(1)
+    ms_gc = time_pw(2)
     # algorithmic bytes per launch (both nets): read the input once, write the output once (+ residual read);
     # gamma/beta (0.4 MB per net, L2-resident across the batch) and W (16-28 KB) are not counted
     pw1_bytes = 2 * B * hw * (nk + nk) * 4
     pw2_bytes = 2 * B * hw * (cat + nk + nk) * 4
     pw_flops = 2 * 2 * B * hw * nk * (nk + cat)
+    gc_bytes = 2 * B * hw * (nk + cat) * 4
+    gc_macs = 2 * B * hw * sum(info.groups[i] * info.group_in[i] * info.group_out[i] * 9 for i in range(info.n_branches))
     hbm_peak, peak_src = peaks()
-    ach = (pw1_bytes + pw2_bytes) / ((ms_pw1 + ms_pw2) * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "pw_tc3_kernel<64>: 1x1 convs (64->64 and 112->64 + residual) of a 28x28x64 channel "
-            "layer with LReLU+LayerNorm-on-load, tcgen05 3xTF32, both nets, B=256 (two launches averaged by bytes)",
-            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-            "peak_source": peak_src, "ms_per_launch": {"pw1_64to64": ms_pw1, "pw2_112to64_res": ms_pw2},
-            "algorithmic_bytes_per_launch": {"pw1": pw1_bytes, "pw2": pw2_bytes},
-            "tflops_fp32_equivalent": pw_flops / ((ms_pw1 + ms_pw2) * 1e-3) / 1e12}
+    pw_gbs = (pw1_bytes + pw2_bytes) / ((ms_pw1 + ms_pw2) * 1e-3) / 1e9
+    ach = gc_bytes / (ms_gc * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "gconv_oct_kernel: grouped dilated 3x3 convs (d = 1, 2, 4; 64 -> 112 channels) of a 28x28x64 "
+            "channel layer with LReLU+LayerNorm-on-load, fp32 FFMA, both nets, B=256, one launch",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01h_gconv_oct_ncu_full_summary.csv);
+            # below the algorithmic bytes because part of the written tensor is still in the 126 MB L2 when the kernel ends
+            "traffic": 230.3e6 if B == 256 else None,
+            "peak_source": peak_src, "ms_per_launch": ms_gc, "algorithmic_bytes_per_launch": gc_bytes,
+            "note": "this kernel is bound by fp32 FFMA issue / shared-memory operand traffic, not by HBM (DESIGN.md section 3): "
+                    "fp32 rate below, against 148 SMs x 128 FMA/clk x 2 x 1.965 GHz = 74.5 TFLOP/s",
+            "tflops_fp32": 2 * gc_macs / (ms_gc * 1e-3) / 1e12, "frac_of_fp32_ffma_peak": 2 * gc_macs / (ms_gc * 1e-3) / 74.5e12,
+            "pw_tc3_kernel<64>": {"what": "1x1 convs (64->64 and 112->64 + residual), tcgen05 3xTF32, timed alone",
+                                  "GB/s": pw_gbs, "frac_of_hbm_peak": pw_gbs / hbm_peak,
+                                  "ms_per_launch": {"pw1_64to64": ms_pw1, "pw2_112to64_res": ms_pw2},
+                                  "algorithmic_bytes_per_launch": {"pw1": pw1_bytes, "pw2": pw2_bytes},
+                                  "traffic": {"pw1": 165.2e6, "pw2": 357.4e6},
+                                  "tflops_fp32_equivalent": pw_flops / ((ms_pw1 + ms_pw2) * 1e-3) / 1e12}}
 
     # ---- the stand-alone fused coupling-law kernel (mask addressing + affine law + per-sample log-det), the
     # HBM-bound kernel the north star names: 12 bytes per element of u

@@ -158,8 +158,9 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1_compresse
                       const DLManagedTensor* params, DLManagedTensor* A, DLManagedTensor* b,
                       DLManagedTensor* workspace, void* stream);
 
-/* measurement hook: launches ONLY the dominant 1x1-conv kernel of residual block 0 (which = 0: pw1,
- * X -> Y1 with LayerNorm-on-load; which = 1: pw2, Y2 (+X) -> X) on the workspace state left by a
+/* measurement hook: launches ONLY one kernel of residual block 0 (which = 0: pw1, X -> Y1 with
+ * LayerNorm-on-load; which = 1: pw2, Y2 (+X) -> X; which = 2: the fused grouped dilated convs, Y1 -> Y2)
+ * on the workspace state left by a
  * previous cnf_coupling_nets / cnf_coupling_forward call with the same batch.  Used by bench.py to time that
  * kernel alone with CUDA events (roofline).  Replaces nothing in the reference. */
 int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace,

@@ -89,8 +89,17 @@ def init_weights(plan, kind='rand', seed=0, ln=True):
 
 
 def synth_inputs(cfg, B, seed=0):
-    """Synthetic xy batches of SURVEY §8(d).  cfg in {'cfg2','cfg3','noise:<H>x<W>x<D>'}."""
+    """Synthetic xy batches of SURVEY §8(d).  cfg in {'cfg2','cfg3','cfg4','cfg5','noise:<H>x<W>x<D>'}."""
     rng = np.random.default_rng(seed)
+    if cfg == 'cfg4':
+        # super-resolution: hr ~ U[0,1) 64x64x3, y = 8x8 block means repeated to 64x64 (up^3(down^3(hr)), F:74-164),
+        # x = hr - y (RESIDUAL, F:252-253), xy = concat(x, y) with 2 % noise (C:312-315)
+        from .data_np import preprocess_SR
+        hr = rng.uniform(0, 1, (B, 64, 64, 3)).astype(np.float32)
+        xy = preprocess_SR(hr, levels=(0, 3)).astype(np.float64)
+        return (0.98 * xy + 0.02 * rng.standard_normal(xy.shape)).astype(np.float32)
+    if cfg == 'cfg5':
+        return rng.standard_normal((B, 128, 128, 4)).astype(np.float32)   # pre-training on noise (P:102-115)
     if cfg in ('cfg2', 'cfg3'):
         H, W, xd = (28, 28, 1) if cfg == 'cfg2' else (32, 32, 3)
         img = 0.98 * rng.uniform(0, 1, (B, H, W, xd)) + 0.02 * rng.standard_normal((B, H, W, xd))

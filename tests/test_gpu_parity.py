@@ -51,6 +51,12 @@ CFG2 = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0],
             num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
 CFG3 = dict(io_shape=[32, 32, 4], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
             num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
+# BASELINE configs 4 and 5 in their "light" variants (the reference's default lists violate
+# `nb_channels % cardinality` on the checkerboard layers once dilation 8 appears, quirk Q6)
+CFG4 = dict(io_shape=[64, 64, 6], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+            num_kernels_list=[64, 64, 32, 32], cardinality_list=[4, 4, 2, 2])
+CFG5 = dict(io_shape=[128, 128, 4], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+            num_kernels_list=[64, 64, 32, 32], cardinality_list=[2, 2, 2, 2])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -185,14 +191,15 @@ def test_coupling_layer_vs_oracle(dev, case):
 @pytest.mark.parametrize("name,cfg,B,kind", [
     ("tiny", TINY, 5, 'rand'), ("small", SMALL, 4, 'rand'), ("small-init", SMALL, 4, 'init'),
     ("mid", MID, 3, 'rand'), ("cfg2", CFG2, 2, 'rand'), ("cfg2-init", CFG2, 2, 'init'), ("cfg3", CFG3, 2, 'rand'),
+    ("cfg4", CFG4, 2, 'rand'), ("cfg5", CFG5, 1, 'rand'),
 ])
 def test_flow_forward_inverse_loss_vs_oracle(dev, name, cfg, B, kind):
     m, o = mk(cfg, kind, seed=2)
     H, W, D = cfg['io_shape']
     if name.startswith("cfg2"):
         x = synth_inputs('cfg2', B, seed=3)
-    elif name == "cfg3":
-        x = synth_inputs('cfg3', B, seed=3)
+    elif name in ("cfg3", "cfg4", "cfg5"):
+        x = synth_inputs(name, B, seed=3)
     else:
         x = synth_inputs(f'noise:{H}x{W}x{D}', B, seed=3)
     xt = torch.from_numpy(x).to(dev)
