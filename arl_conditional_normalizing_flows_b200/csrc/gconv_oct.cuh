@@ -61,18 +61,11 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
   d = *reinterpret_cast<float2*>(&dd);
 }
 
-// position of weight (ci, co) of a tap inside its quad half (ci & 4 selects the half): input channels are taken in PAIRS
-// (2k, 2k+1) so that (x[2k], x[2k+1]) * (w[2k][co], w[2k+1][co]) is one FFMA2 into an (even-ci, odd-ci) accumulator pair
+// position of weight (ci, co) of a tap inside its quad block (ci & 4 selects the block): rows of G outputs per input channel
 #ifndef OCT_PACKED
-#define OCT_PACKED 0   // 1: FFMA2 with (even-ci, odd-ci) accumulator pairs; 0: scalar FFMA (half the accumulator registers)
+#define OCT_PACKED 1   // 1: FFMA2 over output-channel pairs with the activation as broadcast scalar operand; 0: scalar FFMA
 #endif
-__host__ __device__ inline int oct_w_pos(int G, int ci, int co) {
-  const int c4 = ci & 3;
-  if (!OCT_PACKED) return c4 * G + co;                    // rows of G outputs per input channel
-  if (G == 1) return c4;                                  // depthwise: (w[2k], w[2k+1]) multiplies (x[2k], x[2k+1])
-  if (G == 2) return ((c4 >> 1) * 2 + co) * 2 + (c4 & 1);  // quad = 2 groups, each one ci pair
-  return ((c4 >> 1) * G + co) * 2 + (c4 & 1);              // G = 4 (quad = the group) or 8 (group = both quads)
-}
+__host__ __device__ inline int oct_w_pos(int G, int ci, int co) { return (ci & 3) * G + co; }
 
 // byte-free helper: float offset of (pixel P, logical quad hq) inside a swizzled tile
 __device__ __forceinline__ int oct_xoff(int P, int hq) { return P * 8 + ((hq ^ ((P >> 2) & 1)) << 2); }
@@ -85,130 +78,64 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
                                            const float* __restrict__ bias, int P0, int Pmax, int rstep, int dil,
                                            float* __restrict__ dst, long long jstride, int vmask, float& s1, float& s2) {
   constexpr int HS = 4 * G + 4;                 // floats per (tap, quad) weight block (4 of them padding)
-#if !OCT_PACKED
-  {
-    float acc[OCT_PX][8];
-#pragma unroll
-    for (int j = 0; j < OCT_PX; ++j)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
-#pragma unroll 1
-    for (int kx = 0; kx < 3; ++kx) {
-      int Pm[6];
-#pragma unroll
-      for (int m = 0; m < 6; ++m) Pm[m] = min(P0 + kx * dil + m * rstep, Pmax);
-#pragma unroll
-      for (int hq = 0; hq < 2; ++hq) {
-        float4 xw[6];                              // logical quad hq of the 6 input rows
-#pragma unroll
-        for (int m = 0; m < 6; ++m) xw[m] = ld4(xb + oct_xoff(Pm[m], hq));
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const float* wr = wb + ((ky * 3 + kx) * 2 + hq) * HS;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {            // input channel hq * 4 + i
-            float wv[G];
-            if constexpr (G == 8) {
-              const float4 t0 = ld4(wr + i * 8), t1 = ld4(wr + i * 8 + 4);
-              wv[0] = t0.x; wv[1] = t0.y; wv[2] = t0.z; wv[3] = t0.w; wv[4] = t1.x; wv[5] = t1.y; wv[6] = t1.z; wv[7] = t1.w;
-            } else if constexpr (G == 4) {
-              const float4 t0 = ld4(wr + i * 4);
-              wv[0] = t0.x; wv[1] = t0.y; wv[2] = t0.z; wv[3] = t0.w;
-            } else if constexpr (G == 2) {
-              const float2 t0 = *reinterpret_cast<const float2*>(wr + i * 2);
-              wv[0] = t0.x; wv[1] = t0.y;
-            } else {
-              wv[0] = wr[i];
-            }
-#pragma unroll
-            for (int j = 0; j < OCT_PX; ++j) {
-              const float4 xr = xw[j + ky];
-              const float xv = i == 0 ? xr.x : i == 1 ? xr.y : i == 2 ? xr.z : xr.w;
-              constexpr int GG = G < 4 ? G : 4;
-              const int base = G == 8 ? 0 : hq * 4 + (i / GG) * GG;
-#pragma unroll
-              for (int c = 0; c < G; ++c) acc[j][base + c] = fmaf(xv, wv[c], acc[j][base + c]);
-            }
-          }
-        }
-      }
-    }
-    float bq[8];
-    {
-      const float4 b0 = ld4(bias), b1 = ld4(bias + 4);
-      bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
-    }
-#pragma unroll
-    for (int j = 0; j < OCT_PX; ++j) {
-      if (!((vmask >> j) & 1)) continue;
-      float* d = dst + j * jstride;
-      float o[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        o[c] = acc[j][c] + bq[c];
-        const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
-        s1 += l;
-        s2 = fmaf(l, l, s2);
-      }
-      st4(d, make_float4(o[0], o[1], o[2], o[3]));
-      st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
-    }
-    return;
-  }
-#endif
-  // G >= 2: acc[j][c] = (sum over even ci, sum over odd ci) of output channel c.  G == 1: acc[j][k] = channels 2k, 2k+1.
-  constexpr int NA = G == 1 ? 4 : 8;
-  float2 acc[OCT_PX][NA];
+  // acc[j][p] = output channels (2p, 2p+1) of pixel j.  A three-register FFMA issues every other cycle on this part; FFMA2
+  // (two FMAs per issue, the activation as broadcast scalar operand, the weight pair straight from a 128-bit load) is
+  // what reaches the fp32 peak.
+  float2 acc[OCT_PX][4];
 #pragma unroll
   for (int j = 0; j < OCT_PX; ++j)
 #pragma unroll
-    for (int c = 0; c < NA; ++c) acc[j][c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < 4; ++c) acc[j][c] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int kx = 0; kx < 3; ++kx) {
-    int Pm[6];
-#pragma unroll
-    for (int m = 0; m < 6; ++m) Pm[m] = min(P0 + kx * dil + m * rstep, Pmax);
+    const int Pk = P0 + kx * dil;
 #pragma unroll
     for (int hq = 0; hq < 2; ++hq) {
       float4 xw[6];                              // logical quad hq of the 6 input rows
 #pragma unroll
-      for (int m = 0; m < 6; ++m) xw[m] = ld4(xb + oct_xoff(Pm[m], hq));
+      for (int m = 0; m < 6; ++m) xw[m] = ld4(xb + oct_xoff(min(Pk + m * rstep, Pmax), hq));
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float* wr = wb + ((ky * 3 + kx) * 2 + hq) * HS;
+        if constexpr (G == 1) {
+          // depthwise: channels (2k, 2k+1) of the quad times their own weights
+          const float4 t = ld4(wr);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {            // ci pair (2k, 2k+1) of the quad
-          if constexpr (G == 8 || G == 4) {
-            float2 wv[G];
+          for (int j = 0; j < OCT_PX; ++j) {
+            const float4 xr = xw[j + ky];
+            ffma2(acc[j][hq * 2], make_float2(xr.x, xr.y), make_float2(t.x, t.y));
+            ffma2(acc[j][hq * 2 + 1], make_float2(xr.z, xr.w), make_float2(t.z, t.w));
+          }
+        } else {
 #pragma unroll
-            for (int c = 0; c < G; c += 2) {
-              const float4 t = ld4(wr + (k * G + c) * 2);
-              wv[c] = make_float2(t.x, t.y);
-              wv[c + 1] = make_float2(t.z, t.w);
+          for (int i = 0; i < 4; ++i) {            // input channel hq * 4 + i; its row of G output weights
+            float2 wv[G / 2];
+            if constexpr (G == 8) {
+              const float4 t0 = ld4(wr + i * 8), t1 = ld4(wr + i * 8 + 4);
+              wv[0] = make_float2(t0.x, t0.y); wv[1] = make_float2(t0.z, t0.w);
+              wv[2] = make_float2(t1.x, t1.y); wv[3] = make_float2(t1.z, t1.w);
+            } else if constexpr (G == 4) {
+              const float4 t0 = ld4(wr + i * 4);
+              wv[0] = make_float2(t0.x, t0.y); wv[1] = make_float2(t0.z, t0.w);
+            } else {
+              wv[0] = *reinterpret_cast<const float2*>(wr + i * 2);
             }
+            // first output pair of this input channel's group: G == 8: 0; G == 4: quad hq; G == 2: group i / 2 of the quad
+            constexpr int NP = G / 2;
+            const int base = G == 8 ? 0 : G == 4 ? hq * 2 : hq * 2 + (i >> 1);
 #pragma unroll
             for (int j = 0; j < OCT_PX; ++j) {
               const float4 xr = xw[j + ky];
-              const float2 xp = k == 0 ? make_float2(xr.x, xr.y) : make_float2(xr.z, xr.w);
+              const float xv = i == 0 ? xr.x : i == 1 ? xr.y : i == 2 ? xr.z : xr.w;
 #pragma unroll
-              for (int c = 0; c < G; ++c) ffma2(acc[j][(G == 8 ? 0 : hq * 4) + c], xp, wv[c]);
-            }
-          } else if constexpr (G == 2) {
-            const float4 t = ld4(wr + k * 4);     // group k of the quad: (w[0][0], w[1][0], w[0][1], w[1][1])
-#pragma unroll
-            for (int j = 0; j < OCT_PX; ++j) {
-              const float4 xr = xw[j + ky];
-              const float2 xp = k == 0 ? make_float2(xr.x, xr.y) : make_float2(xr.z, xr.w);
-              ffma2(acc[j][hq * 4 + k * 2], xp, make_float2(t.x, t.y));
-              ffma2(acc[j][hq * 4 + k * 2 + 1], xp, make_float2(t.z, t.w));
-            }
-          } else {
-            const float2 t = *reinterpret_cast<const float2*>(wr + k * 2);
-#pragma unroll
-            for (int j = 0; j < OCT_PX; ++j) {
-              const float4 xr = xw[j + ky];
-              const float2 xp = k == 0 ? make_float2(xr.x, xr.y) : make_float2(xr.z, xr.w);
-              ffma2(acc[j][hq * 2 + k], xp, t);
+              for (int c = 0; c < NP; ++c) {
+#if OCT_PACKED
+                ffma2(acc[j][base + c], make_float2(xv, xv), wv[c]);
+#else
+                acc[j][base + c].x = fmaf(xv, wv[c].x, acc[j][base + c].x);
+                acc[j][base + c].y = fmaf(xv, wv[c].y, acc[j][base + c].y);
+#endif
+              }
             }
           }
         }
@@ -227,10 +154,7 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
     float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      float v;
-      if constexpr (G == 1) v = (c & 1) ? acc[j][c >> 1].y : acc[j][c >> 1].x;
-      else v = acc[j][c].x + acc[j][c].y;
-      o[c] = v + bq[c];
+      o[c] = ((c & 1) ? acc[j][c >> 1].y : acc[j][c >> 1].x) + bq[c];
       const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
       s1 += l;
       s2 = fmaf(l, l, s2);
@@ -240,8 +164,7 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
   }
 }
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
+__device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
   extern __shared__ __align__(16) float oct_smem[];
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
   const int net = blockIdx.y;
@@ -441,6 +364,11 @@ __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) {
   cp_async_wait<0>();
 }
 
+// 128 registers: each of the 4 schedulers owns 16 K registers and up to 4 of the CTA's 13-16 warps.  The shared-memory
+// carve-out leaves almost no L1, so a spilled value costs an L2 round trip -- the kernel must not spill (ptxas -v: 0 bytes).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) { gconv_oct_body(a); }
+
 // Host side: eligibility, shared-memory budget, CTA split.  Returns 1 if the shape is not covered (caller falls back to
 // the per-branch kernels), 0 on success, a cudaError otherwise.
 static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
@@ -514,10 +442,12 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   // CTA split: half of the slots per net; octet o gets CTAs in proportion to its FFMA work
   int per_net = std::max(n_oct, slots);
   if (per_net > n_oct * a.n_items) per_net = std::max(n_oct, n_oct * a.n_items);
+  static float ovh = -1.f;
+  if (ovh < 0.f) { const char* e = getenv("CNF_OCT_OVH"); ovh = e ? (float)atof(e) : 24.f; }
   float work[OCT_MAX];
   int nc[OCT_MAX];
   for (int o = 0; o < n_oct; ++o) {
-    work[o] = 24.f;                                            // staging / transform overhead in the same units
+    work[o] = ovh;                                             // per-item staging / transform / barrier overhead in the same units
     for (int i = 0; i < g.n_br; ++i)
       if (o < a.br[i].noct) work[o] += 8.f * a.br[i].G + 6.f;  // FFMA per pixel-tap + epilogue share
     nc[o] = 1;
@@ -541,13 +471,16 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (verbose < 0) { const char* e = getenv("CNF_OCT_VERBOSE"); verbose = e ? atoi(e) : 0; }
   if (verbose > 0) {
     --verbose;
-    fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d nbuf=%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d\n", g.B, g.h, g.w, g.Cin,
-            g.Cout, a.nbuf, S, NT, a.n_items, n_oct, tot, smem, halo);
+    fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d nbuf=%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d split=%d,%d,..,%d\n", g.B, g.h, g.w, g.Cin,
+            g.Cout, a.nbuf, S, NT, a.n_items, n_oct, tot, smem, halo, nc[0], n_oct > 1 ? nc[1] : 0, nc[n_oct - 1]);
   }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gconv_oct_kernel<448>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    // several small CTAs per SM only co-reside if the carve-out is the maximum
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<448>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
