@@ -22,7 +22,11 @@
 namespace cnf {
 
 constexpr int OCT_MAX = 32;   // octets per tensor (nk <= 256)
-constexpr int OCT_PX = 4;
+#ifndef OCT_PX_N
+#define OCT_PX_N 7
+#endif
+constexpr int OCT_PX = OCT_PX_N;   // rows per column segment
+constexpr int OCT_MAXT = 256;      // threads per CTA (8 warps: 2 per scheduler, up to 255 registers each)
 
 struct OctBranch {
   int dil, G, noct, out_off;  // noct = branch channels / 8; out_off = first channel of the branch in the concat
@@ -43,6 +47,7 @@ struct OctArgs {
   int S, halo, SW, SHW, n_items, n_oct, nsps;   // nsps = column-segment slots per sample (max over the branches)
   int tps;                                      // threads per sample: nsps rounded up to whole warps (nsps itself if < 32)
   int n_br;
+  int vec8;                                     // 256-bit stores: out 32-byte aligned, Cout % 8 == 0
   int nbuf;                                     // 2: cp.async double buffering inside the CTA; 1: single buffer, two CTAs per SM overlap
   int dbg;                                      // CNF_OCT_DBG: 1 skip branches, 2 skip transform, 4 skip copies, 8 skip stores, 16 skip coeffs
   OctBranch br[CNF_MAX_BRANCHES];
@@ -76,7 +81,8 @@ __device__ __forceinline__ int oct_xoff(int P, int hq) { return P * 8 + ((hq ^ (
 template <int G>
 __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const float* __restrict__ wb,
                                            const float* __restrict__ bias, int P0, int Pmax, int rstep, int dil,
-                                           float* __restrict__ dst, long long jstride, int vmask, float& s1, float& s2) {
+                                           float* __restrict__ dst, long long jstride, int vmask, bool vec8, float& s1,
+                                           float& s2) {
   constexpr int HS = 4 * G + 4;                 // floats per (tap, quad) weight block (4 of them padding)
   // acc[j][p] = output channels (2p, 2p+1) of pixel j.  A three-register FFMA issues every other cycle on this part; FFMA2
   // (two FMAs per issue, the activation as broadcast scalar operand, the weight pair straight from a 128-bit load) is
@@ -91,9 +97,9 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
     const int Pk = P0 + kx * dil;
 #pragma unroll
     for (int hq = 0; hq < 2; ++hq) {
-      float4 xw[6];                              // logical quad hq of the 6 input rows
+      float4 xw[OCT_PX + 2];                     // logical quad hq of the OCT_PX + 2 input rows
 #pragma unroll
-      for (int m = 0; m < 6; ++m) xw[m] = ld4(xb + oct_xoff(min(Pk + m * rstep, Pmax), hq));
+      for (int m = 0; m < OCT_PX + 2; ++m) xw[m] = ld4(xb + oct_xoff(min(Pk + m * rstep, Pmax), hq));
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float* wr = wb + ((ky * 3 + kx) * 2 + hq) * HS;
@@ -159,10 +165,19 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
       s1 += l;
       s2 = fmaf(l, l, s2);
     }
-    st4(d, make_float4(o[0], o[1], o[2], o[3]));
-    st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
+    // one 256-bit store per pixel (32 lanes = 32 different lines either way; half the store instructions and tag look-ups)
+    if (vec8) st8(d, o);
+    else {
+      st4(d, make_float4(o[0], o[1], o[2], o[3]));
+      st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
+    }
   }
 }
+
+#define OCT_STAMP(slot)                                                                                          \
+  do {                                                                                                           \
+    if ((a.dbg & 128) && rank == 0 && net == 0 && tid == 0 && it < 32 && o < 8) g_tc3_clk[(o * 32 + it) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
   extern __shared__ __align__(16) float oct_smem[];
@@ -263,6 +278,7 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
   for (int it = 0; item < a.n_items; ++it, item += nshare) {
     const int par = dbl ? (it & 1) : 0;
     const int next = item + nshare;
+    OCT_STAMP(0);
     if (dbl) {
       if (next < a.n_items && !(a.dbg & 4)) issue(next, par ^ 1);
       cp_async_commit();
@@ -273,7 +289,9 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
       coeffs(item, 0);
       cp_async_wait<0>();
     }
+    OCT_STAMP(1);
     __syncthreads();                       // ... and everybody else's; mr[par] is visible
+    OCT_STAMP(2);
     const int b0 = item * a.S, ns = min(a.S, a.B - b0);
     float* xb = xbuf + par * xsz;
     // ---- LReLU + LayerNorm in place on the interior pixels (4 float4 units per thread in flight) ----
@@ -308,8 +326,10 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
         }
       }
     }
+    OCT_STAMP(3);
     if (dbl && next < a.n_items && !(a.dbg & 16)) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
     __syncthreads();
+    OCT_STAMP(4);
     // ---- the branches that read this octet ----
     const bool live = tactive && q < ns && !(a.dbg & 1);
     float s1 = 0.f, s2 = 0.f;
@@ -322,7 +342,7 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
         const int d = br.dil;
         const int t = sl / a.w, x = sl - t * a.w;
         const int r = t / br.nsr, k = t - r * br.nsr;
-        const int y0 = r + 4 * k * d;
+        const int y0 = r + OCT_PX * k * d;
         if (r >= d || y0 >= a.h) continue;
         int vmask = 0;
 #pragma unroll
@@ -331,14 +351,16 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
         const float* wb = w_s + br.w_smem;
         float* dptr = out_n + ((long long)(b0 + q) * hw + (long long)y0 * a.w + x) * a.Cout + br.out_off;
         const long long jstride = (long long)d * a.w * a.Cout;
+        const bool vec8 = a.vec8 && !(br.out_off & 7);
         switch (br.G) {
-          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
-          case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
-          case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
-          default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, s1, s2); break;
+          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
+          case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
+          case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
+          default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
         }
       }
     }
+    OCT_STAMP(5);
     // statistics of LReLU(out): fixed-order reduction (bit-reproducible run to run), fp64 across CTAs
     if (a.stats_out) {
       if (a.nsps >= 32) {
@@ -353,6 +375,7 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
       }
     }
     __syncthreads();                       // everyone is done with xb (the next iteration refills it); red is complete
+    OCT_STAMP(6);
     if (a.stats_out && tid < 2 * a.S && (tid >> 1) < ns) {
       const int s = tid >> 1, which = tid & 1;
       double t = 0.0;
@@ -382,6 +405,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   a.stats_in = g.stats_in; a.stats_out = g.stats_out;
   a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
   a.n_br = g.n_br;
+  a.vec8 = (((uintptr_t)g.out & 31) == 0 && (g.Cout % 8) == 0 && ((g.out_net_stride * 4) % 32) == 0) ? 1 : 0;
   { static int d = -1; if (d < 0) { const char* e = getenv("CNF_OCT_DBG"); d = e ? atoi(e) : 0; } a.dbg = d; }
   int halo = 0, n_oct = 0, wtot = 0;
   for (int i = 0; i < g.n_br; ++i) {
@@ -413,10 +437,10 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (!nbuf_env) { const char* e = getenv("CNF_OCT_NBUF"); nbuf_env = (e && e[0] == '1') ? 1 : 2; }
   a.nbuf = nbuf_env;
   auto smem_for = [&](int S) {
-    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * 512;
+    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * OCT_MAXT;
     return f * sizeof(float) + (((size_t)hw * 2 + 15) & ~(size_t)15);
   };
-  if (a.tps > 512 || smem_for(1) > budget) return 1;
+  if (a.tps > OCT_MAXT || smem_for(1) > budget) return 1;
   static int nsm = 0;
   if (!nsm) {
     int dev = 0;
@@ -428,12 +452,12 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   int S = 0, NT = 0, slots = 0;
   static int s_cap = 0;
   if (!s_cap) { const char* e = getenv("CNF_OCT_S"); s_cap = e ? std::max(1, atoi(e)) : 512; }
-  for (int s = std::max(1, std::min(std::min(512 / a.tps, a.nbuf == 1 ? 1 : s_cap), g.B)); s >= 1; --s) {
+  for (int s = std::max(1, std::min(std::min(OCT_MAXT / a.tps, a.nbuf == 1 ? 1 : s_cap), g.B)); s >= 1; --s) {
     if (smem_for(s) > budget) continue;
     if (S && s * a.tps < 96) break;
     S = s;
-    NT = std::min(512, (s * a.tps + 31) / 32 * 32);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, (227 * 1024) / (smem_for(s) + 1024)), 65536 / (NT * 128)));
+    NT = std::min(OCT_MAXT, (s * a.tps + 31) / 32 * 32);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, (227 * 1024) / (smem_for(s) + 1024)), 65536 / (NT * 168)));
     slots = std::min(255, nsm / 2 * per_sm);
     if (((g.B + s - 1) / s) * n_oct >= 3 * slots) break;
   }
@@ -470,22 +494,24 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   static int verbose = -1;
   if (verbose < 0) { const char* e = getenv("CNF_OCT_VERBOSE"); verbose = e ? atoi(e) : 0; }
   if (verbose > 0) {
-    --verbose;
     fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d nbuf=%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d split=%d,%d,..,%d\n", g.B, g.h, g.w, g.Cin,
             g.Cout, a.nbuf, S, NT, a.n_items, n_oct, tot, smem, halo, nc[0], n_oct > 1 ? nc[1] : 0, nc[n_oct - 1]);
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gconv_oct_kernel<448>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    cudaError_t e = cudaFuncSetAttribute(gconv_oct_kernel<OCT_MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     // several small CTAs per SM only co-reside if the carve-out is the maximum
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<448>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<OCT_MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  if (NT <= 448) gconv_oct_kernel<448><<<dim3(tot, 2), NT, smem, st>>>(a);
-  else gconv_oct_kernel<512><<<dim3(tot, 2), NT, smem, st>>>(a);
+  if (verbose > 0) {
+    int occ = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gconv_oct_kernel<OCT_MAXT>, NT, smem);
+    fprintf(stderr, "[gconv_oct] resident CTAs per SM at this launch shape: %d\n", occ);
+  }
+  if (verbose > 0) --verbose;
+  gconv_oct_kernel<OCT_MAXT><<<dim3(tot, 2), NT, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
