@@ -226,10 +226,22 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
   if (a.ln) {
     const float* gam = P + a.g_off + o * 8;
     const float* bet = P + a.be_off + o * 8;
-    for (int i = tid; i < hw * 2; i += NT) {
-      const int p = i >> 1, qd = (i & 1) * 4;
-      st4(gb + p * 8 + qd, ld4(gam + (long long)p * a.Cin + qd));
-      st4(gb + hw * 8 + p * 8 + qd, ld4(bet + (long long)p * a.Cin + qd));
+    for (int i0 = tid; i0 < hw * 2; i0 += 4 * NT) {         // 8 global loads in flight per thread
+      float4 gv[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(i0 + u * NT, hw * 2 - 1);
+        gv[u] = ld4(gam + (long long)(i >> 1) * a.Cin + (i & 1) * 4);
+        bv[u] = ld4(bet + (long long)(i >> 1) * a.Cin + (i & 1) * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NT;
+        if (i < hw * 2) {
+          st4(gb + (i >> 1) * 8 + (i & 1) * 4, gv[u]);
+          st4(gb + hw * 8 + (i >> 1) * 8 + (i & 1) * 4, bv[u]);
+        }
+      }
     }
   }
 
@@ -260,9 +272,18 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
     for (int s = 0; s < ns; ++s) {
       const float* src = src_n + (long long)(b0 + s) * hw * a.Cin;
       float* dst = xb + s * a.SHW * 8;
-      for (int i = tid; i < hw * 2; i += NT) {
-        const int p = i >> 1, qd = (i & 1) * 4;
-        cp_async16_cg(dst + oct_xoff(s * a.SHW + pt[p], i & 1) - s * a.SHW * 8, src + (long long)p * a.Cin + qd);
+      for (int i0 = tid; i0 < hw * 2; i0 += 4 * NT) {       // 4 independent table look-ups in flight
+        int off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = min(i0 + u * NT, hw * 2 - 1);
+          off[u] = oct_xoff(s * a.SHW + pt[i >> 1], i & 1) - s * a.SHW * 8;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * NT;
+          if (i < hw * 2) cp_async16_cg(dst + off[u], src + (long long)(i >> 1) * a.Cin + (i & 1) * 4);
+        }
       }
     }
   };
