@@ -1542,6 +1542,152 @@ __global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// 3b. Head conv for narrow outputs (c2 <= 2: the channel-mask layers), streaming form.  out[p][co] = sum_tap sum_c
+//     x[p + off(tap)][c] W[tap][c][co] is evaluated as (i) d[q][tap][co] = sum_c x[q][c] W[tap][c][co] for every pixel q
+//     -- every activation row is read from HBM exactly once, fully coalesced, LReLU+LayerNorm in registers, no halo
+//     staging of the nk-channel tensor -- and (ii) out[p] = sum_tap d[p + off(tap)][tap] from shared memory, followed by
+//     the same tanh*w / exp / coupling law / scatter / log-det epilogue as head_kernel.  One CTA per sample, both nets.
+//     A lane owns one channel quad of a pixel (W of its quad for the 9 taps lives in registers); the nk/4 lanes of a pixel
+//     are reduced with shuffles.  (A variant with one net per pass and 3-4 pixel groups in flight spilled at 128 registers
+//     and was slower: 120 vs 86 us.)
+// ------------------------------------------------------------------------------------------
+template <int C2T>
+__global__ void __launch_bounds__(256, C2T == 1 ? 2 : 1) head2_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float h2_smem[];
+  __shared__ float red[64];
+  __shared__ float mr_s[2][2];
+  constexpr int NV = 9 * C2T;                    // partial sums per pixel and net
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.x;
+  const int hw = a.h * a.w;
+  const int LPP = a.nk >> 2, PPW = 32 / LPP;     // lanes per pixel (4, 8 or 16), pixels per warp step
+  const int cq = lane % LPP, pl = lane / LPP;
+  float* d_s = h2_smem;                          // [2][hw][NV]
+
+  if (tid < 2) {
+    float m_ = 0.f, r_ = 1.f;
+    if (a.ln) ln_coeffs(a.stats_in, (long long)tid * a.B + b, (double)hw * (double)a.nk, m_, r_);
+    mr_s[tid][0] = r_;
+    mr_s[tid][1] = -m_ * r_;
+  }
+  // this lane's weights: wr[net][tap * C2T + co][i] = W[tap][cq * 4 + i][co]
+  float4 wr[2][NV];
+#pragma unroll
+  for (int net = 0; net < 2; ++net) {
+    const float* Wg = a.params + (long long)net * a.net_stride + a.w_off;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int tap = v / C2T, co = v - tap * C2T;
+      float w4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w4[i] = co < a.c2 ? Wg[((long long)tap * a.nk + cq * 4 + i) * a.c2 + co] : 0.f;
+      wr[net][v] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  }
+  __syncthreads();
+  const float sc[2] = {mr_s[0][0], mr_s[1][0]}, sh[2] = {mr_s[0][1], mr_s[1][1]};
+  const long long sample = (long long)b * hw * a.nk;
+  const int nsteps = (hw + PPW - 1) / PPW;
+  for (int g = wid; g < nsteps; g += 8) {
+    const int p = g * PPW + pl;
+    const bool ok = p < hw;
+    const long long e = (long long)min(p, hw - 1) * a.nk + cq * 4;
+    float4 x[2], gm[2], be[2];
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      x[net] = __ldcs(reinterpret_cast<const float4*>(a.in + (long long)net * a.in_net_stride + sample + e));
+      if (a.ln) {
+        const float* P = a.params + (long long)net * a.net_stride;
+        gm[net] = ld4(P + a.g_off + e);
+        be[net] = ld4(P + a.be_off + e);
+      }
+    }
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      float4 v = x[net];
+      v.x = fmaxf(v.x, CNF_LRELU_SLOPE * v.x); v.y = fmaxf(v.y, CNF_LRELU_SLOPE * v.y);
+      v.z = fmaxf(v.z, CNF_LRELU_SLOPE * v.z); v.w = fmaxf(v.w, CNF_LRELU_SLOPE * v.w);
+      if (a.ln) {
+        v.x = fmaf(fmaf(v.x, sc[net], sh[net]), gm[net].x, be[net].x);
+        v.y = fmaf(fmaf(v.y, sc[net], sh[net]), gm[net].y, be[net].y);
+        v.z = fmaf(fmaf(v.z, sc[net], sh[net]), gm[net].z, be[net].z);
+        v.w = fmaf(fmaf(v.w, sc[net], sh[net]), gm[net].w, be[net].w);
+      }
+      float part[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        part[k] = fmaf(v.x, wr[net][k].x, fmaf(v.y, wr[net][k].y, fmaf(v.z, wr[net][k].z, v.w * wr[net][k].w)));
+      for (int m = LPP >> 1; m > 0; m >>= 1) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], m);
+      }
+      if (cq == 0 && ok) {
+        float* dd = d_s + ((long long)net * hw + p) * NV;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dd[k] = part[k];
+      }
+    }
+  }
+  __syncthreads();
+
+  float ld = 0.f;
+  const float* PA = a.params;
+  const float* PB = a.params + a.net_stride;
+  const float tw_ = PA[a.tanh_off];
+  for (int p = tid; p < hw; p += 256) {
+    const int y = p / a.w, x = p - y * a.w;
+    float acc[2][C2T];
+#pragma unroll
+    for (int net = 0; net < 2; ++net)
+#pragma unroll
+      for (int co = 0; co < C2T; ++co) acc[net][co] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = y + ky - 1;
+      if (iy < 0 || iy >= a.h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = x + kx - 1;
+        if (ix < 0 || ix >= a.w) continue;
+        const int q = iy * a.w + ix;
+#pragma unroll
+        for (int net = 0; net < 2; ++net)
+#pragma unroll
+          for (int co = 0; co < C2T; ++co) acc[net][co] += d_s[((long long)net * hw + q) * NV + (ky * 3 + kx) * C2T + co];
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < C2T; ++co) {
+      if (co < a.c2) {
+        const float raw = acc[0][co] + PA[a.b_off + co];
+        const float A = tw_ * tanhf(raw);                                // M:1198, M:114-116
+        const float t = acc[1][co] + PB[a.b_off + co];
+        if (a.mode == HEAD_EMIT || a.mode == HEAD_EMIT_TANH) {
+          const long long e = ((long long)b * hw + p) * a.c2 + co;
+          a.outA[e] = a.mode == HEAD_EMIT ? A : tanhf(raw);
+          a.outB[e] = t;
+        } else {
+          float* ptr = a.view.base + comp_off(a.view, a.mask_c, b, y, x, co);
+          const float u2 = *ptr;
+          if (a.mode == HEAD_FWD) {
+            *ptr = __fadd_rn(__fmul_rn(expf(A), u2), t);                  // M:1307, M:1230-1231
+            ld += A;                                                      // M:1323
+            if (a.outA) a.outA[((long long)b * hw + p) * a.c2 + co] = tanhf(raw);   // training: tanh(raw_A) for the backward pass
+          } else {
+            *ptr = __fmul_rn(__frcp_rn(expf(A)), __fsub_rn(u2, t));       // M:1379, M:1250-1251
+          }
+        }
+      }
+    }
+  }
+  if (a.mode == HEAD_FWD && a.logdet) {
+    double d1, d2;
+    block_sum2(ld, 0.f, red, d1, d2);
+    if (tid == 0) atomicAdd(a.logdet + b, d1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 #define CU_TRY(x)                      \
@@ -1989,7 +2135,26 @@ static int launch_head_t(const HeadArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+template <int C2T>
+static int launch_head2_t(const HeadArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)2 * a.h * a.w * 9 * C2T * sizeof(float);
+  auto kern = head2_kernel<C2T>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  kern<<<a.B, 256, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
 static int launch_head(HeadArgs a, cudaStream_t st) {
+  // narrow heads (channel-mask layers): streaming kernel, every activation row read once
+  static int h2 = -1;
+  if (h2 < 0) { const char* e = getenv("CNF_HEAD2"); h2 = (e && e[0] == '0') ? 0 : 1; }
+  if (h2 && a.ks == 3 && a.c2 <= 2 && (a.nk == 16 || a.nk == 32 || a.nk == 64) &&
+      (size_t)2 * a.h * a.w * 9 * (a.c2 <= 1 ? 1 : 2) * sizeof(float) <= 100 * 1024)
+    return a.c2 <= 1 ? launch_head2_t<1>(a, st) : launch_head2_t<2>(a, st);
   if (a.w > HD_NT) return (int)cudaErrorInvalidConfiguration;
   const int n_tiles = (a.h * a.w + HD_NT - 1) / HD_NT;
   a.TH = (a.h + n_tiles - 1) / n_tiles;
