@@ -1542,6 +1542,103 @@ __global__ void __launch_bounds__(HD_NT) head_kernel(const HeadArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// 1c. Stem conv, dedicated form (M:1106-1111, M:1150-1155): out[net][b][p][:] = bias + sum_k u1c[p + off(k)] W[k][:] with
+//     K = 9 c1 (9 .. 108) inputs per pixel.  The generic GEMM staged an im2col tile per CTA with two integer divisions per
+//     element; here one CTA owns one sample (both nets): the compressed input (masked gather from the flow buffer) is staged
+//     once with a zero halo, both weight matrices live in smem, a lane owns one output-channel quad of PX pixels
+//     (32 accumulators for the two nets) and the stores are fully coalesced 128-bit rows.  Write-bound.
+// ------------------------------------------------------------------------------------------
+template <int PX>
+__global__ void __launch_bounds__(256) stem2_kernel(const GemmArgs a) {
+  extern __shared__ __align__(16) float st_smem[];
+  __shared__ float red[64];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.x;
+  const int SW = a.w + 2, SH = a.h + 2;
+  const int in_sz = (SH * SW * a.c1 + 3) & ~3;
+  float* in_s = st_smem;                     // [SH][SW][c1]
+  float* w_s = in_s + in_sz;                 // [2][K][N]
+  float* b_s = w_s + 2 * a.K * a.N;          // [2][N]
+  for (int idx = tid; idx < SH * SW * a.c1; idx += 256) {
+    const int ci = idx % a.c1, pix = idx / a.c1;
+    const int iy = pix / SW - 1, ix = pix % SW - 1;
+    float v = 0.f;
+    if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) v = a.view.base[comp_off(a.view, a.mask, b, iy, ix, ci)];
+    in_s[idx] = v;
+  }
+  for (int net = 0; net < 2; ++net) {
+    const float* P = a.params + (long long)net * a.net_stride;
+    for (int idx = tid; idx < a.K * a.N; idx += 256) w_s[net * a.K * a.N + idx] = P[a.w_off + idx];
+    if (tid < a.N) b_s[net * a.N + tid] = P[a.b_off + tid];
+  }
+  __syncthreads();
+  const int NQ = a.N >> 2, PPW = 32 / NQ;    // lanes per pixel (4, 8, 16), pixel columns per warp
+  const int quad = lane % NQ, pcol = lane / NQ;
+  const float4 bias0 = ld4(b_s + quad * 4), bias1 = ld4(b_s + a.N + quad * 4);
+  float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+  const int per_it = PPW * PX;
+  for (int it = wid; it * per_it < a.hw; it += 8) {
+    int pb[PX];
+    bool ok[PX];
+    float4 acc[2][PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      const int p = it * per_it + j * PPW + pcol;
+      ok[j] = p < a.hw;
+      const int pc = min(p, a.hw - 1);
+      const int y = pc / a.w, x = pc - y * a.w;
+      pb[j] = (y * SW + x) * a.c1;
+      acc[0][j] = bias0;
+      acc[1][j] = bias1;
+    }
+    int k = 0;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int toff = (ky * SW + kx) * a.c1;
+        for (int ci = 0; ci < a.c1; ++ci, ++k) {
+          const float4 w0 = ld4(w_s + k * a.N + quad * 4), w1 = ld4(w_s + (a.K + k) * a.N + quad * 4);
+#pragma unroll
+          for (int j = 0; j < PX; ++j) {
+            const float xv = in_s[pb[j] + toff + ci];
+            acc[0][j].x = fmaf(xv, w0.x, acc[0][j].x); acc[0][j].y = fmaf(xv, w0.y, acc[0][j].y);
+            acc[0][j].z = fmaf(xv, w0.z, acc[0][j].z); acc[0][j].w = fmaf(xv, w0.w, acc[0][j].w);
+            acc[1][j].x = fmaf(xv, w1.x, acc[1][j].x); acc[1][j].y = fmaf(xv, w1.y, acc[1][j].y);
+            acc[1][j].z = fmaf(xv, w1.z, acc[1][j].z); acc[1][j].w = fmaf(xv, w1.w, acc[1][j].w);
+          }
+        }
+      }
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.hw * a.N;
+#pragma unroll
+      for (int j = 0; j < PX; ++j) {
+        if (!ok[j]) continue;
+        const int p = it * per_it + j * PPW + pcol;
+        const float4 o = acc[net][j];
+        __stcs(reinterpret_cast<float4*>(out_s + (long long)p * a.N + quad * 4), o);
+        float l;
+        l = fmaxf(o.x, CNF_LRELU_SLOPE * o.x); s1[net] += l; s2[net] = fmaf(l, l, s2[net]);
+        l = fmaxf(o.y, CNF_LRELU_SLOPE * o.y); s1[net] += l; s2[net] = fmaf(l, l, s2[net]);
+        l = fmaxf(o.z, CNF_LRELU_SLOPE * o.z); s1[net] += l; s2[net] = fmaf(l, l, s2[net]);
+        l = fmaxf(o.w, CNF_LRELU_SLOPE * o.w); s1[net] += l; s2[net] = fmaf(l, l, s2[net]);
+      }
+    }
+  }
+  if (a.stats_out) {
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      double d1, d2;
+      block_sum2(s1[net], s2[net], red, d1, d2);
+      if (tid == 0) {
+        double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+        atomicAdd(so, d1);
+        atomicAdd(so + 1, d2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 3b. Head conv for narrow outputs (c2 <= 2: the channel-mask layers), streaming form.  out[p][co] = sum_tap sum_c
 //     x[p + off(tap)][c] W[tap][c][co] is evaluated as (i) d[q][tap][co] = sum_c x[q][c] W[tap][c][co] for every pixel q
 //     -- every activation row is read from HBM exactly once, fully coalesced, LReLU+LayerNorm in registers, no halo
@@ -1712,8 +1809,28 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+static int launch_stem2(const GemmArgs& a, cudaStream_t st) {
+  const size_t smem = ((((size_t)(a.h + 2) * (a.w + 2) * a.c1 + 3) & ~(size_t)3) + 2 * (size_t)a.K * a.N + 2 * a.N) * sizeof(float);
+  auto kern = stem2_kernel<4>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = std::max(smem, (size_t)48 * 1024);
+  }
+  kern<<<a.B, 256, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
 template <bool STEM>
 static int launch_gemm(GemmArgs a, cudaStream_t st) {
+  if (STEM) {
+    static int s2 = -1;
+    if (s2 < 0) { const char* e = getenv("CNF_STEM2"); s2 = (e && e[0] == '0') ? 0 : 1; }
+    const size_t smem = ((size_t)(a.h + 2) * (a.w + 2) * a.c1 + 4 + 2 * (size_t)a.K * a.N + 2 * a.N) * sizeof(float);
+    if (s2 && a.ks == 3 && a.K == 9 * a.c1 && (a.N == 16 || a.N == 32 || a.N == 64) && !a.w_trans && !a.no_bias && !a.res &&
+        smem <= 200 * 1024)
+      return launch_stem2(a, st);
+  }
   const int Kp = (a.K + 3) & ~3;
   a.KC = std::min(Kp, 128);
   if (a.N > 32) return launch_gemm_t<64, 2, 8, STEM>(a, st);
