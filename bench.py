@@ -246,7 +246,7 @@ def run_ours(args):
     ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
     ms_e2e = timed(step_e2e, K, 2)
 
-    # ---- dominant kernel (profiles/r01h_summary.md: ~55 % of the step): the fused grouped dilated 3x3 convs of the 28x28x64
+    # ---- dominant kernel (profiles/r01i_summary.md: 42 % of the step): the fused grouped dilated 3x3 convs of the 28x28x64
     # channel layers (gconv_oct_kernel, all dilation branches in one launch), timed ALONE with CUDA events on the stream it
     # is launched on; the 1x1-conv kernel (pw_tc3_kernel<64>, tcgen05 3xTF32) is timed the same way and reported beside it.
     layer = model.coupling_layers[2]        # block 0, mask 2: h,w,nk = 28,28,64
@@ -284,11 +284,11 @@ def run_ours(args):
     pw_gbs = (pw1_bytes + pw2_bytes) / ((ms_pw1 + ms_pw2) * 1e-3) / 1e9
     ach = gc_bytes / (ms_gc * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "gconv_oct_kernel: grouped dilated 3x3 convs (d = 1, 2, 4; 64 -> 112 channels) of a 28x28x64 "
-            "channel layer with LReLU+LayerNorm-on-load, fp32 FFMA, both nets, B=256, one launch",
+            "channel layer with LReLU+LayerNorm-on-load, fp32 FFMA2, both nets, B=256, one launch",
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01h_gconv_oct_ncu_full_summary.csv);
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01i_gconv_oct_ncu_full_summary.csv);
             # below the algorithmic bytes because part of the written tensor is still in the 126 MB L2 when the kernel ends
-            "traffic": 230.3e6 if B == 256 else None,
+            "traffic": 232.2e6 if B == 256 else None,
             "peak_source": peak_src, "ms_per_launch": ms_gc, "algorithmic_bytes_per_launch": gc_bytes,
             "note": "this kernel is bound by fp32 FFMA issue / shared-memory operand traffic, not by HBM (DESIGN.md section 3): "
                     "fp32 rate below, against 148 SMs x 128 FMA/clk x 2 x 1.965 GHz = 74.5 TFLOP/s",
