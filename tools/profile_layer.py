@@ -11,8 +11,10 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mask = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 torch.manual_seed(0)
-layer = coupling_layer([28, 28, 2], mask, 3, 8, 64, 3, None, LAYER_NORM=True, which_dilations=[1, 2, 4], device="cuda:0")
-u = torch.randn(B, 28, 28, 2, device="cuda:0")
+small = len(sys.argv) > 4 and sys.argv[4] == "small"      # a level-1 layer of config 2: io (14,14,4), nk 32, cardinality 4
+shape, card, nk, dil = ([14, 14, 4], 4, 32, [1, 2]) if small else ([28, 28, 2], 8, 64, [1, 2, 4])
+layer = coupling_layer(shape, mask, 3, card, nk, 3, None, LAYER_NORM=True, which_dilations=dil, device="cuda:0")
+u = torch.randn(B, *shape, device="cuda:0")
 for _ in range(reps):
     v, s, _ = layer.forward_and_Jacobian(u, 0.0, None)
 torch.cuda.synchronize()
