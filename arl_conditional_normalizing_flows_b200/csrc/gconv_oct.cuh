@@ -51,7 +51,7 @@ struct OctArgs {
   int nbuf;                                     // 2: cp.async double buffering inside the CTA; 1: single buffer, two CTAs per SM overlap
   int dbg;                                      // CNF_OCT_DBG: 1 skip branches, 2 skip transform, 4 skip copies, 8 skip stores, 16 skip coeffs
   OctBranch br[CNF_MAX_BRANCHES];
-  unsigned char cta_first[OCT_MAX + 1];         // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
+  unsigned short cta_first[OCT_MAX + 1];        // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
 };
 
 __host__ __device__ inline int oct_w_floats(int G) { return 9 * 2 * (4 * G + 4); }   // [tap][half][4 rows x G + pad 4]
@@ -471,6 +471,8 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   // walk down from the largest S (<= 512 threads, fits shared memory) until every CTA slot has >= 3 items to pipeline,
   // but keep at least ~96 busy threads per CTA
   int S = 0, NT = 0, slots = 0;
+  static int max_per_sm = 0;
+  if (!max_per_sm) { const char* e = getenv("CNF_OCT_PER_SM"); max_per_sm = e ? std::max(1, atoi(e)) : 4; }
   static int s_cap = 0;
   if (!s_cap) { const char* e = getenv("CNF_OCT_S"); s_cap = e ? std::max(1, atoi(e)) : 512; }
   for (int s = std::max(1, std::min(std::min(OCT_MAXT / a.tps, a.nbuf == 1 ? 1 : s_cap), g.B)); s >= 1; --s) {
@@ -478,8 +480,8 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
     if (S && s * a.tps < 96) break;
     S = s;
     NT = std::min(OCT_MAXT, (s * a.tps + 31) / 32 * 32);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, (227 * 1024) / (smem_for(s) + 1024)), 65536 / (NT * 168)));
-    slots = std::min(255, nsm / 2 * per_sm);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(max_per_sm, (227 * 1024) / (smem_for(s) + 1024)), 65536 / (NT * 200)));
+    slots = std::min(1023, nsm / 2 * per_sm);
     if (((g.B + s - 1) / s) * n_oct >= 3 * slots) break;
   }
   a.S = S;
@@ -508,9 +510,9 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
     ++nc[best];
   }
   int tot = 0;
-  for (int o = 0; o < n_oct; ++o) { a.cta_first[o] = (unsigned char)tot; tot += nc[o]; }
-  a.cta_first[n_oct] = (unsigned char)tot;
-  if (tot > 255) return 1;
+  for (int o = 0; o < n_oct; ++o) { a.cta_first[o] = (unsigned short)tot; tot += nc[o]; }
+  a.cta_first[n_oct] = (unsigned short)tot;
+  if (tot > 1023) return 1;
   const size_t smem = smem_for(S);
   static int verbose = -1;
   if (verbose < 0) { const char* e = getenv("CNF_OCT_VERBOSE"); verbose = e ? atoi(e) : 0; }
