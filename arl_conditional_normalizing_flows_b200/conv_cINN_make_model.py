@@ -624,8 +624,13 @@ class cFlow:
         return self._update_trackers(self.log_loss(xy))
 
     # -- gradients of log_loss (the tf.GradientTape block of train_step, M:1863-1871) --------------------------
+    #: True: keep only the per-layer flow states in the forward pass and re-compute each layer's s/t-net activations during
+    #: the backward pass (same gradients, ~1/n_layers of the activation memory, one extra forward pass)
+    recompute_activations = False
+
     def _train_workspace(self, B):
-        need = int(lib.cnf_plan_train_workspace_bytes(self._plan, B))
+        need = int((lib.cnf_plan_train_workspace_bytes_recompute if self.recompute_activations
+                    else lib.cnf_plan_train_workspace_bytes)(self._plan, B))
         ws = getattr(self, '_train_ws', None)
         if ws is None or ws.numel() < need or ws.device != self.params.device:
             self._train_ws = ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
@@ -645,8 +650,9 @@ class cFlow:
         if getattr(self, '_grads', None) is None or self._grads.device != self.params.device:
             self._grads = torch.empty_like(self.params)
         br = Borrowed()
-        check(lib.cnf_flow_loss_and_grad(self._plan, br(xy), br(self.params), br(self._grads), br(zy), br(ll_z),
-                                         br(ll_y), br(ld), br(loss4), br(self._train_workspace(B)), stream_ptr()))
+        fn = lib.cnf_flow_loss_and_grad_recompute if self.recompute_activations else lib.cnf_flow_loss_and_grad
+        check(fn(self._plan, br(xy), br(self.params), br(self._grads), br(zy), br(ll_z), br(ll_y), br(ld), br(loss4),
+                 br(self._train_workspace(B)), stream_ptr()))
         self.last_logdet_per_sample = ld
         self.last_per_sample = {'ll_z': ll_z, 'll_y': ll_y, 'logdet': ld, 'zy': zy}
         return (loss4[0], loss4[1], loss4[2], loss4[3]), self._grads

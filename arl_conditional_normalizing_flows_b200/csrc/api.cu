@@ -224,8 +224,9 @@ namespace {
 struct TrainLayout {
   int64_t state_bytes, states_off, G_off, ld_off, scratch_off, total;
   std::vector<int64_t> saved_off;
+  int64_t ld2_off = 0, tmp_off = 0;   // recompute mode: dummy log-det accumulator, scratch flow buffer
 };
-TrainLayout train_layout(const cnf_plan* p, int64_t B) {
+TrainLayout train_layout(const cnf_plan* p, int64_t B, bool recompute = false) {
   auto al = [](int64_t x) { return (x + 255) & ~int64_t(255); };
   TrainLayout t;
   const int n = (int)p->couplings.size();
@@ -237,7 +238,18 @@ TrainLayout train_layout(const cnf_plan* p, int64_t B) {
   int64_t scratch = 0;
   for (auto* c : p->couplings) scratch = std::max(scratch, coupling_bwd_scratch_bytes(c, B));
   t.scratch_off = off; off += scratch;
-  for (auto* c : p->couplings) { t.saved_off.push_back(off); off += coupling_saved_bytes(c, B); }
+  if (!recompute) {
+    for (auto* c : p->couplings) { t.saved_off.push_back(off); off += coupling_saved_bytes(c, B); }
+  } else {
+    // ONE activation region, re-filled layer by layer during the backward pass (and used as the plain s/t-net workspace in
+    // the forward pass)
+    t.ld2_off = off; off += al(B * 8);
+    t.tmp_off = off; off += t.state_bytes;
+    int64_t region = 0;
+    for (auto* c : p->couplings) region = std::max(region, std::max(coupling_saved_bytes(c, B), al(coupling_ws_bytes(c, B))));
+    for (size_t i = 0; i < p->couplings.size(); ++i) t.saved_off.push_back(off);
+    off += region;
+  }
   t.total = off;
   return t;
 }
@@ -248,9 +260,15 @@ int64_t cnf_plan_train_workspace_bytes(const cnf_plan* p, int64_t batch) {
   return train_layout(p, batch).total;
 }
 
-int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
-                           DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
-                           DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream) {
+int64_t cnf_plan_train_workspace_bytes_recompute(const cnf_plan* p, int64_t batch) {
+  if (!p || batch < 0) return -1;
+  return train_layout(p, batch, true).total;
+}
+
+static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                              DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                              DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream,
+                              bool recompute) {
   if (!p) return fail(CNF_ERR_ARG, "null plan");
   Ten X, P, Gd, Z, A, Bt, L, F, W;
   TRY(borrow(xy, "xy", 4, &X));
@@ -271,7 +289,7 @@ int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const D
   if (P.numel < p->param_count || Gd.numel < p->param_count)
     return fail(CNF_ERR_SHAPE, "params/grads: need %lld floats", (long long)p->param_count);
   if (X.p == Z.p) return fail(CNF_ERR_ARG, "zy must not alias xy");
-  const TrainLayout T = train_layout(p, B);
+  const TrainLayout T = train_layout(p, B, recompute);
   if (W.bytes < T.total) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)T.total, (long long)W.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)W.p;
@@ -295,8 +313,9 @@ int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const D
     (void)src;
     TRY(cuda_rc(launch_copy(sv.state, dst, B * per, stream), "copy"));
     FlowView v = make_view(dst, p->H, p->W, p->D, p->level[li]);
-    TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], v, c->mask, v, (int)B, HEAD_FWD, ldacc, nullptr, nullptr, nullptr,
-                             stream, &sv), "coupling layer"));
+    // recompute mode: plain forward (the shared region is the s/t-net workspace); only the layer's input state is kept
+    TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], v, c->mask, v, (int)B, HEAD_FWD, ldacc, nullptr, nullptr,
+                             recompute ? base + T.saved_off[li] : nullptr, stream, recompute ? nullptr : &sv), "coupling layer"));
   }
   if (n == 0) TRY(cuda_rc(launch_copy(X.p, Z.p, B * per, stream), "copy"));
   TRY(cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream), "logdet"));
@@ -308,12 +327,35 @@ int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const D
   if (const char* e = getenv("CNF_BWD_FIRST_LAYER")) first_layer = atoi(e);
   for (int li = n - 1; li >= first_layer; --li) {
     const cnf_coupling* c = p->couplings[li];
+    if (recompute) {
+      // re-run this layer's forward from its kept input state with every activation saved (same kernels, same reduction
+      // orders: the activations are the ones the first pass produced)
+      float* tmp = (float*)(base + T.tmp_off);
+      double* ld2 = (double*)(base + T.ld2_off);
+      TRY(cuda_rc(launch_copy(saved[li].state, tmp, B * per, stream), "copy"));
+      FlowView tv = make_view(tmp, p->H, p->W, p->D, p->level[li]);
+      TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], tv, c->mask, tv, (int)B, HEAD_FWD, ld2, nullptr, nullptr, nullptr, stream,
+                               &saved[li]), "coupling layer (recompute)"));
+    }
     FlowView gv = make_view(G, p->H, p->W, p->D, p->level[li]);
     FlowView sview = make_view(saved[li].state, p->H, p->W, p->D, p->level[li]);
     TRY(cuda_rc(run_coupling_backward(c, P.p + p->param_off[li], Gd.p + p->param_off[li], saved[li], gv, sview, (int)B,
                                       invB, scratch, stream), "coupling layer backward"));
   }
   return CNF_OK;
+}
+
+int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                           DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                           DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream) {
+  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, false);
+}
+
+int cnf_flow_loss_and_grad_recompute(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                                     DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                                     DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace,
+                                     void* stream) {
+  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, true);
 }
 
 int cnf_adam_step(DLManagedTensor* params, const DLManagedTensor* grads, DLManagedTensor* m, DLManagedTensor* v,

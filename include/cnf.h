@@ -138,6 +138,17 @@ int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const D
                            DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
                            DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
                            DLManagedTensor* workspace, void* stream);
+/* Same result with ~1/n_layers of the activation memory: the forward pass keeps only the flow state in
+ * front of every coupling layer (H*W*D floats per sample and layer); during the backward pass each layer's s/t-net
+ * activations are re-computed from that state into ONE shared region.  The re-computation runs the same kernels with
+ * the same reduction orders, so the gradients equal those of cnf_flow_loss_and_grad; it costs one extra forward pass.
+ * (Recovering the states themselves with the inverse pass, M:1333-1394, is NOT done: with trained weights the fp32
+ * round trip is only ~1e-3 accurate)  workspace: cnf_plan_train_workspace_bytes_recompute bytes. */
+int64_t cnf_plan_train_workspace_bytes_recompute(const cnf_plan* p, int64_t batch);
+int cnf_flow_loss_and_grad_recompute(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                                     DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
+                                     DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
+                                     DLManagedTensor* workspace, void* stream);
 /* optimizer.apply_gradients with keras Adam (M:1874; C:567 / P:130: lr 3e-4, beta 0.9/0.999, eps 1e-7):
  * one fused update of the flat parameter buffer; `step` counts from 1; grads are multiplied by
  * grad_scale first (1/world_size after a data-parallel sum all-reduce). */

@@ -161,3 +161,37 @@ def test_training_reduces_loss(dev):
     first = float(m.log_loss(xy)[0])
     assert np.isfinite(first)
     assert hist['loss'][1] < hist['loss'][0]
+
+
+CFG2_FULL = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+                 num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
+
+
+@pytest.mark.parametrize("cfg,B,shape", [(SMALL, 6, 'noise:8x8x3'), (CFG2_FULL, 8, 'cfg2')])
+def test_recompute_mode_gives_the_same_gradients(dev, cfg, B, shape):
+    """keeping only the per-layer flow states and re-computing each layer's s/t-net activations in the
+    backward pass runs the same kernels in the same order -> same loss, same gradients (1e-6 of the largest entry;
+    the only freedom is the arrival order of fp64 atomics), with a fraction of the workspace."""
+    from arl_conditional_normalizing_flows_b200 import _lib
+    m, _, _ = mk(cfg, 'rand', seed=4)
+    x = torch.from_numpy(synth_inputs(shape, B, seed=5)).to(dev)
+    four_a, g_a = m.loss_and_grad(x)
+    four_a = [float(t) for t in four_a]
+    g_a = g_a.clone()
+    full = int(_lib.lib.cnf_plan_train_workspace_bytes(m._plan, B))
+    small = int(_lib.lib.cnf_plan_train_workspace_bytes_recompute(m._plan, B))
+    assert small < full
+    if cfg is CFG2_FULL:
+        assert small < 0.3 * full                        # the 4 widest of the 16 layers hold most of it: one region instead
+    m.recompute_activations = True
+    m._train_ws = None
+    four_b, g_b = m.loss_and_grad(x)
+    assert m._train_ws.numel() == small
+    np.testing.assert_allclose([float(t) for t in four_b], four_a, rtol=1e-6)
+    scale = float(g_a.abs().max())
+    assert float((g_b - g_a).abs().max()) <= 1e-6 * scale
+    # and the optimizer step works in this mode
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam
+    m.compile(optimizer=Adam(3e-4))
+    logs = m.train_step(x)
+    assert np.isfinite(logs['loss'])
