@@ -18,6 +18,7 @@
 // consecutive columns; the two channel quads of a pixel are stored swapped when bit 2 of the pixel index is set, which
 // makes every 8-lane phase of the 128-bit loads conflict-free without padding the tile.
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
 namespace cnf {
 
@@ -47,6 +48,7 @@ struct OctArgs {
   int S, halo, SW, SHW, n_items, n_oct, nsps;   // nsps = column-segment slots per sample (max over the branches)
   int tps;                                      // threads per sample: nsps rounded up to whole warps (nsps itself if < 32)
   int n_br;
+  int tma;                                      // 1: the tiles (zero halo included) arrive by TMA (cp.async.bulk.tensor.4d, 32-byte swizzle)
   int vec8;                                     // 256-bit stores: out 32-byte aligned, Cout % 8 == 0
   int nbuf;                                     // 2: cp.async double buffering inside the CTA; 1: single buffer, two CTAs per SM overlap
   int dbg;                                      // CNF_OCT_DBG: 1 skip branches, 2 skip transform, 4 skip copies, 8 skip stores, 16 skip coeffs
@@ -179,8 +181,9 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
     if ((a.dbg & 128) && rank == 0 && net == 0 && tid == 0 && it < 32 && o < 8) g_tc3_clk[(o * 32 + it) * 8 + (slot)] = clock64(); \
   } while (0)
 
-__device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
-  extern __shared__ __align__(16) float oct_smem[];
+__device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorMap* tmap) {
+  extern __shared__ __align__(1024) float oct_smem[];
+  __shared__ __align__(8) uint64_t tma_bar[2];
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
   const int net = blockIdx.y;
   const int hw = a.h * a.w;
@@ -205,7 +208,13 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
   float* out_n = a.out + (long long)net * a.out_net_stride + o * 8;
 
   // ---- one-time setup: zero tiles (the halo stays zero for the whole launch), tables, weights, gamma/beta ----
-  for (int i = tid; i < a.nbuf * xsz / 4; i += NT) st4(xbuf + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (!a.tma) {
+    for (int i = tid; i < a.nbuf * xsz / 4; i += NT) st4(xbuf + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+  } else if (tid == 0) {
+    mbar_init(&tma_bar[0], 1);
+    mbar_init(&tma_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int p = tid; p < hw; p += NT) {
     const int y = p / a.w, x = p - y * a.w;
     pt[p] = (unsigned short)((y + a.halo) * a.SW + x + a.halo);
@@ -266,9 +275,26 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
       mr[(par * a.S + tid) * 2 + 1] = sh;
     }
   };
-  auto issue = [&](int item, int par) {    // cp.async the raw octet rows of `item` into buffer `par`
+  auto issue = [&](int item, int par) {    // the raw octet rows of `item` -> buffer `par` (TMA tiles or cp.async pieces)
     const int b0 = item * a.S, ns = min(a.S, a.B - b0);
     float* xb = xbuf + par * xsz;
+    if (a.tma) {
+      // one thread: order the CTA's earlier generic-proxy accesses to the buffer before the async-proxy writes, arm the
+      // barrier with the byte count, one box [SH][SW][8 channels] per sample; out-of-image rows / columns are zero-filled
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bar = smem_u32(&tma_bar[par]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(ns * a.SHW * 32)) : "memory");
+        for (int s = 0; s < ns; ++s) {
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+              ::"r"(smem_u32(xb + s * a.SHW * 8)), "l"((unsigned long long)tmap), "r"(o * 8), "r"(-a.halo), "r"(-a.halo),
+              "r"(net * a.B + b0 + s), "r"(bar)
+              : "memory");
+        }
+      }
+      return;
+    }
     for (int s = 0; s < ns; ++s) {
       const float* src = src_n + (long long)(b0 + s) * hw * a.Cin;
       float* dst = xb + s * a.SHW * 8;
@@ -303,7 +329,8 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
     if (dbl) {
       if (next < a.n_items && !(a.dbg & 4)) issue(next, par ^ 1);
       cp_async_commit();
-      cp_async_wait<1>();                  // this thread's copies of `item` have landed
+      if (a.tma) mbar_wait(&tma_bar[par], (it >> 1) & 1);   // the tile(s) of `item` have landed (async proxy -> visible)
+      else cp_async_wait<1>();             // this thread's copies of `item` have landed
     } else {
       if (!(a.dbg & 4)) issue(item, 0);    // single buffer: the SM's other CTA computes while these copies fly
       cp_async_commit();
@@ -411,7 +438,33 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a) {
 // 128 registers: each of the 4 schedulers owns 16 K registers and up to 4 of the CTA's 13-16 warps.  The shared-memory
 // carve-out leaves almost no L1, so a spilled value costs an L2 round trip -- the kernel must not spill (ptxas -v: 0 bytes).
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a) { gconv_oct_body(a); }
+__global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a, const __grid_constant__ CUtensorMap tmap) {
+  gconv_oct_body(a, &tmap);
+}
+
+// 4-D tensor map over the input [2 nets * B][h][w][Cin] with box [1][h + 2 halo][w + 2 halo][8] and the 32-byte swizzle (16-byte
+// chunk index ^= address bit 7, i.e. the tile's quad swizzle).  Returns false if the driver entry point is unavailable.
+static bool oct_make_tmap(CUtensorMap* tm, const float* in, int rows, int h, int w, int Cin, int SH, int SW) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (encode_fn)ptr;
+  }
+  if (!fn) return false;
+  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)rows};
+  const cuuint64_t gstr[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)w * Cin * 4, (cuuint64_t)h * w * Cin * 4};
+  const cuuint32_t box[4] = {8, (cuuint32_t)SW, (cuuint32_t)SH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // Host side: eligibility, shared-memory budget, CTA split.  Returns 1 if the shape is not covered (caller falls back to
 // the per-branch kernels), 0 on success, a cudaError otherwise.
@@ -534,7 +587,17 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
     fprintf(stderr, "[gconv_oct] resident CTAs per SM at this launch shape: %d\n", occ);
   }
   if (verbose > 0) --verbose;
-  gconv_oct_kernel<OCT_MAXT><<<dim3(tot, 2), NT, smem, st>>>(a);
+  // TMA tiles: nets stacked contiguously, 16-byte aligned strides, boxes <= 256 per dimension, buffers on 256-byte phases
+  static int tma_env = -1;
+  if (tma_env < 0) { const char* e = getenv("CNF_OCT_TMA"); tma_env = (e && e[0] == '0') ? 0 : 1; }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  const int SH = g.h + 2 * halo;
+  a.tma = 0;
+  if (tma_env && a.nbuf == 2 && g.in_net_stride == (long long)g.B * hw * g.Cin && (((uintptr_t)g.in) & 15) == 0 && SH <= 256 &&
+      a.SW <= 256 && (a.SHW % 4) == 0 && ((S * a.SHW) % 8) == 0)
+    a.tma = oct_make_tmap(&tm, g.in, 2 * g.B, g.h, g.w, g.Cin, SH, a.SW) ? 1 : 0;
+  gconv_oct_kernel<OCT_MAXT><<<dim3(tot, 2), NT, smem, st>>>(a, tm);
   return (int)cudaGetLastError();
 }
 

@@ -170,8 +170,9 @@ CFG2_FULL = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0
 @pytest.mark.parametrize("cfg,B,shape", [(SMALL, 6, 'noise:8x8x3'), (CFG2_FULL, 8, 'cfg2')])
 def test_recompute_mode_gives_the_same_gradients(dev, cfg, B, shape):
     """keeping only the per-layer flow states and re-computing each layer's s/t-net activations in the
-    backward pass runs the same kernels in the same order -> same loss, same gradients (1e-6 of the largest entry;
-    the only freedom is the arrival order of fp64 atomics), with a fraction of the workspace."""
+    backward pass runs the same kernels in the same order -> same loss, same gradients up to the arrival order of the
+    fp32 atomics that accumulate the weight gradients (2e-5 of the largest entry; two runs of the stored mode differ by
+    the same amount), with a fraction of the workspace."""
     from arl_conditional_normalizing_flows_b200 import _lib
     m, _, _ = mk(cfg, 'rand', seed=4)
     x = torch.from_numpy(synth_inputs(shape, B, seed=5)).to(dev)
@@ -189,7 +190,7 @@ def test_recompute_mode_gives_the_same_gradients(dev, cfg, B, shape):
     assert m._train_ws.numel() == small
     np.testing.assert_allclose([float(t) for t in four_b], four_a, rtol=1e-6)
     scale = float(g_a.abs().max())
-    assert float((g_b - g_a).abs().max()) <= 1e-6 * scale
+    assert float((g_b - g_a).abs().max()) <= 2e-5 * scale
     # and the optimizer step works in this mode
     from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam
     m.compile(optimizer=Adam(3e-4))
