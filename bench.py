@@ -288,7 +288,7 @@ def run_ours(args):
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01i_gconv_oct_ncu_full_summary.csv);
             # below the algorithmic bytes because part of the written tensor is still in the 126 MB L2 when the kernel ends
-            "traffic": 232.2e6 if B == 256 else None,
+            "traffic": 235.8e6 if B == 256 else None,
             "peak_source": peak_src, "ms_per_launch": ms_gc, "algorithmic_bytes_per_launch": gc_bytes,
             "note": "this kernel is bound by fp32 FFMA issue / shared-memory operand traffic, not by HBM (DESIGN.md section 3): "
                     "fp32 rate below, against 148 SMs x 128 FMA/clk x 2 x 1.965 GHz = 74.5 TFLOP/s",
