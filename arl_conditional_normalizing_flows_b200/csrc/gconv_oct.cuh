@@ -316,6 +316,8 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
   __syncthreads();                         // pt[] and the zero fill are visible before the first copies land
   int item = rank;
   const bool dbl = a.nbuf == 2;
+  const int ctid = tid - (NT - 32);          // lanes of the last warp compute the next item's LayerNorm coefficients
+  double nx0 = 0.0, nx1 = 1.0;
   if (dbl && item < a.n_items) {
     issue(item, 0);
     coeffs(item, 0);
@@ -329,6 +331,13 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
     if (dbl) {
       if (next < a.n_items && !(a.dbg & 4)) issue(next, par ^ 1);
       cp_async_commit();
+      // LayerNorm sums of the NEXT item: loaded now by a few lanes of the last warp, turned into coefficients after the
+      // branches (the load latency never sits in front of a barrier)
+      if (ctid >= 0 && ctid < a.S && a.ln && next < a.n_items && next * a.S + ctid < a.B && !(a.dbg & 16)) {
+        const double* sp = a.stats_in + 2 * ((long long)net * a.B + next * a.S + ctid);
+        nx0 = sp[0];
+        nx1 = sp[1];
+      }
       if (a.tma) mbar_wait(&tma_bar[par], (it >> 1) & 1);   // the tile(s) of `item` have landed (async proxy -> visible)
       else cp_async_wait<1>();             // this thread's copies of `item` have landed
     } else {
@@ -375,7 +384,6 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
       }
     }
     OCT_STAMP(3);
-    if (dbl && next < a.n_items && !(a.dbg & 16)) coeffs(next, par ^ 1);   // global loads overlap the compute phase (visible after 2 barriers)
     __syncthreads();
     OCT_STAMP(4);
     // ---- the branches that read this octet ----
@@ -408,6 +416,17 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
         }
       }
     }
+    if (dbl && ctid >= 0 && ctid < a.S && next < a.n_items && !(a.dbg & 16)) {
+      float sc = 1.f, sh = 0.f;
+      if (a.ln && next * a.S + ctid < a.B) {
+        const float m = (float)nx0 * inv_n;
+        const float var = fmaxf(fmaf(-m, m, (float)nx1 * inv_n), 0.f);
+        sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
+        sh = -m * sc;
+      }
+      mr[((par ^ 1) * a.S + ctid) * 2] = sc;      // read after the next iteration's first barrier
+      mr[((par ^ 1) * a.S + ctid) * 2 + 1] = sh;
+    }
     OCT_STAMP(5);
     // statistics of LReLU(out): fixed-order reduction (bit-reproducible run to run), fp64 across CTAs
     if (a.stats_out) {
@@ -424,8 +443,9 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
     }
     __syncthreads();                       // everyone is done with xb (the next iteration refills it); red is complete
     OCT_STAMP(6);
-    if (a.stats_out && tid < 2 * a.S && (tid >> 1) < ns) {
-      const int s = tid >> 1, which = tid & 1;
+    const int ft = NT >= 64 ? tid - 32 : tid;   // flushed by warp 1: thread 0 goes straight to the next TMA issue
+    if (a.stats_out && ft >= 0 && ft < 2 * a.S && (ft >> 1) < ns) {
+      const int s = ft >> 1, which = ft & 1;
       double t = 0.0;
       const int cnt = a.nsps >= 32 ? (a.tps >> 5) : a.nsps;      // partial sums of sample s: per warp or per thread
       for (int k = 0; k < cnt; ++k) t += (double)red[2 * (s * cnt + k) + which];
