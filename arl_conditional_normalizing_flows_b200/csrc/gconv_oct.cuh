@@ -51,7 +51,7 @@ struct OctArgs {
   int tma;                                      // 1: the tiles (zero halo included) arrive by TMA (cp.async.bulk.tensor.4d, 32-byte swizzle)
   int vec8;                                     // 256-bit stores: out 32-byte aligned, Cout % 8 == 0
   int nbuf;                                     // 2: cp.async double buffering inside the CTA; 1: single buffer, two CTAs per SM overlap
-  int dbg;                                      // CNF_OCT_DBG: 1 skip branches, 2 skip transform, 4 skip copies, 8 skip stores, 16 skip coeffs
+  int dbg;                                      // CNF_OCT_DBG (timing experiments, wrong results): 1 skip branches, 2 transform, 4 copies, 8 epilogue, 16 coeffs, 32 weight loads (G = 8), 128 clock stamps
   OctBranch br[CNF_MAX_BRANCHES];
   unsigned short cta_first[OCT_MAX + 1];        // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
 };
@@ -84,7 +84,7 @@ template <int G>
 __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const float* __restrict__ wb,
                                            const float* __restrict__ bias, int P0, int Pmax, int rstep, int dil,
                                            float* __restrict__ dst, long long jstride, int vmask, bool vec8, float& s1,
-                                           float& s2) {
+                                           float& s2, bool wskip = false) {
   constexpr int HS = 4 * G + 4;                 // floats per (tap, quad) weight block (4 of them padding)
   // acc[j][p] = output channels (2p, 2p+1) of pixel j.  A three-register FFMA issues every other cycle on this part; FFMA2
   // (two FMAs per issue, the activation as broadcast scalar operand, the weight pair straight from a 128-bit load) is
@@ -119,7 +119,8 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
           for (int i = 0; i < 4; ++i) {            // input channel hq * 4 + i; its row of G output weights
             float2 wv[G / 2];
             if constexpr (G == 8) {
-              const float4 t0 = ld4(wr + i * 8), t1 = ld4(wr + i * 8 + 4);
+              float4 t0 = make_float4(0.5f, 0.25f, 0.125f, 0.0625f), t1 = t0;
+              if (!wskip) { t0 = ld4(wr + i * 8); t1 = ld4(wr + i * 8 + 4); }
               wv[0] = make_float2(t0.x, t0.y); wv[1] = make_float2(t0.z, t0.w);
               wv[2] = make_float2(t1.x, t1.y); wv[3] = make_float2(t1.z, t1.w);
             } else if constexpr (G == 4) {
@@ -409,7 +410,7 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
         const long long jstride = (long long)d * a.w * a.Cout;
         const bool vec8 = a.vec8 && !(br.out_off & 7);
         switch (br.G) {
-          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
+          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2, (a.dbg & 32) != 0); break;
           case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
           case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
           default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;

@@ -1,7 +1,7 @@
 """clock64() stamps of the fused grouped-conv kernel (CNF_OCT_DBG=128): thread 0 of the first CTA of every octet (net 0),
 per item: top, copies landed, after barrier A, after transform, after barrier B, after the branches, after barrier C."""
 import os, sys, ctypes
-os.environ['CNF_OCT_DBG'] = '128'
+os.environ['CNF_OCT_DBG'] = os.environ.get('CNF_OCT_DBG_EXTRA', '128')   # add 8: no epilogue, 32: no weight loads
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from arl_conditional_normalizing_flows_b200 import _lib
