@@ -1,22 +1,24 @@
 // Fused grouped dilated 3x3 convs of one residual block (F:364-413, F:577-590): ALL dilation branches in one
-// persistent, double-buffered launch.  Included by stnet_kernels.cu after tc_kernels.cuh (cp.async helpers).
+// persistent, double-buffered launch.  Included by stnet_kernels.cu after tc_kernels.cuh (cp.async / mbarrier helpers).
 //
 // Work decomposition: a CTA owns one OCTET of input channels (8 consecutive channels of the 1x1-conv output) of one
 // net and walks over batch items (S samples each).  Branch d reads the first nk/d channels (Q3), so octet o feeds
 // every branch with nk/d > 8 o: the d = 1 group(s) of the octet, and -- for the low octets -- the d = 2, 4, ... groups
 // that read the same channels.  The activation octet is therefore fetched from HBM/L2 ONCE for all branches
 // (the per-branch kernels fetched it once per branch), gamma/beta of the octet and the octet's weights stay resident in
-// shared memory for the whole launch, and the next item's raw rows stream in with cp.async while the current item is
-// transformed (LReLU + LayerNorm, in place) and convolved.  Octets that feed more branches get proportionally more CTAs
+// shared memory for the whole launch, and the next item's raw tile (zero halo included) arrives by TMA
+// (cp.async.bulk.tensor.4d with the 32-byte swizzle, completion on an mbarrier; 16-byte cp.async pieces where the shape does
+// not allow a tensor map) while the current item is transformed (LReLU + LayerNorm, in place) and convolved.  Octets that feed more branches get proportionally more CTAs
 // (host-side split, launch_gconv_oct).
 //
-// Compute: a thread owns a COLUMN SEGMENT of 4 output pixels spaced `dil` rows apart x the full octet (8 in, 8 out).  For
-// each kx it loads the 6 input rows the segment's 3 ky taps touch ONCE (6 x 128-bit shared loads per channel quad) and
-// reuses them from registers for the three ky taps, so every staged pixel is read 4.5x instead of 9x.  The weights are
+// Compute: a thread owns a COLUMN SEGMENT of OCT_PX = 7 output pixels spaced `dil` rows apart x the full octet (8 in, 8 out).
+// For each kx it loads the 9 input rows the segment's 3 ky taps touch ONCE (9 x 128-bit shared loads per channel quad) and
+// reuses them from registers for the three ky taps, so every staged pixel is read ~3.9x instead of 9x.  The weights are
 // block-diagonal with G x G blocks (G = group width in {1, 2, 4, 8}) and are read with warp-uniform (broadcast) addresses.
-// Input channels are consumed in pairs with packed FFMA2 into (even-ci, odd-ci) accumulator pairs.  Lanes of a warp are
-// consecutive columns; the two channel quads of a pixel are stored swapped when bit 2 of the pixel index is set, which
-// makes every 8-lane phase of the 128-bit loads conflict-free without padding the tile.
+// The FMAs are FFMA2 over output-channel PAIRS with the activation as broadcast scalar operand (no extra accumulators, no
+// spills at 8 warps x <= 200 registers).  Lanes of a warp are consecutive columns; the two channel quads of a pixel are
+// stored swapped when bit 2 of the pixel index is set (= the TMA 32-byte swizzle), which makes every 8-lane phase of the
+// 128-bit loads conflict-free without padding the tile.
 #pragma once
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
@@ -456,8 +458,8 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
   cp_async_wait<0>();
 }
 
-// 128 registers: each of the 4 schedulers owns 16 K registers and up to 4 of the CTA's 13-16 warps.  The shared-memory
-// carve-out leaves almost no L1, so a spilled value costs an L2 round trip -- the kernel must not spill (ptxas -v: 0 bytes).
+// 8 warps (2 per scheduler, each scheduler owns 16 K registers): up to 255 registers per thread.  The shared-memory carve-out
+// leaves almost no L1, so a spilled value costs an L2 round trip -- the kernel must not spill (ptxas -v: 0 bytes).
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a, const __grid_constant__ CUtensorMap tmap) {
   gconv_oct_body(a, &tmap);
