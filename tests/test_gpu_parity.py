@@ -371,3 +371,22 @@ def test_toy_vs_oracle(dev, width, num_layers, n):
     want_inv, _ = o.call(xy, 1)
     got_inv, _ = m(xt, 1)
     assert rel(got_inv.cpu().numpy(), want_inv) < RTOL
+
+
+@pytest.mark.parametrize("shape,nk,card,dil,B", [([28, 28, 2], 64, 8, [1, 2, 4], 9), ([14, 14, 4], 32, 4, [1, 2], 9),
+                                                 ([14, 14, 4], 32, 4, [1, 2], 70), ([32, 32, 4], 64, 8, [1, 2, 4], 5)])
+def test_st_nets_are_batch_independent_bitwise(dev, shape, nk, card, dil, B):
+    """The fused grouped-conv kernel packs several samples into one item (ragged last item, TMA tiles, two buffers); its
+    LayerNorm statistics are reduced in a fixed per-sample order, so any sub-batch reproduces the full batch bit for bit."""
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import coupling_layer
+    layer = coupling_layer(shape, 2, 2, card, nk, 3, None, LAYER_NORM=True, which_dilations=dil, device=dev)
+    info = layer._info
+    g = torch.Generator(device=dev).manual_seed(11)
+    u = torch.randn(B, info.h, info.w, info.c1, device=dev, generator=g)
+    A, b = layer.A_wrapper(u).clone(), layer.b_wrapper(u).clone()
+    assert torch.isfinite(A).all() and torch.isfinite(b).all()
+    for k in (1, 2, B - 1):
+        Ak, bk = layer.A_wrapper(u[:k].contiguous()), layer.b_wrapper(u[:k].contiguous())
+        assert torch.equal(Ak, A[:k]) and torch.equal(bk, b[:k]), k
+    # and a second evaluation of the same batch is identical (no order-dependent accumulation)
+    assert torch.equal(layer.A_wrapper(u), A)
