@@ -82,6 +82,8 @@ def _load():
         "cnf_plan_coupling_param_offset": (I64, [P, I]),
         "cnf_plan_coupling_level": (I, [P, I]),
         "cnf_plan_workspace_bytes": (I64, [P, I64]),
+        "cnf_plan_set_fusion": (I, [P, I]),
+        "cnf_coupling_set_fusion": (I, [P, I]),
         "cnf_flow_forward": (I, [P, P, P, P, P, P, V]),
         "cnf_flow_inverse": (I, [P, P, P, P, P, V]),
         "cnf_flow_log_loss": (I, [P, P, P, P, P, P, P, P, P, V]),

@@ -368,6 +368,11 @@ class coupling_layer(Layer):
     def inverse_coupling_law(self, inv_exp_A_v1, b_v1, v2_compressed):
         return inv_exp_A_v1 * (v2_compressed - b_v1)
 
+    def set_fusion(self, enable):
+        """Inference path selection (no reference counterpart): one activation-resident launch per layer when the
+        layer fits it (default) or the layer-per-kernel path."""
+        check(lib.cnf_coupling_set_fusion(self._h, 1 if enable else 0))
+
     # -- the layer (M:1258-1328, M:1333-1394) -------------------------------------------------------
     def forward_and_Jacobian(self, u, sum_log_detJ, zy):
         u = self._check_uv(u, "u")
@@ -519,6 +524,10 @@ class cFlow:
 
     def compile(self, optimizer=None):
         self.optimizer = optimizer
+
+    def set_fusion(self, enable):
+        """Inference path selection for every coupling layer (see coupling_layer.set_fusion)."""
+        check(lib.cnf_plan_set_fusion(self._plan, 1 if enable else 0))
 
     def count_params(self):
         n = 0

@@ -40,6 +40,7 @@ struct ResBlockLayout {
 struct cnf_coupling {
   int H, W, D, mask, mask_c, R, card, nk, ks, ln;
   int h, w, c1, c2, cat;
+  int fuse = 1;   // inference: use the activation-resident kernel (fused_kernels.cu) when the layer fits it
   std::vector<int> dil;
   int64_t stem_w, stem_b, lnf_g, lnf_b, head_w, head_b, tanh_w;
   std::vector<cnf::ResBlockLayout> rb;
@@ -108,6 +109,11 @@ int64_t coupling_saved_bytes(const cnf_coupling* c, int64_t B);
 CouplingSaved carve_saved(const cnf_coupling* c, int64_t B, void* mem);
 // scratch of the backward pass of one layer (gradient buffers, per-sample LN-backward sums)
 int64_t coupling_bwd_scratch_bytes(const cnf_coupling* c, int64_t B);
+
+// fused_kernels.cu: one launch per coupling layer, s/t-net activations resident in shared memory (inference only).
+// Returns -1 when the layer does not fit that kernel (never a cudaError value), else a cudaError as int.
+int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
+                          int B, int mode, double* logdet_acc, void* ws, void* stream);
 
 int64_t coupling_ws_bytes(const cnf_coupling* c, int64_t B);
 CouplingWorkspace carve_ws(const cnf_coupling* c, int64_t B, void* ws);

@@ -495,6 +495,24 @@ int cnf_plan_coupling_level(const cnf_plan* p, int i) {
   return p->level[i];
 }
 
+int cnf_coupling_set_fusion(cnf_coupling* c, int enable) {
+  if (!c) {
+    set_error("null argument");
+    return CNF_ERR_ARG;
+  }
+  c->fuse = enable ? 1 : 0;
+  return CNF_OK;
+}
+
+int cnf_plan_set_fusion(cnf_plan* p, int enable) {
+  if (!p) {
+    set_error("null argument");
+    return CNF_ERR_ARG;
+  }
+  for (auto* c : p->couplings) c->fuse = enable ? 1 : 0;
+  return CNF_OK;
+}
+
 int64_t cnf_plan_workspace_bytes(const cnf_plan* p, int64_t batch) {
   if (!p || batch < 0) return -1;
   int64_t m = 0;

@@ -2293,6 +2293,10 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
                  const CouplingSaved* sv) {
   cudaStream_t st = (cudaStream_t)stream;
   if (B <= 0) return 0;
+  if (!sv && c->fuse && (mode == HEAD_FWD || mode == HEAD_INV)) {
+    const int rc = launch_fused_coupling(c, params, in_view, in_mask, out_view, B, mode, logdet_acc, ws, stream);
+    if (rc != -1) return rc;
+  }
   CouplingWorkspace W = {};
   if (!sv) W = carve_ws(c, B, ws);
   else W.stats = sv->stats;

@@ -108,6 +108,12 @@ const cnf_coupling* cnf_plan_coupling(const cnf_plan* p, int coupling_idx);
 int64_t cnf_plan_coupling_param_offset(const cnf_plan* p, int coupling_idx);
 int cnf_plan_coupling_level(const cnf_plan* p, int coupling_idx); /* squeezes applied before it */
 int64_t cnf_plan_workspace_bytes(const cnf_plan* p, int64_t batch);
+/* Inference runs a coupling layer whose per-sample s/t-net activations fit one CTA's shared memory (the 14x14 / 7x7
+ * levels of config 2) as ONE activation-resident launch (csrc/fused_kernels.cu); enable = 0 forces the layer-per-kernel
+ * path for every layer (A/B measurements, tests of both paths).  Default: enabled.  Host-side flag of the descriptor,
+ * not thread-safe against concurrent calls that use the same plan.  Replaces nothing in the reference. */
+int cnf_plan_set_fusion(cnf_plan* p, int enable);
+int cnf_coupling_set_fusion(cnf_coupling* c, int enable);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* cFlow.call(xy, direction=+1) (M:1743-1772): zy in the ORIGINAL (H,W,D) layout plus the PER-SAMPLE

@@ -125,11 +125,21 @@ LAYER_CASES = [
     ([14, 14, 4], 3, 3, 4, 32, [1, 2], True),
     ([16, 16, 4], 2, 1, 1, 16, [1, 2], True),     # cardinality 1: plain conv over all channels (F:389-395)
     ([64, 64, 6], 0, 1, 4, 64, [1, 2, 4, 8], True),   # tiled grouped conv, wide head (c2 = 12)
+    # shapes the activation-resident kernel (fused_kernels.cu) covers: config 2 / config 3 below the first level
+    ([28, 28, 2], 1, 3, 8, 64, [1, 2, 4], True),  # (14,14,4) nk 32, groups of 4/2/1, 7-row segments
+    ([14, 14, 4], 0, 3, 4, 32, [1, 2], True),     # (7,7,8) nk 16, c2 = 8
+    ([14, 14, 4], 2, 3, 4, 32, [1, 2], True),     # (14,14,2) nk 32, groups of 8/4
+    ([32, 32, 4], 0, 3, 8, 64, [1, 2, 4], True),  # (16,16,8) nk 32: one 512-thread CTA per SM, 8-row segments
+    ([16, 16, 8], 3, 2, 4, 32, [1, 2], True),     # (16,16,4) nk 32
+    ([16, 16, 8], 1, 2, 4, 32, [1, 2], True),     # (8,8,16) nk 16: c1 = 16, c2 = 16 -> layer-per-kernel path
+    ([16, 16, 6], 2, 2, 4, 32, [1, 2, 4], True),  # (16,16,3) nk 32, groups 8/4/2
+    ([16, 16, 5], 2, 1, 2, 16, [1, 2], True),     # odd depth through the resident kernel: c1 = 3, c2 = 2
 ]
 
 
+@pytest.mark.parametrize("fuse", [1, 0], ids=["resident", "per-kernel"])
 @pytest.mark.parametrize("case", LAYER_CASES, ids=[f"{c[0]}m{c[1]}" for c in LAYER_CASES])
-def test_coupling_layer_vs_oracle(dev, case):
+def test_coupling_layer_vs_oracle(dev, case, fuse):
     from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import coupling_layer
     from oracle.flow_torch import st_net, _t
     shape, m, R, card, nk, dil, ln = case
@@ -138,6 +148,7 @@ def test_coupling_layer_vs_oracle(dev, case):
     W = init_weights({'layers': [L]}, 'rand', seed=11, ln=ln)[0]
     layer = coupling_layer(shape, m, R, card, nk, 3, None, LAYER_NORM=ln, which_dilations=dil, device=dev)
     layer.set_weights(W)
+    layer.set_fusion(fuse)      # activation-resident launch (where the layer fits it) / layer-per-kernel path
     B = 3
     rng = np.random.default_rng(5)
     u = rng.standard_normal((B, *shape)).astype(np.float32)
@@ -236,6 +247,28 @@ def test_flow_forward_inverse_loss_vs_oracle(dev, name, cfg, B, kind):
     td = m.test_step(xt)
     assert set(td) == {'loss', 'z_loss', 'y_loss', 'detJ_loss'}
     np.testing.assert_allclose(td['loss'], four_want[0], rtol=RTOL)
+
+
+@pytest.mark.parametrize("name,cfg,B", [("cfg2", CFG2, 33), ("cfg3", CFG3, 5), ("mid", MID, 4)])
+def test_resident_path_equals_per_kernel_path(dev, name, cfg, B):
+    """The activation-resident launch and the layer-per-kernel path are two implementations of the same layer: same
+    zy / per-sample log-det / samples to fp32 rounding (summation orders differ), and identical pass-through halves."""
+    m, _ = mk(cfg, 'rand', seed=7, dtype=torch.float32)
+    H, W, D = cfg['io_shape']
+    x = torch.from_numpy(synth_inputs(name if name.startswith('cfg') else f'noise:{H}x{W}x{D}', B, seed=4)).to(dev)
+    out = {}
+    for fuse in (1, 0):
+        m.set_fusion(fuse)
+        zy, _ = m(x, 1)
+        out[fuse] = (zy.clone(), m.last_logdet_per_sample.clone(), m(x, -1).clone())
+    for a, b_ in zip(out[1], out[0]):
+        assert torch.isfinite(a).all()
+        err = float((a - b_).abs().max() / b_.abs().max())
+        assert err < 2e-5, err
+    # sub-batches reproduce the full batch bit for bit on the resident path (one CTA per sample, fixed reduction order)
+    m.set_fusion(1)
+    zy_k, _ = m(x[:3].contiguous(), 1)
+    assert torch.equal(zy_k, out[1][0][:3])
 
 
 def test_flow_layerwise_equals_fused_call(dev):
