@@ -80,8 +80,8 @@ struct FusedArgs {
   int ldx, ldy2;                // padded row strides (floats) of X / Y1 and of Y2
   int off_y1, off_y2, off_w;    // smem offsets (floats)
   int pw_variant, nr_variant, c2t;
-  int npg, npg_pad;             // pixel groups of the pw / stem tiling, rounded up to a multiple of 32
-  unsigned div_w_m, div_npgp_m, div_qnk_m, div_qcat_m, div_c1_m, div_sw_m;   // ceil(2^32 / d): n / d == umulhi(n, m), n * d < 2^32
+  int lognl;                    // log2(nk / 4): output quads per warp in the GEMM-shaped stages
+  unsigned div_w_m, div_qnk_m, div_qcat_m, div_c1_m, div_sw_m;   // ceil(2^32 / d): n / d == umulhi(n, m), n * d < 2^32
   double* logdet;
   float* tscratch;              // [B][hw][c2]: t = net b output, parked while net A runs
 };
@@ -92,16 +92,16 @@ struct FzDynamic {
 };
 
 // dilations are 1, 2, 4 (the planner's list for k = 3, M:1553-1617); G0..G2 = group widths of the branches (0 = absent)
-template <int H_, int W_, int NK_, int C1_, int C2_, int G0_, int G1_, int G2_, int NT_, int PXT_, int NO_, int NR_>
+template <int H_, int W_, int NK_, int C1_, int C2_, int G0_, int G1_, int G2_, int NT_, int PXT_, int NR_>
 struct FzStatic {
   static constexpr bool kStatic = true;
   static constexpr int H = H_, W = W_, HW = H_ * W_, NK = NK_, C1 = C1_, C2 = C2_;
   static constexpr int NBR = (G0_ > 0) + (G1_ > 0) + (G2_ > 0);
   static constexpr int CAT = NK_ + (G1_ > 0 ? NK_ / 2 : 0) + (G2_ > 0 ? NK_ / 4 : 0);
   static constexpr int LDX = NK_ + 4, LDY2 = (CAT > NK_ ? CAT : NK_) + 4;
-  static constexpr int NT = NT_, PXT = PXT_, NO = NO_, NR = NR_;
+  static constexpr int NT = NT_, PXT = PXT_, NR = NR_;
+  static constexpr int LOGNL = NK_ == 8 ? 1 : NK_ == 16 ? 2 : NK_ == 32 ? 3 : 4;   // log2(NK / 4)
   static constexpr int C2T = C2_ <= 2 ? 2 : C2_ <= 4 ? 4 : 8;
-  static constexpr int NPG = (HW + PXT_ - 1) / PXT_, NPG_PAD = (NPG + 31) / 32 * 32;
   __host__ __device__ static constexpr int g(int i) { return i == 0 ? G0_ : i == 1 ? G1_ : G2_; }
 };
 
@@ -119,11 +119,9 @@ struct Dm {   // dimension accessors: constants for FzStatic, kernel arguments f
   __device__ __forceinline__ int ldy2() const { if constexpr (S::kStatic) return S::LDY2; else return a.ldy2; }
   __device__ __forceinline__ int nt() const { if constexpr (S::kStatic) return S::NT; else return (int)blockDim.x; }
   __device__ __forceinline__ int n_br() const { if constexpr (S::kStatic) return S::NBR; else return a.n_br; }
-  __device__ __forceinline__ int npg() const { if constexpr (S::kStatic) return S::NPG; else return a.npg; }
-  __device__ __forceinline__ int npg_pad() const { if constexpr (S::kStatic) return S::NPG_PAD; else return a.npg_pad; }
+  __device__ __forceinline__ int lognl() const { if constexpr (S::kStatic) return S::LOGNL; else return a.lognl; }
   // divisions by shape constants (n >= 0)
   __device__ __forceinline__ int div_w(int n) const { if constexpr (S::kStatic) return n / S::W; else return (int)__umulhi((unsigned)n, a.div_w_m); }
-  __device__ __forceinline__ int div_npgp(int n) const { if constexpr (S::kStatic) return n / S::NPG_PAD; else return (int)__umulhi((unsigned)n, a.div_npgp_m); }
   __device__ __forceinline__ int div_qnk(int n) const { if constexpr (S::kStatic) return n / (S::NK / 4); else return (int)__umulhi((unsigned)n, a.div_qnk_m); }
   __device__ __forceinline__ int div_qcat(int n) const { if constexpr (S::kStatic) return n / (S::CAT / 4); else return (int)__umulhi((unsigned)n, a.div_qcat_m); }
   __device__ __forceinline__ int div_c1(int n) const { if constexpr (S::kStatic) return n / S::C1; else return (a.div_c1_m ? (int)__umulhi((unsigned)n, a.div_c1_m) : n); }
@@ -187,30 +185,35 @@ __device__ __forceinline__ void fz_stat2(const float2 o, float& s1, float& s2) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// GEMM-shaped stages.  out[p][n] = bias[n] + sum_k A(p, k) W[k][n] (+ res[p][n]); a thread owns PXT pixels
-// (p_j = pg + j * npg: consecutive lanes -> consecutive pixels) x NO consecutive output channels; thread slot
-// t = nb * npg_pad + pg (npg_pad = npg rounded up to 32), so the lanes of a warp share the output block and the weight
-// loads are warp-uniform (broadcast).
+// GEMM-shaped stages.  out[p][n] = bias[n] + sum_k A(p, k) W[k][n] (+ res[p][n]).
+// A warp owns a tile of (PL * PXT) pixels x all N output channels, as an outer product over its lanes: lane = pgl * NL +
+// nbl with NL = N / 4 output quads and PL = 32 / NL pixel lanes; a thread owns the pixels tile0 + pgl + PL * j (j < PXT)
+// x the 4 outputs of quad nbl.  Shared memory serves the DISTINCT words of a warp-wide load (measured,
+// tools/microbench/lds_patterns.cu: 128 B of distinct 16-byte words per cycle whatever lanes ask for them), so an A load
+// costs PL x 16 B and a W load NL x 16 B: (PXT + 4) wavefronts per 4 k for 4 PXT FFMA2 per lane.
 //   STEM = false: A(p, k) = Ain[p * lda + k]           (1x1 conv, K = channels)
 //   STEM = true : A(p, (tap, ci)) = Ain[((y + ky) * (w + 2) + x + kx) * c1 + ci]   (3x3 conv on the zero-haloed input)
 // --------------------------------------------------------------------------------------------------------------
-template <class S, int PXT, int NO, bool STEM>
+template <class S, int PXT, bool STEM>
 __device__ __forceinline__ void fz_gemm_stage(const FusedArgs& a, const float* __restrict__ Ain, int lda, int K,
                                               const float* __restrict__ Ws, const float* __restrict__ bs,
                                               float* __restrict__ Out, const float* __restrict__ Res, float& s1, float& s2) {
-  constexpr int NP = NO / 2, NQ = NO / 4;
   const Dm<S> d{a};
   const int N = d.nk(), ldo = d.ldx(), hw = d.hw();
-  const int npg = d.npg(), npgp = d.npg_pad();
-  const int nslot = npgp * (N / NO);
-  for (int t = threadIdx.x; t < nslot; t += d.nt()) {
-    const int nb = d.div_npgp(t), pg = t - nb * npgp;
-    if (pg >= npg) continue;
+  const int lognl = d.lognl(), NL = 1 << lognl, PL = 32 >> lognl;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = d.nt() >> 5;
+  const int nbl = lane & (NL - 1), pgl = lane >> lognl;
+  const int tile_px = PL * PXT;
+  const int ntiles = (hw + tile_px - 1) / tile_px;
+  const float* wcol = Ws + 4 * nbl;
+  const float4 bv = ld4(bs + 4 * nbl);
+  for (int tile = wid; tile < ntiles; tile += nw) {
+    const int p0 = tile * tile_px + pgl;
     int pbase[PXT];
-    float2 acc[PXT][NP];
+    float2 acc[PXT][2];
 #pragma unroll
     for (int j = 0; j < PXT; ++j) {
-      const int p = pg + j * npg;
+      const int p = p0 + PL * j;
       const int pc = p < hw ? p : hw - 1;
       if (STEM) {
         const int y = d.div_w(pc), x = pc - y * d.w();
@@ -218,71 +221,78 @@ __device__ __forceinline__ void fz_gemm_stage(const FusedArgs& a, const float* _
       } else {
         pbase[j] = pc * lda;
       }
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const float4 bv = ld4(bs + nb * NO + 4 * q);
-        acc[j][2 * q] = make_float2(bv.x, bv.y);
-        acc[j][2 * q + 1] = make_float2(bv.z, bv.w);
-      }
+      acc[j][0] = make_float2(bv.x, bv.y);
+      acc[j][1] = make_float2(bv.z, bv.w);
     }
-    const float* wcol = Ws + nb * NO;
     if (STEM) {
       const int c1 = d.c1(), SW = d.w() + 2;
-      int k = 0;
+      const int vec = (c1 & 3) == 0 ? 4 : (c1 & 1) == 0 ? 2 : 1;
 #pragma unroll 1
-      for (int ky = 0; ky < 3; ++ky)
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const float* ap = Ain + (ky * SW + kx) * c1;
+        const float* wp = wcol + tap * c1 * N;
+        if (vec == 4) {
 #pragma unroll 1
-        for (int kx = 0; kx < 3; ++kx) {
-          const int toff = (ky * SW + kx) * c1;
-#pragma unroll 2
-          for (int ci = 0; ci < c1; ++ci, ++k) {
-            float4 wv[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) wv[q] = ld4(wcol + k * N + 4 * q);
+          for (int ci = 0; ci < c1; ci += 4) {
+            const float4 w0 = ld4(wp + ci * N), w1 = ld4(wp + (ci + 1) * N), w2 = ld4(wp + (ci + 2) * N), w3 = ld4(wp + (ci + 3) * N);
 #pragma unroll
             for (int j = 0; j < PXT; ++j) {
-              const float xv = Ain[pbase[j] + toff + ci];
-#pragma unroll
-              for (int q = 0; q < NQ; ++q) fz_bfma4(acc[j][2 * q], acc[j][2 * q + 1], xv, wv[q]);
+              const float4 xv = ld4(ap + pbase[j] + ci);
+              fz_bfma4(acc[j][0], acc[j][1], xv.x, w0);
+              fz_bfma4(acc[j][0], acc[j][1], xv.y, w1);
+              fz_bfma4(acc[j][0], acc[j][1], xv.z, w2);
+              fz_bfma4(acc[j][0], acc[j][1], xv.w, w3);
             }
           }
+        } else if (vec == 2) {
+#pragma unroll 1
+          for (int ci = 0; ci < c1; ci += 2) {
+            const float4 w0 = ld4(wp + ci * N), w1 = ld4(wp + (ci + 1) * N);
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) {
+              const float2 xv = *reinterpret_cast<const float2*>(ap + pbase[j] + ci);
+              fz_bfma4(acc[j][0], acc[j][1], xv.x, w0);
+              fz_bfma4(acc[j][0], acc[j][1], xv.y, w1);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int ci = 0; ci < c1; ++ci) {
+            const float4 w0 = ld4(wp + ci * N);
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) fz_bfma4(acc[j][0], acc[j][1], ap[pbase[j] + ci], w0);
+          }
         }
+      }
     } else {
 #pragma unroll 2
       for (int k0 = 0; k0 < K; k0 += 4) {
         float4 av[PXT];
 #pragma unroll
         for (int j = 0; j < PXT; ++j) av[j] = ld4(Ain + pbase[j] + k0);
+        const float4 w0 = ld4(wcol + k0 * N), w1 = ld4(wcol + (k0 + 1) * N), w2 = ld4(wcol + (k0 + 2) * N), w3 = ld4(wcol + (k0 + 3) * N);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          float4 wv[NQ];
-#pragma unroll
-          for (int q = 0; q < NQ; ++q) wv[q] = ld4(wcol + (k0 + kk) * N + 4 * q);
-#pragma unroll
-          for (int j = 0; j < PXT; ++j) {
-            const float xv = kk == 0 ? av[j].x : kk == 1 ? av[j].y : kk == 2 ? av[j].z : av[j].w;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) fz_bfma4(acc[j][2 * q], acc[j][2 * q + 1], xv, wv[q]);
-          }
+        for (int j = 0; j < PXT; ++j) {
+          fz_bfma4(acc[j][0], acc[j][1], av[j].x, w0);
+          fz_bfma4(acc[j][0], acc[j][1], av[j].y, w1);
+          fz_bfma4(acc[j][0], acc[j][1], av[j].z, w2);
+          fz_bfma4(acc[j][0], acc[j][1], av[j].w, w3);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < PXT; ++j) {
-      const int p = pg + j * npg;
+      const int p = p0 + PL * j;
       if (p >= hw) continue;
-      float* o = Out + p * ldo + nb * NO;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        float4 v = make_float4(acc[j][2 * q].x, acc[j][2 * q].y, acc[j][2 * q + 1].x, acc[j][2 * q + 1].y);
-        if (Res) {
-          const float4 r = ld4(Res + p * ldo + nb * NO + 4 * q);
-          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-        }
-        st4(o + 4 * q, v);
-        fz_stat2(make_float2(v.x, v.y), s1, s2);
-        fz_stat2(make_float2(v.z, v.w), s1, s2);
+      float4 v = make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
+      if (Res) {
+        const float4 r = ld4(Res + p * ldo + 4 * nbl);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
       }
+      st4(Out + p * ldo + 4 * nbl, v);
+      fz_stat2(make_float2(v.x, v.y), s1, s2);
+      fz_stat2(make_float2(v.z, v.w), s1, s2);
     }
   }
 }
@@ -291,14 +301,13 @@ template <class S, bool STEM>
 __device__ __forceinline__ void fz_gemm_dispatch(const FusedArgs& a, const float* Ain, int lda, int K, const float* Ws,
                                                  const float* bs, float* Out, const float* Res, float& s1, float& s2) {
   if constexpr (S::kStatic) {
-    fz_gemm_stage<S, S::PXT, S::NO, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2);
+    fz_gemm_stage<S, S::PXT, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2);
   } else {
     switch (a.pw_variant) {
-      case 0: fz_gemm_stage<S, 7, 4, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
-      case 1: fz_gemm_stage<S, 4, 8, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
-      case 2: fz_gemm_stage<S, 2, 8, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
-      case 3: fz_gemm_stage<S, 1, 8, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
-      default: fz_gemm_stage<S, 1, 4, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
+      case 0: fz_gemm_stage<S, 7, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
+      case 1: fz_gemm_stage<S, 4, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
+      case 2: fz_gemm_stage<S, 2, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
+      default: fz_gemm_stage<S, 1, STEM>(a, Ain, lda, K, Ws, bs, Out, Res, s1, s2); break;
     }
   }
 }
@@ -737,12 +746,12 @@ static int fz_launch(const FusedArgs& a, int B, int nt, size_t smem, cudaStream_
   return (int)cudaGetLastError();
 }
 
-// compiled-in shapes: H, W, NK, C1, C2, G0, G1, G2, NT, PXT, NO, NR
-using FzCfg2A = FzStatic<14, 14, 32, 4, 4, 4, 2, 1, 256, 7, 4, 7>;    // config 2 level 0 checkerboard
-using FzCfg2B = FzStatic<14, 14, 32, 2, 2, 8, 4, 0, 256, 7, 4, 7>;    // config 2 level 1 channel
-using FzCfg2C = FzStatic<7, 7, 16, 8, 8, 4, 2, 0, 128, 1, 8, 7>;      // config 2 level 1 checkerboard
-using FzCfg3A = FzStatic<16, 16, 32, 8, 8, 4, 2, 1, 512, 2, 8, 8>;    // config 3 level 0 checkerboard
-using FzCfg3B = FzStatic<16, 16, 32, 4, 4, 8, 4, 0, 512, 2, 8, 8>;    // config 3 level 1 channel
+// compiled-in shapes: H, W, NK, C1, C2, G0, G1, G2, NT, PXT, NR
+using FzCfg2A = FzStatic<14, 14, 32, 4, 4, 4, 2, 1, 256, 7, 7>;    // config 2 level 0 checkerboard: 7 warp tiles of 28 pixels
+using FzCfg2B = FzStatic<14, 14, 32, 2, 2, 8, 4, 0, 256, 7, 7>;    // config 2 level 1 channel
+using FzCfg2C = FzStatic<7, 7, 16, 8, 8, 4, 2, 0, 128, 2, 7>;      // config 2 level 1 checkerboard: 4 warp tiles of 16 pixels
+using FzCfg3A = FzStatic<16, 16, 32, 8, 8, 4, 2, 1, 512, 4, 8>;    // config 3 level 0 checkerboard: 16 warp tiles of 16 pixels
+using FzCfg3B = FzStatic<16, 16, 32, 4, 4, 8, 4, 0, 512, 4, 8>;    // config 3 level 1 channel
 
 template <class S>
 static bool fz_matches(const cnf_coupling* c) {
@@ -762,7 +771,7 @@ int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView i
   if (!c->ln || c->ks != 3 || c->R < 1 || c->R > FZ_MAXR) return -1;
   if (in_mask < 0 || in_mask > 3) return -1;
   const int nk = c->nk, cat = c->cat, hw = c->hw();
-  if (nk % 8 || cat % 4 || nk > 64 || c->c2 > 8 || c->c1 > 16) return -1;
+  if (!(nk == 8 || nk == 16 || nk == 32 || nk == 64) || cat % 4 || c->c2 > 8 || c->c1 > 16) return -1;
   if ((int)c->dil.size() > FZ_MAXBR || c->h > 16 || c->w > 32) return -1;
   FusedArgs a = {};
   a.in_view = in_view; a.out_view = out_view; a.in_mask = in_mask; a.mask_c = c->mask_c; a.mode = mode;
@@ -823,19 +832,17 @@ int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView i
   int nt = two ? 256 : 512;
   if (hw <= 64) nt = 128;
   {
-    // pixel tiling of the GEMM-shaped stages: fewest rounds x tile work, ties -> first (larger tile)
-    static const int PXT[5] = {7, 4, 2, 1, 1}, NO[5] = {4, 8, 8, 8, 4};
+    // pixel tiling of the GEMM-shaped stages: a warp tile is (32 / NL) * PXT pixels; fewest rounds x tile work
+    a.lognl = nk == 8 ? 1 : nk == 16 ? 2 : nk == 32 ? 3 : 4;
+    const int PL = 32 >> a.lognl, nw = nt / 32;
+    static const int PXT[4] = {7, 4, 2, 1};
     long best = -1;
-    for (int v = 0; v < 5; ++v) {
-      if (nk % NO[v]) continue;
-      const int npg = (hw + PXT[v] - 1) / PXT[v], npgp = (npg + 31) / 32 * 32;
-      const long slots = (long)npgp * (nk / NO[v]);
-      const long rounds = (slots + nt - 1) / nt;
-      const long cost = rounds * (PXT[v] * NO[v] + 4) * 32 / std::min(32, npg);   // partially filled warps cost a full one
-      if (best < 0 || cost < best) { best = cost; a.pw_variant = v; a.npg = npg; a.npg_pad = npgp; }
+    for (int v = 0; v < 4; ++v) {
+      const int tiles = (hw + PL * PXT[v] - 1) / (PL * PXT[v]);
+      const long cost = (long)((tiles + nw - 1) / nw) * (PXT[v] + 1);
+      if (best < 0 || cost < best) { best = cost; a.pw_variant = v; }
     }
   }
-  a.div_npgp_m = recip32((unsigned)a.npg_pad);
   return fz_launch<FzDynamic, 512, 1>(a, B, nt, smem, st);
 }
 

@@ -121,11 +121,16 @@ def test_gradients_without_layer_norm(dev):
 def test_loss_and_grad_forward_equals_log_loss(dev):
     m, _, _ = mk(SMALL)
     xy = torch.from_numpy(synth_inputs('noise:8x8x3', 7, seed=4)).to(dev)
+    m.set_fusion(0)                        # layer-per-kernel inference path: the kernels the training forward runs
     a = [float(t) for t in m.log_loss(xy)]
     zy_a = m.last_per_sample['zy'].clone()
     b = [float(t) for t in m.loss_and_grad(xy)[0]]
     assert a == b                                                       # same kernels, same order
     assert torch.equal(zy_a, m.last_per_sample['zy'])
+    m.set_fusion(1)                        # activation-resident inference path: same values to fp32 rounding
+    c = [float(t) for t in m.log_loss(xy)]
+    np.testing.assert_allclose(c, b, rtol=1e-5)
+    assert float((m.last_per_sample['zy'] - zy_a).abs().max() / zy_a.abs().max()) < 1e-5
 
 
 def test_train_step_adam_matches_oracle(dev):
