@@ -19,6 +19,10 @@ LIB_PATH = os.path.join(_HERE, "libcnf.so")
 
 CNF_MAX_BRANCHES = 8
 CNF_NAME_CAP = 64
+# kernel families a coupling layer must NOT use (include/cnf.h, cnf_*_set_kernel_paths)
+(CNF_PATH_NO_RESIDENT, CNF_PATH_NO_TCGEN05, CNF_PATH_NO_PW_FFMA, CNF_PATH_NO_OCTET, CNF_PATH_NO_BRANCH,
+ CNF_PATH_NO_GCONV2, CNF_PATH_NO_STEM2, CNF_PATH_NO_HEAD2) = (1, 2, 4, 8, 16, 32, 64, 128)
+CNF_PATH_ALL = 255
 
 (CNF_OK, CNF_ERR_ARG, CNF_ERR_SHAPE, CNF_ERR_DTYPE, CNF_ERR_DEVICE, CNF_ERR_LAYOUT, CNF_ERR_CUDA,
  CNF_ERR_UNSUPPORTED, CNF_ERR_WORKSPACE) = range(9)
@@ -84,6 +88,8 @@ def _load():
         "cnf_plan_workspace_bytes": (I64, [P, I64]),
         "cnf_plan_set_fusion": (I, [P, I]),
         "cnf_coupling_set_fusion": (I, [P, I]),
+        "cnf_plan_set_kernel_paths": (I, [P, I]),
+        "cnf_coupling_set_kernel_paths": (I, [P, I]),
         "cnf_flow_forward": (I, [P, P, P, P, P, P, V]),
         "cnf_flow_inverse": (I, [P, P, P, P, P, V]),
         "cnf_flow_log_loss": (I, [P, P, P, P, P, P, P, P, P, V]),
@@ -97,8 +103,7 @@ def _load():
         "cnf_coupling_backward": (I, [P, P, P, P, P, V]),
         "cnf_coupling_nets": (I, [P, P, P, P, P, P, V]),
         "cnf_coupling_law": (I, [P, P, P, I, I, P, P, V]),
-        "cnf_debug_pw_conv": (I, [P, P, P, I64, I, V]),
-        "cnf_debug_read_clocks": (I, [POINTER(c_int64), I]),
+        "cnf_measure_stage": (I, [P, P, P, I64, I, V]),
         "cnf_mask": (I, [P, I, I, P, V]),
         "cnf_decompress_mask": (I, [P, I, P, V]),
         "cnf_space_to_depth": (I, [P, P, V]),

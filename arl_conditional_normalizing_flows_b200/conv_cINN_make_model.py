@@ -373,6 +373,11 @@ class coupling_layer(Layer):
         layer fits it (default) or the layer-per-kernel path."""
         check(lib.cnf_coupling_set_fusion(self._h, 1 if enable else 0))
 
+    def set_kernel_paths(self, excluded):
+        """`excluded`: CNF_PATH_* bits (see _lib / include/cnf.h) naming the kernel families this layer must not use;
+        0 = the fastest eligible kernel for every stage.  All choices give the same results to fp32 rounding."""
+        check(lib.cnf_coupling_set_kernel_paths(self._h, int(excluded)))
+
     # -- the layer (M:1258-1328, M:1333-1394) -------------------------------------------------------
     def forward_and_Jacobian(self, u, sum_log_detJ, zy):
         u = self._check_uv(u, "u")
@@ -528,6 +533,10 @@ class cFlow:
     def set_fusion(self, enable):
         """Inference path selection for every coupling layer (see coupling_layer.set_fusion)."""
         check(lib.cnf_plan_set_fusion(self._plan, 1 if enable else 0))
+
+    def set_kernel_paths(self, excluded):
+        """Kernel-family exclusion bits for every coupling layer (see coupling_layer.set_kernel_paths)."""
+        check(lib.cnf_plan_set_kernel_paths(self._plan, int(excluded)))
 
     def count_params(self):
         n = 0

@@ -100,44 +100,19 @@ int64_t max_coupling_ws(const cnf_plan* p, int64_t B) {
   return m;
 }
 
-// Samples per pass through the layers.  Every op is per-sample, so the batch can be cut into chunks
-// whose s/t-net activations (3 buffers of 2*chunk*h*w*nk floats) stay resident in the 126 MB L2 between the
-// kernel that writes them and the kernel that reads them.  CNF_BATCH_CHUNK overrides (0 = whole batch).
-int batch_chunk(const cnf_plan* p, int64_t B) {
-  static int env = -2;
-  if (env == -2) {
-    const char* e = getenv("CNF_BATCH_CHUNK");
-    env = e ? atoi(e) : -1;
-  }
-  if (env <= 0) return (int)B;   // default: whole batch (measured: chunking under-fills the small layers)
-  if (env > 0) return (int)std::min<int64_t>(B, env);
-  // (unused) auto policy: keep the two live buffers of the widest layer under ~48 MB
-  int64_t per_sample = 0;
-  for (auto* c : p->couplings) {
-    const int64_t b = 2LL * c->hw() * (c->nk + std::max(c->nk, c->cat)) * 4;
-    per_sample = std::max(per_sample, b);
-  }
-  int64_t chunk = (48LL << 20) / std::max<int64_t>(per_sample, 1);
-  chunk = std::max<int64_t>(8, (chunk / 8) * 8);
-  return (int)std::min<int64_t>(B, chunk);
-}
-
 // direction +1: all couplings in order, in place on `buf`; -1: reversed with the inverse law.
 int run_flow(const cnf_plan* p, const float* params, float* buf, int B, int direction, double* ldacc, void* ws,
              void* stream) {
+  // whole batch per layer: every op is per-sample, and cutting the batch into L2-sized chunks under-fills the launches
+  // (measured in round 1)
   const int n = (int)p->couplings.size();
-  const int chunk = batch_chunk(p, B);
-  const long long per = (long long)p->H * p->W * p->D;
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int nb = std::min(chunk, B - b0);
-    for (int s = 0; s < n; ++s) {
-      const int li = direction == 1 ? s : n - 1 - s;
-      const cnf_coupling* c = p->couplings[li];
-      FlowView v = make_view(buf + b0 * per, p->H, p->W, p->D, p->level[li]);
-      const int e = run_coupling(c, params + p->param_off[li], v, c->mask, v, nb, direction == 1 ? HEAD_FWD : HEAD_INV,
-                                 ldacc ? ldacc + b0 : nullptr, nullptr, nullptr, ws, stream);
-      if (e) return cuda_rc(e, "coupling layer");
-    }
+  for (int s = 0; s < n; ++s) {
+    const int li = direction == 1 ? s : n - 1 - s;
+    const cnf_coupling* c = p->couplings[li];
+    FlowView v = make_view(buf, p->H, p->W, p->D, p->level[li]);
+    const int e = run_coupling(c, params + p->param_off[li], v, c->mask, v, B, direction == 1 ? HEAD_FWD : HEAD_INV, ldacc,
+                               nullptr, nullptr, ws, stream);
+    if (e) return cuda_rc(e, "coupling layer");
   }
   return CNF_OK;
 }
@@ -215,6 +190,8 @@ int cnf_flow_log_loss(const cnf_plan* p, const DLManagedTensor* xy, const DLMana
   Ten X;
   TRY(borrow(xy, "xy", 4, &X));
   if (X.shape[0] == 0) return fail(CNF_ERR_ARG, "empty batch: the batch means of the loss are undefined");
+  if (zy && zy->dl_tensor.data && (char*)zy->dl_tensor.data + zy->dl_tensor.byte_offset == (char*)X.p)
+    return fail(CNF_ERR_ARG, "zy must not alias xy: the L1 term of the loss reads xy after the flow has written zy");
   TRY(cnf_flow_forward(p, xy, params, zy, logdet, workspace, stream));
   return cnf_prior_loss(zy, xy, logdet, p->x_d, p->lambda_y, ll_z, ll_y, loss4, stream);
 }
@@ -307,15 +284,16 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
     saved.push_back(carve_saved(c, B, base + T.saved_off[li]));
     CouplingSaved& sv = saved.back();
     sv.state = (float*)(base + T.states_off + T.state_bytes * li);
-    const float* src = li == 0 ? X.p : saved[li - 1].state;
     float* dst = li == n - 1 ? Z.p : (float*)(base + T.states_off + T.state_bytes * (li + 1));
     if (li == 0) TRY(cuda_rc(launch_copy(X.p, sv.state, B * per, stream), "copy"));
-    (void)src;
     TRY(cuda_rc(launch_copy(sv.state, dst, B * per, stream), "copy"));
     FlowView v = make_view(dst, p->H, p->W, p->D, p->level[li]);
     // recompute mode: plain forward (the shared region is the s/t-net workspace); only the layer's input state is kept
+    // (the layer-per-kernel path in both modes: the backward pass re-runs exactly these kernels, so the two modes give the
+    // same loss and gradients)
     TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], v, c->mask, v, (int)B, HEAD_FWD, ldacc, nullptr, nullptr,
-                             recompute ? base + T.saved_off[li] : nullptr, stream, recompute ? nullptr : &sv), "coupling layer"));
+                             recompute ? base + T.saved_off[li] : nullptr, stream, recompute ? nullptr : &sv,
+                             CNF_PATH_NO_RESIDENT), "coupling layer"));
   }
   if (n == 0) TRY(cuda_rc(launch_copy(X.p, Z.p, B * per, stream), "copy"));
   TRY(cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream), "logdet"));
@@ -323,9 +301,7 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
   // ---- backward
   const float invB = 1.0f / (float)B;
   TRY(cuda_rc(launch_loss_grad(Z.p, X.p, G, B * per, p->D, p->x_d, (float)p->lambda_y, invB, stream), "loss gradient"));
-  int first_layer = 0;   // debug: CNF_BWD_FIRST_LAYER=k stops the backward pass after layer k (scratch keeps its buffers)
-  if (const char* e = getenv("CNF_BWD_FIRST_LAYER")) first_layer = atoi(e);
-  for (int li = n - 1; li >= first_layer; --li) {
+  for (int li = n - 1; li >= 0; --li) {
     const cnf_coupling* c = p->couplings[li];
     if (recompute) {
       // re-run this layer's forward from its kept input state with every activation saved (same kernels, same reduction
@@ -437,7 +413,7 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1c, const D
   return cuda_rc(run_coupling(c, P.p, v, MASK_DENSE, v, (int)B, HEAD_EMIT, nullptr, TA.p, TB.p, W.p, stream), "s/t networks");
 }
 
-int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace, int64_t batch,
+int cnf_measure_stage(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace, int64_t batch,
                       int which, void* stream) {
   if (!c) return fail(CNF_ERR_ARG, "null coupling layer");
   Ten P, W;
@@ -449,9 +425,11 @@ int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLMa
   return cuda_rc(run_pw_only(c, P.p, (int)batch, which, W.p, stream), "1x1 conv");
 }
 
+#ifdef CNF_DEBUG
 int cnf_debug_read_clocks(long long* out, int n) {
   return cuda_rc(read_tc3_clocks(out, n), "debug clocks");
 }
+#endif
 
 int cnf_coupling_law(const DLManagedTensor* u, const DLManagedTensor* s, const DLManagedTensor* t, int which_mask,
                      int inverse, DLManagedTensor* v, DLManagedTensor* logdet, void* stream) {

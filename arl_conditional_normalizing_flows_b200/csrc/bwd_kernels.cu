@@ -666,11 +666,8 @@ static int launch_wgrad3(Wgrad3Args a, cudaStream_t st) {
   a.SB = std::max(1, (a.B + want - 1) / want);
   const int sbs = (a.B + a.SB - 1) / a.SB;
   const size_t smem = bytes(a.TH);
-  static size_t configured = 0;
-  if (smem > configured && smem > 48 * 1024) {
-    CU_TRY(cudaFuncSetAttribute(wgrad3_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)wgrad3_small_kernel, smem, cache));
   dim3 grid(tiles * sbs, a.ci_chunks, 2);
   wgrad3_small_kernel<<<grid, 256, smem, st>>>(a);
   return (int)cudaGetLastError();
@@ -834,8 +831,8 @@ static int launch_wgrad3_wide_t(const Wgrad3WideArgs& a, cudaStream_t st) {
 
 // returns 1 when the shape is not covered (caller falls back to wgrad3_small_kernel)
 static int launch_wgrad3_wide(const Wgrad3WideArgs& a, cudaStream_t st) {
-  if (a.ks != 3 && a.ks != 1) return 1;
-  if (a.CW > 256) return 1;
+  if (a.ks != 3 && a.ks != 1) return CNF_NOT_ELIGIBLE;
+  if (a.CW > 256) return CNF_NOT_ELIGIBLE;
   if (a.CW <= 32) {
     if (a.CN >= 4) return launch_wgrad3_wide_t<1, 4>(a, st);
     if (a.CN >= 2) return launch_wgrad3_wide_t<1, 2>(a, st);
@@ -971,16 +968,13 @@ __global__ void __launch_bounds__(256) stem_dgrad_kernel(const Dgrad3Args a) {
 
 static int launch_head_dgrad(const Dgrad3Args& a, cudaStream_t st) {
   const size_t smem = (size_t)a.ks * a.ks * a.CN * a.CW * sizeof(float);
-  if (a.CW > 256 || smem > 160 * 1024 || (a.ks != 3 && a.ks != 1)) return 1;
+  if (a.CW > 256 || smem > 160 * 1024 || (a.ks != 3 && a.ks != 1)) return CNF_NOT_ELIGIBLE;
   const long long total = (long long)a.B * a.h * a.w;
   dim3 grid((unsigned)std::min<long long>((total + 7) / 8, 148 * 8), 2);
 #define CNF_LAUNCH_HD(WPL)                                                                                     \
   {                                                                                                            \
-    static size_t configured = 0;                                                                              \
-    if (smem > configured && smem > 48 * 1024) {                                                               \
-      CU_TRY(cudaFuncSetAttribute(head_dgrad_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                       \
-    }                                                                                                          \
+    static SmemAttrCache cache;                                                                                \
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)head_dgrad_kernel<WPL>, smem, cache));                         \
     head_dgrad_kernel<WPL><<<grid, 256, smem, st>>>(a);                                                        \
   }
   if (a.CW <= 32) CNF_LAUNCH_HD(1)
@@ -993,16 +987,13 @@ static int launch_head_dgrad(const Dgrad3Args& a, cudaStream_t st) {
 
 static int launch_stem_dgrad(const Dgrad3Args& a, cudaStream_t st) {
   const size_t smem = (size_t)a.ks * a.ks * a.CN * a.CW * sizeof(float);
-  if (a.CW > 256 || smem > 160 * 1024 || (a.ks != 3 && a.ks != 1)) return 1;
+  if (a.CW > 256 || smem > 160 * 1024 || (a.ks != 3 && a.ks != 1)) return CNF_NOT_ELIGIBLE;
   const long long total = (long long)a.B * a.h * a.w;
   dim3 grid((unsigned)std::min<long long>((total + 7) / 8, 148 * 8), 2);
 #define CNF_LAUNCH_SD(WPL)                                                                                     \
   {                                                                                                            \
-    static size_t configured = 0;                                                                              \
-    if (smem > configured && smem > 48 * 1024) {                                                               \
-      CU_TRY(cudaFuncSetAttribute(stem_dgrad_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                       \
-    }                                                                                                          \
+    static SmemAttrCache cache;                                                                                \
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)stem_dgrad_kernel<WPL>, smem, cache));                         \
     stem_dgrad_kernel<WPL><<<grid, 256, smem, st>>>(a);                                                        \
   }
   if (a.CW <= 32) CNF_LAUNCH_SD(1)
@@ -1190,7 +1181,7 @@ static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   const int Cb = a.groups * G, d = a.dil;
   const int tpt = (3 / KYS) * Cb;
   const int max_nt = KYS == 3 ? 256 : 768;
-  if (tpt > max_nt) return 1;
+  if (tpt > max_nt) return CNF_NOT_ELIGIBLE;
   a.TW = std::min(a.w, 32);
   a.TH = std::min(a.h, 32);
   auto bytes = [&](int th) { return (size_t)((((th + 2 * d) * (a.TW + 2 * d) * Cb + 3) & ~3) + th * a.TW * Cb) * sizeof(float); };
@@ -1206,11 +1197,8 @@ static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   const int sbs = (a.B + a.SB - 1) / a.SB;
   const size_t smem = std::max(bytes(a.TH), (size_t)(Cb * 9 * G + Cb) * sizeof(float));
   auto kern = wgrad_gconv_kernel<G, KYS>;
-  static size_t configured = 0;
-  if (smem > configured && smem > 48 * 1024) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   dim3 grid(tiles * sbs, 1, 2);
   kern<<<grid, NT, smem, st>>>(a);
   return (int)cudaGetLastError();
@@ -1220,10 +1208,10 @@ template <int G>
 static int launch_wgrad_gconv_g(const WgradGcArgs& a, cudaStream_t st) {
   if (G <= 8) {
     const int rc = launch_wgrad_gconv_t<G, 3>(a, st);
-    if (rc != 1) return rc;
+    if (rc != CNF_NOT_ELIGIBLE) return rc;
   }
   const int rc = launch_wgrad_gconv_t<G, 1>(a, st);
-  return rc == 1 ? (int)cudaErrorInvalidConfiguration : rc;
+  return rc == CNF_NOT_ELIGIBLE ? (int)cudaErrorInvalidConfiguration : rc;
 }
 
 static int launch_wgrad_gconv(const WgradGcArgs& a, int G, cudaStream_t st) {
@@ -1402,7 +1390,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
     ww.g_off = c->lnf_g; ww.be_off = c->lnf_b; ww.stats = stats(3 * R);
     ww.B = B; ww.h = c->h; ww.w = c->w; ww.ks = c->ks; ww.ln = c->ln;
     int rc = launch_wgrad3_wide(ww, st);
-    if (rc == 1) rc = launch_wgrad3(a, st);
+    if (rc == CNF_NOT_ELIGIBLE) rc = launch_wgrad3(a, st);
     CU_TRY(rc);
     Dgrad3Args dg = {};
     dg.in = DR; dg.in_net_stride = (long long)B * hw * c2;
@@ -1410,7 +1398,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
     dg.B = B; dg.h = c->h; dg.w = c->w; dg.CW = nk; dg.CN = c2; dg.ks = c->ks;
     dg.out = GA; dg.out_net_stride = (long long)B * hw * nk;
     rc = launch_head_dgrad(dg, st);
-    if (rc == 1) {
+    if (rc == CNF_NOT_ELIGIBLE) {
       Conv3tArgs t = {};
       t.in = DR; t.in_net_stride = (long long)B * hw * c2;
       t.params = params; t.net_stride = ns; t.w_off = c->head_w;
@@ -1483,7 +1471,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
     ww.params = params; ww.grads = grads; ww.net_stride = ns; ww.w_off = c->stem_w; ww.b_off = c->stem_b;
     ww.B = B; ww.h = c->h; ww.w = c->w; ww.ks = c->ks; ww.ln = 0;
     int rc = launch_wgrad3_wide(ww, st);
-    if (rc == 1) rc = launch_wgrad3(a, st);
+    if (rc == CNF_NOT_ELIGIBLE) rc = launch_wgrad3(a, st);
     CU_TRY(rc);
     Dgrad3Args dg = {};
     dg.in = GX; dg.in_net_stride = (long long)B * hw * nk;
@@ -1491,7 +1479,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
     dg.B = B; dg.h = c->h; dg.w = c->w; dg.CW = nk; dg.CN = c->c1; dg.ks = c->ks;
     dg.view = g_view; dg.mask = c->mask;
     rc = launch_stem_dgrad(dg, st);
-    if (rc == 1) {
+    if (rc == CNF_NOT_ELIGIBLE) {
       Conv3tArgs t = {};
       t.in = GX; t.in_net_stride = (long long)B * hw * nk;
       t.params = params; t.net_stride = ns; t.w_off = c->stem_w;

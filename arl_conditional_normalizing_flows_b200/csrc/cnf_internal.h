@@ -14,6 +14,23 @@ namespace cnf {
 
 void set_error(const char* fmt, ...);
 
+// "this launcher does not cover the shape": never a cudaError_t value (cudaErrorInvalidValue == 1)
+constexpr int CNF_NOT_ELIGIBLE = -1;
+constexpr int CNF_MAX_DEVICES = 64;
+
+// Tuning / ablation switches.  Release builds use the built-in default and never read the environment; a
+// -DCNF_DEBUG build (make EXTRA=-DCNF_DEBUG) reads CNF_<NAME> so that profiling experiments need no rebuild.
+int knob_int(const char* name, int dflt);
+float knob_float(const char* name, float dflt);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: one cache per launcher, indexed by
+// the current device, guarded by a mutex (plan.cpp).  Returns a cudaError as int.
+struct SmemAttrCache {
+  size_t set[CNF_MAX_DEVICES] = {};
+};
+int ensure_dynamic_smem(const void* kernel, size_t bytes, SmemAttrCache& cache);
+int device_sm_count(int* n_sm);   // SM count of the current device (cached per device)
+
 struct ParamEntry {
   std::string name;
   int64_t offset;  // floats from the start of the net's block
@@ -40,7 +57,7 @@ struct ResBlockLayout {
 struct cnf_coupling {
   int H, W, D, mask, mask_c, R, card, nk, ks, ln;
   int h, w, c1, c2, cat;
-  int fuse = 1;   // inference: use the activation-resident kernel (fused_kernels.cu) when the layer fits it
+  int paths = 0;  // CNF_PATH_* bits (cnf.h): kernel families this layer must NOT use (0 = fastest path for every stage)
   std::vector<int> dil;
   int64_t stem_w, stem_b, lnf_g, lnf_b, head_w, head_b, tanh_w;
   std::vector<cnf::ResBlockLayout> rb;
@@ -121,7 +138,7 @@ CouplingWorkspace carve_ws(const cnf_coupling* c, int64_t B, void* ws);
 // launchers (kernels.cu); all enqueue on `stream`, return cudaError as int (0 ok)
 int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask,
                  FlowView out_view, int B, int mode, double* logdet_acc, float* outA, float* outB,
-                 void* ws, void* stream, const CouplingSaved* sv = nullptr);
+                 void* ws, void* stream, const CouplingSaved* sv = nullptr, int extra_excluded_paths = 0);
 // backward of one coupling layer (bwd_kernels.cu): G is the gradient w.r.t. the layer OUTPUT in the flow
 // buffer layout (updated in place to the gradient w.r.t. the layer INPUT); grads has the layout of params.
 int run_coupling_backward(const cnf_coupling* c, const float* params, float* grads, const CouplingSaved& sv,

@@ -36,15 +36,15 @@ __device__ __forceinline__ long long comp_off(const FlowView& v, int m, int b, i
 // producing kernel.  Biased variance, eps 1e-3 (F:350-360 -> keras LayerNormalization defaults).
 __device__ __forceinline__ void ln_coeffs(const double* __restrict__ stats, long long idx, double n,
                                           float& mean, float& rstd) {
-  // The sums are accumulated in fp64; the three scalar ops below run in fp32 (relative error ~1e-7,
-  // far inside the 1e-4 budget) because fp64 divide / sqrt sequences are slow on B200 and would
-  // serialise the prologue of every CTA.
-  const float inv_n = 1.0f / (float)n;
-  const float m = (float)stats[2 * idx] * inv_n;
-  float var = fmaf(-m, m, (float)stats[2 * idx + 1] * inv_n);
-  var = fmaxf(var, 0.f);
-  mean = m;
-  rstd = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
+  // The sums are fp64; mean and the CENTRED variance are formed in fp64 too (E[x^2] - mean^2 cancels catastrophically in
+  // fp32 once |mean| is tens of standard deviations: large biases / a growing residual stream).  Three DP multiplies and one
+  // DP subtraction per call; only the reciprocal square root runs in fp32.
+  const double inv_n = 1.0 / n;
+  const double m = stats[2 * idx] * inv_n;
+  double var = stats[2 * idx + 1] * inv_n - m * m;
+  var = var > 0.0 ? var : 0.0;
+  mean = (float)m;
+  rstd = 1.0f / sqrtf((float)var + (float)CNF_LN_EPS);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -26,7 +26,6 @@
 
 #include <algorithm>
 #include <cstdint>
-#include <mutex>
 
 #include "cnf_internal.h"
 #include "device_utils.cuh"
@@ -726,22 +725,9 @@ constexpr size_t kFzStatic = 1024;   // static shared memory of the kernel (FzRe
 
 template <class S, int NTB, int MINB>
 static int fz_launch(const FusedArgs& a, int B, int nt, size_t smem, cudaStream_t st) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return (int)e;
-  if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
-  {
-    // the opt-in shared-memory limit is a per-device attribute of each instantiation
-    static std::mutex mu;
-    static bool configured[64] = {};
-    std::lock_guard<std::mutex> lk(mu);
-    if (!configured[dev]) {
-      e = cudaFuncSetAttribute(fused_coupling_kernel<S, NTB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(227 * 1024 - kFzStatic));
-      if (e != cudaSuccess) return (int)e;
-      configured[dev] = true;
-    }
-  }
+  static SmemAttrCache cache;   // per instantiation, per device
+  const int e = ensure_dynamic_smem((const void*)fused_coupling_kernel<S, NTB, MINB>, 227 * 1024 - kFzStatic, cache);
+  if (e) return e;
   fused_coupling_kernel<S, NTB, MINB><<<B, nt, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
@@ -764,15 +750,15 @@ static bool fz_matches(const cnf_coupling* c) {
   return true;
 }
 
-// -1: this layer is not covered by the activation-resident kernel (the caller runs the layer-per-kernel path)
+// CNF_NOT_ELIGIBLE: this layer is not covered by the activation-resident kernel (the caller runs the layer-per-kernel path)
 int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
                           int B, int mode, double* logdet_acc, void* ws, void* stream) {
-  if (mode != HEAD_FWD && mode != HEAD_INV) return -1;
-  if (!c->ln || c->ks != 3 || c->R < 1 || c->R > FZ_MAXR) return -1;
-  if (in_mask < 0 || in_mask > 3) return -1;
+  if (mode != HEAD_FWD && mode != HEAD_INV) return CNF_NOT_ELIGIBLE;
+  if (!c->ln || c->ks != 3 || c->R < 1 || c->R > FZ_MAXR) return CNF_NOT_ELIGIBLE;
+  if (in_mask < 0 || in_mask > 3) return CNF_NOT_ELIGIBLE;
   const int nk = c->nk, cat = c->cat, hw = c->hw();
-  if (!(nk == 8 || nk == 16 || nk == 32 || nk == 64) || cat % 4 || c->c2 > 8 || c->c1 > 16) return -1;
-  if ((int)c->dil.size() > FZ_MAXBR || c->h > 16 || c->w > 32) return -1;
+  if (!(nk == 8 || nk == 16 || nk == 32 || nk == 64) || cat % 4 || c->c2 > 8 || c->c1 > 16) return CNF_NOT_ELIGIBLE;
+  if ((int)c->dil.size() > FZ_MAXBR || c->h > 16 || c->w > 32) return CNF_NOT_ELIGIBLE;
   FusedArgs a = {};
   a.in_view = in_view; a.out_view = out_view; a.in_mask = in_mask; a.mask_c = c->mask_c; a.mode = mode;
   a.params = params; a.net_stride = c->net_stride;
@@ -790,7 +776,7 @@ int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView i
   int wt = 0, gw_floats = 0;
   for (int i = 0; i < a.n_br; ++i) {
     const Branch& s = c->rb[0].br[i];
-    if (s.gin != s.gout || !(s.gin == 1 || s.gin == 2 || s.gin == 4 || s.gin == 8) || s.channels % 4) return -1;
+    if (s.gin != s.gout || !(s.gin == 1 || s.gin == 2 || s.gin == 4 || s.gin == 8) || s.channels % 4) return CNF_NOT_ELIGIBLE;
     a.br[i] = fz_branch_geom(c->h, c->w, a.nr_variant, s.dil, s.gin, s.channels, s.out_off, wt, gw_floats);
     wt += a.br[i].nwt;
     gw_floats = a.br[i].sb + s.channels;
@@ -806,7 +792,7 @@ int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView i
   }
   // shared-memory carve-up
   const int sz_x = hw * a.ldx, sz_y2 = hw * a.ldy2;
-  if ((c->h + 2) * (c->w + 2) * c->c1 > sz_x) return -1;
+  if ((c->h + 2) * (c->w + 2) * c->c1 > sz_x) return CNF_NOT_ELIGIBLE;
   int wmax = 9 * c->c1 * nk + nk;
   wmax = std::max(wmax, nk * nk + nk);
   wmax = std::max(wmax, gw_floats);
@@ -815,7 +801,7 @@ int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView i
   wmax = (wmax + 3) & ~3;
   a.off_y1 = sz_x; a.off_y2 = 2 * sz_x; a.off_w = 2 * sz_x + sz_y2;
   const size_t smem = (size_t)(a.off_w + wmax) * sizeof(float);
-  if (smem + kFzStatic > 227 * 1024) return -1;
+  if (smem + kFzStatic > 227 * 1024) return CNF_NOT_ELIGIBLE;
   a.div_w_m = recip32((unsigned)c->w);
   a.div_qnk_m = recip32((unsigned)(nk / 4));
   a.div_qcat_m = recip32((unsigned)(cat / 4));

@@ -262,15 +262,16 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
   // depend on the batch size or on the sample's position inside the item)
   const int q = tid / a.tps, sl = tid - q * a.tps;
   const bool tactive = q < a.S && sl < a.nsps;
-  const float inv_n = 1.0f / ((float)hw * (float)a.Cin);
+  const double inv_n = 1.0 / ((double)hw * (double)a.Cin);   // mean and centred variance in fp64 (see ln_coeffs)
   auto coeffs = [&](int item, int par) {   // LayerNorm coefficients of the samples of `item` -> mr[par]
     if (tid < a.S) {
       float sc = 1.f, sh = 0.f;
       const int s = item * a.S + tid;
       if (a.ln && s < a.B) {
         const double* sp = a.stats_in + 2 * ((long long)net * a.B + s);
-        const float m = (float)sp[0] * inv_n;
-        const float var = fmaxf(fmaf(-m, m, (float)sp[1] * inv_n), 0.f);
+        const double md = sp[0] * inv_n;
+        const float m = (float)md;
+        const float var = fmaxf((float)(sp[1] * inv_n - md * md), 0.f);
         sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
         sh = -m * sc;
       }
@@ -422,8 +423,9 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
     if (dbl && ctid >= 0 && ctid < a.S && next < a.n_items && !(a.dbg & 16)) {
       float sc = 1.f, sh = 0.f;
       if (a.ln && next * a.S + ctid < a.B) {
-        const float m = (float)nx0 * inv_n;
-        const float var = fmaxf(fmaf(-m, m, (float)nx1 * inv_n), 0.f);
+        const double md = nx0 * inv_n;
+        const float m = (float)md;
+        const float var = fmaxf((float)(nx1 * inv_n - md * md), 0.f);
         sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
         sh = -m * sc;
       }
@@ -489,13 +491,11 @@ static bool oct_make_tmap(CUtensorMap* tm, const float* in, int rows, int h, int
             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Host side: eligibility, shared-memory budget, CTA split.  Returns 1 if the shape is not covered (caller falls back to
-// the per-branch kernels), 0 on success, a cudaError otherwise.
+// Host side: eligibility, shared-memory budget, CTA split.  Returns CNF_NOT_ELIGIBLE if the shape is not covered (caller
+// falls back to the per-branch kernels), 0 on success, a cudaError otherwise.
 static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("CNF_GC_OCT"); enabled = (e && e[0] == '0') ? 0 : 1; }
-  if (!enabled || g.bwd || g.ks != 3 || g.n_br < 1) return 1;
-  if ((g.Cin % 4) || (g.Cout % 4)) return 1;
+  if (g.bwd || g.ks != 3 || g.n_br < 1) return CNF_NOT_ELIGIBLE;
+  if ((g.Cin % 4) || (g.Cout % 4)) return CNF_NOT_ELIGIBLE;
   OctArgs a{};
   a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
   a.params = g.params; a.net_stride = g.net_stride; a.g_off = g.g_off; a.be_off = g.be_off;
@@ -503,13 +503,13 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
   a.n_br = g.n_br;
   a.vec8 = (((uintptr_t)g.out & 31) == 0 && (g.Cout % 8) == 0 && ((g.out_net_stride * 4) % 32) == 0) ? 1 : 0;
-  { static int d = -1; if (d < 0) { const char* e = getenv("CNF_OCT_DBG"); d = e ? atoi(e) : 0; } a.dbg = d; }
+  { static int d = -1; if (d < 0) d = knob_int("OCT_DBG", 0); a.dbg = d; }   // ablation modes: -DCNF_DEBUG builds only
   int halo = 0, n_oct = 0, wtot = 0;
   for (int i = 0; i < g.n_br; ++i) {
     const GconvBranch& b = g.br[i];
     const int G = b.gin, ch = b.groups * b.gin;
-    if (b.gin != b.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || (ch % 8) || b.in_off != 0 || (b.out_off % 4)) return 1;
-    if (ch > g.Cin) return 1;
+    if (b.gin != b.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || (ch % 8) || b.in_off != 0 || (b.out_off % 4)) return CNF_NOT_ELIGIBLE;
+    if (ch > g.Cin) return CNF_NOT_ELIGIBLE;
     OctBranch& ob = a.br[i];
     ob.dil = b.dil; ob.G = G; ob.noct = ch / 8; ob.out_off = b.out_off; ob.w_off = b.w_off; ob.b_off = b.b_off;
     ob.w_smem = wtot;
@@ -517,10 +517,10 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
     halo = std::max(halo, b.dil);
     n_oct = std::max(n_oct, ob.noct);
   }
-  if (n_oct > OCT_MAX || n_oct < 1) return 1;
+  if (n_oct > OCT_MAX || n_oct < 1) return CNF_NOT_ELIGIBLE;
   const int hw = g.h * g.w;
   a.halo = halo; a.SW = g.w + 2 * halo; a.SHW = (g.h + 2 * halo) * a.SW; a.n_oct = n_oct;
-  if ((long long)a.SHW >= 65536 / 1) return 1;                 // pt[] is 16 bit
+  if ((long long)a.SHW >= 65536 / 1) return CNF_NOT_ELIGIBLE;                 // pt[] is 16 bit
   a.nsps = 0;
   for (int i = 0; i < g.n_br; ++i) {
     const int d = a.br[i].dil;
@@ -531,26 +531,22 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   // samples per item: as many as keep <= 512 threads busy and fit the shared-memory budget
   const size_t budget = 227 * 1024 - 1024;
   static int nbuf_env = 0;
-  if (!nbuf_env) { const char* e = getenv("CNF_OCT_NBUF"); nbuf_env = (e && e[0] == '1') ? 1 : 2; }
+  if (!nbuf_env) nbuf_env = knob_int("OCT_NBUF", 2) == 1 ? 1 : 2;
   a.nbuf = nbuf_env;
   auto smem_for = [&](int S) {
     size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * OCT_MAXT;
     return f * sizeof(float) + (((size_t)hw * 2 + 15) & ~(size_t)15);
   };
-  if (a.tps > OCT_MAXT || smem_for(1) > budget) return 1;
-  static int nsm = 0;
-  if (!nsm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 2) nsm = 148;
-  }
+  if (a.tps > OCT_MAXT || smem_for(1) > budget) return CNF_NOT_ELIGIBLE;
+  int nsm = 0;
+  if (device_sm_count(&nsm) != 0 || nsm < 2) nsm = 148;
   // walk down from the largest S (<= 512 threads, fits shared memory) until every CTA slot has >= 3 items to pipeline,
   // but keep at least ~96 busy threads per CTA
   int S = 0, NT = 0, slots = 0;
   static int max_per_sm = 0;
-  if (!max_per_sm) { const char* e = getenv("CNF_OCT_PER_SM"); max_per_sm = e ? std::max(1, atoi(e)) : 4; }
+  if (!max_per_sm) max_per_sm = std::max(1, knob_int("OCT_PER_SM", 4));
   static int s_cap = 0;
-  if (!s_cap) { const char* e = getenv("CNF_OCT_S"); s_cap = e ? std::max(1, atoi(e)) : 512; }
+  if (!s_cap) s_cap = std::max(1, knob_int("OCT_S", 512));
   for (int s = std::max(1, std::min(std::min(OCT_MAXT / a.tps, a.nbuf == 1 ? 1 : s_cap), g.B)); s >= 1; --s) {
     if (smem_for(s) > budget) continue;
     if (S && s * a.tps < 96) break;
@@ -566,7 +562,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   int per_net = std::max(n_oct, slots);
   if (per_net > n_oct * a.n_items) per_net = std::max(n_oct, n_oct * a.n_items);
   static float ovh = -1.f;
-  if (ovh < 0.f) { const char* e = getenv("CNF_OCT_OVH"); ovh = e ? (float)atof(e) : 24.f; }
+  if (ovh < 0.f) ovh = knob_float("OCT_OVH", 24.f);
   float work[OCT_MAX];
   int nc[OCT_MAX];
   for (int o = 0; o < n_oct; ++o) {
@@ -588,21 +584,22 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   int tot = 0;
   for (int o = 0; o < n_oct; ++o) { a.cta_first[o] = (unsigned short)tot; tot += nc[o]; }
   a.cta_first[n_oct] = (unsigned short)tot;
-  if (tot > 1023) return 1;
+  if (tot > 1023) return CNF_NOT_ELIGIBLE;
   const size_t smem = smem_for(S);
   static int verbose = -1;
-  if (verbose < 0) { const char* e = getenv("CNF_OCT_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  if (verbose < 0) verbose = knob_int("OCT_VERBOSE", 0);
   if (verbose > 0) {
     fprintf(stderr, "[gconv_oct] B=%d %dx%dx%d->%d nbuf=%d S=%d NT=%d items=%d octets=%d ctas/net=%d smem=%zu halo=%d split=%d,%d,..,%d\n", g.B, g.h, g.w, g.Cin,
             g.Cout, a.nbuf, S, NT, a.n_items, n_oct, tot, smem, halo, nc[0], n_oct > 1 ? nc[1] : 0, nc[n_oct - 1]);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gconv_oct_kernel<OCT_MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  {
+    static SmemAttrCache cache;
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    const bool first = dev >= 0 && dev < CNF_MAX_DEVICES && cache.set[dev] == 0;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)gconv_oct_kernel<OCT_MAXT>, budget, cache));
     // several small CTAs per SM only co-reside if the carve-out is the maximum
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gconv_oct_kernel<OCT_MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    if (first) CU_TRY(cudaFuncSetAttribute(gconv_oct_kernel<OCT_MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   if (verbose > 0) {
     int occ = -1;
@@ -612,7 +609,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (verbose > 0) --verbose;
   // TMA tiles: nets stacked contiguously, 16-byte aligned strides, boxes <= 256 per dimension, buffers on 256-byte phases
   static int tma_env = -1;
-  if (tma_env < 0) { const char* e = getenv("CNF_OCT_TMA"); tma_env = (e && e[0] == '0') ? 0 : 1; }
+  if (tma_env < 0) tma_env = knob_int("OCT_TMA", 1) ? 1 : 0;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   const int SH = g.h + 2 * halo;

@@ -5,7 +5,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+
+#include <cuda_runtime.h>
 
 #include "cnf_internal.h"
 
@@ -21,6 +25,64 @@ void set_error(const char* fmt, ...) {
 }
 
 static int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+int knob_int(const char* name, int dflt) {
+#ifdef CNF_DEBUG
+  char key[96];
+  snprintf(key, sizeof(key), "CNF_%s", name);
+  const char* e = getenv(key);
+  return e ? atoi(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
+
+float knob_float(const char* name, float dflt) {
+#ifdef CNF_DEBUG
+  char key[96];
+  snprintf(key, sizeof(key), "CNF_%s", name);
+  const char* e = getenv(key);
+  return e ? (float)atof(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
+
+static std::mutex g_dev_mu;
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes, SmemAttrCache& cache) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= CNF_MAX_DEVICES) return (int)cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  const size_t want = bytes < 48 * 1024 ? (size_t)48 * 1024 : bytes;
+  if (want > cache.set[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e != cudaSuccess) return (int)e;
+    cache.set[dev] = want;
+  }
+  return 0;
+}
+
+int device_sm_count(int* n_sm) {
+  static int cached[CNF_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= CNF_MAX_DEVICES) return (int)cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!cached[dev]) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    cached[dev] = n;
+  }
+  *n_sm = cached[dev];
+  return 0;
+}
 
 struct LayoutBuilder {
   int64_t cur = 0;
@@ -495,12 +557,30 @@ int cnf_plan_coupling_level(const cnf_plan* p, int i) {
   return p->level[i];
 }
 
+int cnf_coupling_set_kernel_paths(cnf_coupling* c, int excluded) {
+  if (!c || excluded < 0 || excluded > CNF_PATH_ALL) {
+    set_error("cnf_coupling_set_kernel_paths: null descriptor or bits outside CNF_PATH_ALL");
+    return CNF_ERR_ARG;
+  }
+  c->paths = excluded;
+  return CNF_OK;
+}
+
+int cnf_plan_set_kernel_paths(cnf_plan* p, int excluded) {
+  if (!p || excluded < 0 || excluded > CNF_PATH_ALL) {
+    set_error("cnf_plan_set_kernel_paths: null plan or bits outside CNF_PATH_ALL");
+    return CNF_ERR_ARG;
+  }
+  for (auto* c : p->couplings) c->paths = excluded;
+  return CNF_OK;
+}
+
 int cnf_coupling_set_fusion(cnf_coupling* c, int enable) {
   if (!c) {
     set_error("null argument");
     return CNF_ERR_ARG;
   }
-  c->fuse = enable ? 1 : 0;
+  c->paths = enable ? (c->paths & ~CNF_PATH_NO_RESIDENT) : (c->paths | CNF_PATH_NO_RESIDENT);
   return CNF_OK;
 }
 
@@ -509,7 +589,7 @@ int cnf_plan_set_fusion(cnf_plan* p, int enable) {
     set_error("null argument");
     return CNF_ERR_ARG;
   }
-  for (auto* c : p->couplings) c->fuse = enable ? 1 : 0;
+  for (auto* c : p->couplings) cnf_coupling_set_fusion(c, enable);
   return CNF_OK;
 }
 

@@ -48,7 +48,8 @@ struct GemmArgs {
   int B, hw, K, N, KC, ln;
   // backward-pass uses of gemm_kernel: raw_in = no LReLU/LN on A; w_trans = B[k][n] = W[n*ldw + k]; no_bias
   int raw_in, w_trans, ldw, no_bias;
-  int dbg;   // timing experiments only (CNF_PW_DBG): 1 skip epilogue stores, 2 skip cp.async, 4 skip MMAs, 8 skip transform math
+  int dbg;   // timing experiments only (-DCNF_DEBUG builds, CNF_PW_DBG): 1 skip epilogue stores, 2 skip cp.async, 4 skip MMAs, 8 skip transform math
+  int paths; // CNF_PATH_* bits of the layer: kernel families NOT to use
 };
 
 template <int TN, int NQ, int RM, bool STEM>
@@ -465,7 +466,8 @@ struct GconvArgs {
   double* stats_out;
   int B, h, w, Cin, Cout, ln, ks;
   int TH, TW, tiles_y, tiles_x;
-  int dbg;  // debug: bit0 skip global loads in staging, bit1 skip the FFMA taps
+  int dbg;  // debug (-DCNF_DEBUG builds): bit0 skip global loads in staging, bit1 skip the FFMA taps
+  int paths;  // CNF_PATH_* bits of the layer: kernel families NOT to use
   // backward-input mode: raw input (no LReLU/LN), flipped+transposed weights, accumulate into `out`, no bias, no stats
   int bwd;
   int n_br;
@@ -703,9 +705,6 @@ __global__ void __launch_bounds__(GC_NT) gconv_kernel(const GconvArgs a) {
   }
 }
 
-}  // namespace cnf
-#include "tc_gconv.cuh"
-namespace cnf {
 
 // ------------------------------------------------------------------------------------------
 // 2b. Grouped dilated convs, register-blocked: 128-thread CTAs; the weights of the current tap
@@ -1148,205 +1147,6 @@ __global__ void __launch_bounds__(320, 2) gconv3_kernel(const GconvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 2d. Grouped dilated convs with fully asynchronous staging: every thread issues ALL of its raw copies
-//     (x, gamma, beta; cp.async, 16/8/4 B) for the CTA's tile at once, waits once, applies
-//     LReLU + LayerNorm in shared memory on the slots it copied itself, and only then does the CTA
-//     synchronise and run the register-blocked FFMA taps of gconv3.  One global-latency exposure per
-//     CTA instead of one per staging row; row bands keep the three raw tiles small enough for 3 CTAs/SM.
-// ------------------------------------------------------------------------------------------
-template <int BYTES>
-__device__ __forceinline__ void cp_async_any(void* smem_dst, const void* gsrc) {
-  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-  else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
-template <int G, int PX>
-__global__ void __launch_bounds__(256) gconv4_kernel(const GconvArgs a) {
-  constexpr int V = G >= 4 ? 4 : G;
-  constexpr int VPP = G / V;
-  constexpr int GS = G + ((G % 8) == 0 ? 4 : 0);
-  using T = typename VecT<V>::T;
-  extern __shared__ __align__(16) float smem[];
-  __shared__ float red[64];
-  __shared__ float mr[2];
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
-  const int b = blockIdx.y, net = blockIdx.z;
-  const GconvBranch& br = a.br[0];
-  const int tiles = a.tiles_y * a.tiles_x;
-  const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-  const int y0 = (tile / a.tiles_x) * a.TH, x0 = (tile % a.tiles_x) * a.TW;
-  const int th = min(a.TH, a.h - y0), tw = min(a.TW, a.w - x0);
-  const int d = br.dil, halo = d;
-  const int SH = th + 2 * halo, SW = tw + 2 * halo;
-  const int in_sz = (SH * SW * GS + 3) & ~3;
-  float* x_s = smem;                       // [SH*SW][GS] raw x, then LN(LReLU(x)) in place
-  float* g_s = x_s + in_sz;                // raw gamma
-  float* be_s = g_s + in_sz;               // raw beta
-  float* w_s = be_s + in_sz;               // [9][G][G]
-  float* b_s = w_s + ((9 * G * G + 3) & ~3);
-
-  const float* P = a.params + (long long)net * a.net_stride;
-  const float* src_s = a.in + (long long)net * a.in_net_stride + (long long)b * a.h * a.w * a.Cin;
-  const float* gam = P + a.g_off;
-  const float* bet = P + a.be_off;
-  const int cin0 = g * G;
-  const int row_slots = SW * VPP;
-  // ---- issue everything
-  for (int sy = wid; sy < SH; sy += nw) {
-    const int gy = y0 - halo + sy;
-    if (gy < 0 || gy >= a.h) continue;
-    for (int sl = lane; sl < row_slots; sl += 32) {
-      const int sx = sl / VPP, cv = sl % VPP;
-      const int gx = x0 - halo + sx;
-      if (gx < 0 || gx >= a.w) continue;
-      const long long e = ((long long)gy * a.w + gx) * a.Cin + cin0 + cv * V;
-      const int so = (sy * SW + sx) * GS + cv * V;
-      cp_async_any<4 * V>(x_s + so, src_s + e);
-      if (a.ln) {
-        cp_async_any<4 * V>(g_s + so, gam + e);
-        cp_async_any<4 * V>(be_s + so, bet + e);
-      }
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  if (tid == 0) {
-    float mean = 0.f, rstd = 1.f;
-    if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, (double)a.h * a.w * (double)a.Cin, mean, rstd);
-    mr[0] = rstd;
-    mr[1] = -mean * rstd;
-  }
-  {
-    const float* wsrc = P + br.w_off + (long long)g * 9 * G * G;
-    for (int i = tid; i < 9 * G * G; i += NT) w_s[i] = wsrc[i];
-    if (tid < G) b_s[tid] = P[br.b_off + g * G + tid];
-  }
-  __syncthreads();                         // mr visible
-  const float sc = mr[0], shf = mr[1];
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // ---- transform the slots this thread copied (same loops), zero the padding
-  for (int sy = wid; sy < SH; sy += nw) {
-    const int gy = y0 - halo + sy;
-    const bool rowok = gy >= 0 && gy < a.h;
-    for (int sl = lane; sl < row_slots; sl += 32) {
-      const int sx = sl / VPP, cv = sl % VPP;
-      const int gx = x0 - halo + sx;
-      const int so = (sy * SW + sx) * GS + cv * V;
-      float o[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) o[i] = 0.f;
-      if (rowok && gx >= 0 && gx < a.w) {
-        const T xv = *reinterpret_cast<const T*>(x_s + so);
-        const float* xf = reinterpret_cast<const float*>(&xv);
-        if (a.ln) {
-          const T gv = *reinterpret_cast<const T*>(g_s + so);
-          const T bv = *reinterpret_cast<const T*>(be_s + so);
-          const float* gf = reinterpret_cast<const float*>(&gv);
-          const float* bf = reinterpret_cast<const float*>(&bv);
-#pragma unroll
-          for (int i = 0; i < V; ++i) o[i] = fmaf(fmaf(fmaxf(xf[i], CNF_LRELU_SLOPE * xf[i]), sc, shf), gf[i], bf[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < V; ++i) o[i] = fmaxf(xf[i], CNF_LRELU_SLOPE * xf[i]);
-        }
-      }
-      *reinterpret_cast<T*>(x_s + so) = *reinterpret_cast<const T*>(o);
-    }
-  }
-  __syncthreads();
-
-  const int TP = th * tw;
-  float acc[PX][G];
-  int poff[PX];
-#pragma unroll
-  for (int j = 0; j < PX; ++j) {
-    const int p = min(tid + j * NT, TP - 1);
-    poff[j] = ((p / tw) * SW + (p % tw)) * GS;
-#pragma unroll
-    for (int co = 0; co < G; ++co) acc[j][co] = 0.f;
-  }
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int ky = tap / 3, kx = tap - ky * 3;
-    const int toff = (ky * d * SW + kx * d) * GS;
-    const float* wt = w_s + tap * G * G;
-    float xv[PX][G];
-#pragma unroll
-    for (int j = 0; j < PX; ++j) {
-      const float* src = x_s + poff[j] + toff;
-      if (G % 4 == 0) {
-#pragma unroll
-        for (int c4 = 0; c4 < G; c4 += 4) {
-          const float4 t = ld4(src + c4);
-          xv[j][c4] = t.x; xv[j][c4 + 1] = t.y; xv[j][c4 + 2] = t.z; xv[j][c4 + 3] = t.w;
-        }
-      } else if (G == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(src);
-        xv[j][0] = t.x; xv[j][G - 1] = t.y;
-      } else {
-        xv[j][0] = src[0];
-      }
-    }
-#pragma unroll
-    for (int ci = 0; ci < G; ++ci) {
-      float wv[G];
-      if (G % 4 == 0) {
-#pragma unroll
-        for (int c4 = 0; c4 < G; c4 += 4) {
-          const float4 t = ld4(wt + ci * G + c4);
-          wv[c4] = t.x; wv[c4 + 1] = t.y; wv[c4 + 2] = t.z; wv[c4 + 3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < G; ++c) wv[c] = wt[ci * G + c];
-      }
-#pragma unroll
-      for (int j = 0; j < PX; ++j)
-#pragma unroll
-        for (int co = 0; co < G; ++co) acc[j][co] = fmaf(xv[j][ci], wv[co], acc[j][co]);
-    }
-  }
-
-  float* out_s = a.out + (long long)net * a.out_net_stride + (long long)b * a.h * a.w * a.Cout;
-  const int cbase = br.out_off + g * G;
-  const bool vec = (G % 4 == 0) && (a.Cout % 4 == 0) && (cbase % 4 == 0);
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < PX; ++j) {
-    const int p = tid + j * NT;
-    if (p < TP) {
-      const int y = y0 + p / tw, x = x0 + p % tw;
-      float* dst = out_s + ((long long)y * a.w + x) * a.Cout + cbase;
-      float o[G];
-#pragma unroll
-      for (int co = 0; co < G; ++co) {
-        o[co] = acc[j][co] + b_s[co];
-        const float l = fmaxf(o[co], CNF_LRELU_SLOPE * o[co]);
-        s1 += l;
-        s2 = fmaf(l, l, s2);
-      }
-      if (vec) {
-#pragma unroll
-        for (int c4 = 0; c4 < G; c4 += 4) st4(dst + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
-      } else {
-#pragma unroll
-        for (int co = 0; co < G; ++co) dst[co] = o[co];
-      }
-    }
-  }
-  if (a.stats_out) {
-    double d1, d2;
-    block_sum2(s1, s2, red, d1, d2);
-    if (tid == 0) {
-      double* so = a.stats_out + 2 * ((long long)net * a.B + b);
-      atomicAdd(so, d1);
-      atomicAdd(so + 1, d2);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // 3. Head conv (both nets) fused with tanh*w, exp, the affine coupling law, the decompress
 //    scatter into the flow buffer and the per-sample log-det (M:1133-1150, M:1198, M:1307-1326,
 //    M:1379-1394).  One thread per output pixel, all c2 channels of both nets.
@@ -1363,6 +1163,7 @@ struct HeadArgs {
   double* logdet;  // [B], accumulated (forward only)
   float *outA, *outB;  // HEAD_EMIT: [B][hw][c2]
   int TH, CC;
+  int paths;  // CNF_PATH_* bits of the layer: kernel families NOT to use
 };
 
 constexpr int HD_NT = 256;
@@ -1798,11 +1599,8 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
   constexpr int CT = TN / (4 * NQ), RT = 128 / CT, TM = RM * RT;
   const size_t smem = ((size_t)TM * (a.KC + 4) + (size_t)a.KC * TN) * sizeof(float);
   auto kern = gemm_kernel<TN, NQ, RM, STEM>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   const int tiles_m = (a.hw + TM - 1) / TM, tiles_n = (a.N + TN - 1) / TN;
   dim3 grid(tiles_m * tiles_n, a.B, 2);
   kern<<<grid, 128, smem, st>>>(a);
@@ -1812,11 +1610,8 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
 static int launch_stem2(const GemmArgs& a, cudaStream_t st) {
   const size_t smem = ((((size_t)(a.h + 2) * (a.w + 2) * a.c1 + 3) & ~(size_t)3) + 2 * (size_t)a.K * a.N + 2 * a.N) * sizeof(float);
   auto kern = stem2_kernel<4>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   kern<<<a.B, 256, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
@@ -1824,8 +1619,7 @@ static int launch_stem2(const GemmArgs& a, cudaStream_t st) {
 template <bool STEM>
 static int launch_gemm(GemmArgs a, cudaStream_t st) {
   if (STEM) {
-    static int s2 = -1;
-    if (s2 < 0) { const char* e = getenv("CNF_STEM2"); s2 = (e && e[0] == '0') ? 0 : 1; }
+    const bool s2 = !(a.paths & CNF_PATH_NO_STEM2);
     const size_t smem = ((size_t)(a.h + 2) * (a.w + 2) * a.c1 + 4 + 2 * (size_t)a.K * a.N + 2 * a.N) * sizeof(float);
     if (s2 && a.ks == 3 && a.K == 9 * a.c1 && (a.N == 16 || a.N == 32 || a.N == 64) && !a.w_trans && !a.no_bias && !a.res &&
         smem <= 200 * 1024)
@@ -1845,73 +1639,29 @@ static int launch_pw_t(GemmArgs a, cudaStream_t st) {
   a.KC = (((a.K + nchunks - 1) / nchunks) + 3) & ~3;
   const size_t smem = ((size_t)S * PT * (a.KC + 4) + (size_t)a.KC * TN) * sizeof(float);
   auto kern = pw_kernel<TN, NQ>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   const int tiles_p = (a.hw + PT - 1) / PT, tiles_n = (a.N + TN - 1) / TN;
   dim3 grid(tiles_p * tiles_n, (a.B + S - 1) / S, 2);
   kern<<<grid, 256, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
-template <int N>
-static int launch_pw_tc_t(const GemmArgs& a, cudaStream_t st) {
-  constexpr size_t smem = 2 * (size_t)(2 * 128 * 32 + 2 * N * 32) * sizeof(float);
-  auto kern = pw_tc_kernel<N>;
-  static bool configured = false;
-  if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  dim3 grid((a.hw + 31) / 32, (a.B + 3) / 4, 2);
-  kern<<<grid, 256, smem, st>>>(a);
-  return (int)cudaGetLastError();
-}
-
-// persistent tcgen05 1x1 conv; returns 1 when the resident-W image does not fit shared memory
-template <int N>
-static int launch_pw_tc2_t(const GemmArgs& a, cudaStream_t st) {
-  const int nchunks = (a.K + 31) / 32;
-  const size_t smem = ((size_t)4 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
-  if (smem > 220 * 1024) return 1;
-  auto kern = pw_tc2_kernel<N>;
-  static size_t configured = 0;
-  static int n_sm = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    CU_TRY(cudaGetDevice(&dev));
-    CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    configured = smem;
-  }
-  const int tiles_p = (a.hw + 31) / 32, tiles_s = (a.B + 3) / 4;
-  const int grid = std::min(2 * tiles_p * tiles_s, n_sm & ~1);   // even: CTAs alternate between the two nets
-  kern<<<grid, 256, smem, st>>>(a, tiles_p, tiles_s);
-  return (int)cudaGetLastError();
-}
-
-// warp-specialised persistent tcgen05 1x1 conv; returns 1 when the resident-W image does not fit
+// warp-specialised persistent tcgen05 1x1 conv; CNF_NOT_ELIGIBLE when the resident-W image does not fit
 template <int N, int TW, int NST>
 static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   const int nchunks = (a.K + 31) / 32;
   const size_t smem = ((size_t)NST * 2 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
-  if (smem > 225 * 1024) return 1;
+  if (smem > 225 * 1024) return CNF_NOT_ELIGIBLE;
   auto kern = pw_tc3_kernel<N, TW, NST>;
-  static size_t configured = 0;
-  static int n_sm = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    CU_TRY(cudaGetDevice(&dev));
-    CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    configured = smem;
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
+  int n_sm = 0;
+  CU_TRY((cudaError_t)device_sm_count(&n_sm));
   const int tiles_p = (a.hw + 31) / 32, tiles_s = (a.B + 3) / 4;
   const int grid = std::min(2 * tiles_p * tiles_s, n_sm & ~1);
   GemmArgs b = a;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CNF_PW_DBG"); dbg = e ? atoi(e) : 0; } b.dbg = dbg; }
+  { static int dbg = -1; if (dbg < 0) dbg = knob_int("PW_DBG", 0); b.dbg = dbg; }
   kern<<<grid, (TW + 1 + 8 + 4) * 32, smem, st>>>(b, tiles_p, tiles_s);
   return (int)cudaGetLastError();
 }
@@ -1920,102 +1670,33 @@ static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
 template <int N>
 static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
   static int nst = -1;
-  if (nst < 0) { const char* e = getenv("CNF_PW_NST"); nst = e ? atoi(e) : 4; }
-  int rc = 1;
+  if (nst < 0) nst = knob_int("PW_NST", 4);
+  int rc = CNF_NOT_ELIGIBLE;
   if (nst >= 4) rc = launch_pw_tc3_tw<N, 8, 4>(a, st);
-  if (rc == 1 && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3>(a, st);
-  if (rc == 1) rc = launch_pw_tc3_tw<N, 8, 2>(a, st);
+  if (rc == CNF_NOT_ELIGIBLE && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3>(a, st);
+  if (rc == CNF_NOT_ELIGIBLE) rc = launch_pw_tc3_tw<N, 8, 2>(a, st);
   return rc;
 }
 
-static bool use_tensor_cores() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CNF_PW_TC");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-// 1x1 conv dispatcher: tcgen05 3xTF32 kernel when the shape fits one UMMA tile family (N in {16,32,64},
-// K % 8 == 0); otherwise the FFMA multi-sample kernel (K % 4 == 0) or the per-sample generic kernel.
+// 1x1 conv dispatcher: tcgen05 3xTF32 kernel when the shape fits its UMMA tile family (N in {16,32,64}, K % 8 == 0);
+// otherwise (or when a.paths excludes it) the FFMA multi-sample kernel (K % 4 == 0), then the generic GEMM kernel.
 static int launch_pw(const GemmArgs& a, cudaStream_t st) {
-  static int v2 = -1;
-  if (v2 < 0) { const char* e = getenv("CNF_PW_V2"); v2 = e ? atoi(e) : 3; }   // 3: warp-specialised, 2: persistent, 0: per-tile CTAs
-  if (use_tensor_cores() && v2 == 3 && a.K % 8 == 0 && (a.N == 64 || a.N == 32 || a.N == 16)) {
+  if (!(a.paths & CNF_PATH_NO_TCGEN05) && a.K % 8 == 0 && (a.N == 64 || a.N == 32 || a.N == 16)) {
     const int rc = a.N == 64 ? launch_pw_tc3_t<64>(a, st) : a.N == 32 ? launch_pw_tc3_t<32>(a, st) : launch_pw_tc3_t<16>(a, st);
-    if (rc != 1) return rc;
+    if (rc != CNF_NOT_ELIGIBLE) return rc;
   }
-  if (use_tensor_cores() && v2 && a.K % 8 == 0 && (a.N == 64 || a.N == 32 || a.N == 16)) {
-    const int rc = a.N == 64 ? launch_pw_tc2_t<64>(a, st) : a.N == 32 ? launch_pw_tc2_t<32>(a, st) : launch_pw_tc2_t<16>(a, st);
-    if (rc != 1) return rc;
-  }
-  if (use_tensor_cores() && a.K % 8 == 0 && (a.B + 3) / 4 <= 65535) {
-    if (a.N == 64) return launch_pw_tc_t<64>(a, st);
-    if (a.N == 32) return launch_pw_tc_t<32>(a, st);
-    if (a.N == 16) return launch_pw_tc_t<16>(a, st);
-  }
-  if (a.K % 4 == 0 && a.B <= 65535 * 8) {
+  if (!(a.paths & CNF_PATH_NO_PW_FFMA) && a.K % 4 == 0 && a.B <= 65535 * 8) {
     if (a.N > 32) return launch_pw_t<64, 2>(a, st);
     return launch_pw_t<32, 1>(a, st);
   }
   return launch_gemm<false>(a, st);
 }
 
-static bool use_tensor_cores_gconv() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CNF_GC_TC");
-    v = (e && e[0] == '1') ? 1 : 0;   // default: FFMA gconv3 (8-wide groups are smem-read bound on tcgen05)
-  }
-  return v == 1;
-}
-
-// One dilation branch on tcgen05 (tc_gconv.cuh).  Returns 1 if the shape is not eligible.
-static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
-  const GconvBranch& br = g.br[bi];
-  const int G = br.gin, C = br.groups * br.gout;
-  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8 || G == 16)) return 1;
-  if (C % 16 || g.Cin % 4 || g.Cout % 4 || br.out_off % 4 || g.B > 65535) return 1;
-  const int halo = br.dil, SW = g.w + 2 * halo;
-  const int th_max = (GCT_MT * 128) / SW;
-  if (th_max < 1) return 1;
-  const int n_bands = (g.h + th_max - 1) / th_max;
-  const int TH = (g.h + n_bands - 1) / n_bands;
-  const int Q = (TH + 2 * halo) * SW;
-  int Qp = Q + 128 + 2 * halo + 1;
-  while ((Qp & 7) != 2) ++Qp;
-  const size_t smem = ((size_t)2 * 16 * Qp + 2 * 9 * 256) * sizeof(float);
-  if (smem > 200 * 1024) return 1;
-  GcTcArgs a = {};
-  a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
-  a.params = g.params; a.net_stride = g.net_stride; a.g_off = g.g_off; a.be_off = g.be_off;
-  a.stats_in = g.stats_in; a.stats_out = g.stats_out;
-  a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
-  a.TH = TH; a.n_bands = n_bands; a.Qp_max = Qp;
-  { const char* e = getenv("CNF_DBG"); a.dbg = e ? atoi(e) : 0; }
-  a.n_br = 1;
-  a.br[0] = br;
-  a.br[0].first_item = 0;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
-  dim3 grid((C / 16) * n_bands, g.B, 2);
-  gconv_tc_kernel<<<grid, GCT_NT, smem, st>>>(a);
-  return (int)cudaGetLastError();
-}
-
 template <int G, int PX, int S>
 static int launch_gconv3_t(const GconvArgs& a, int NT, size_t smem, cudaStream_t st) {
   auto kern = gconv3_kernel<G, PX, S>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   dim3 grid(a.br[0].groups * a.tiles_y * a.tiles_x, (a.B + S - 1) / S, 2);
   kern<<<grid, NT * S, smem, st>>>(a);
   return (int)cudaGetLastError();
@@ -2035,17 +1716,17 @@ static int launch_gconv3_g(const GconvArgs& a, int PX, int NT, size_t smem, cuda
   }
 }
 
-// One branch with gin == gout in {1,2,4,8}, ksize 3.  Returns 1 if not eligible.
+// One branch with gin == gout in {1,2,4,8}, ksize 3.  CNF_NOT_ELIGIBLE for other shapes.
 static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   const GconvBranch& br = g.br[bi];
   const int G = br.gin;
-  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || g.B > 65535) return 1;
-  if ((G >= 4 && g.Cin % 4) || (G == 2 && g.Cin % 2)) return 1;
+  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || g.B > 65535) return CNF_NOT_ELIGIBLE;
+  if ((G >= 4 && g.Cin % 4) || (G == 2 && g.Cin % 2)) return CNF_NOT_ELIGIBLE;
   GconvArgs a = g;
   a.n_br = 1;
   a.br[0] = br;
   a.br[0].first_item = 0;
-  { const char* e = getenv("CNF_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.dbg = 0;
   a.TH = std::min(a.h, 32);
   a.TW = std::min(a.w, 32);
   a.tiles_y = (a.h + a.TH - 1) / a.TH;
@@ -2054,7 +1735,7 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   // pixels per thread: thread slots nt*px (idle slots still issue), each tap re-reads the group's weights once per
   // thread, so the per-pixel cost falls like (1 + alpha/px); 32-thread samples are allowed (two samples share a CTA)
   static float alpha = -1.f;
-  if (alpha < 0.f) { const char* e = getenv("CNF_GC_ALPHA"); alpha = e ? (float)atof(e) : 2.0f; }
+  if (alpha < 0.f) alpha = knob_float("GC_ALPHA", 2.0f);
   int best_px = 8, best_nt = 128;
   float best_cost = 1e30f;
   for (int px = 8; px >= 1; --px) {
@@ -2069,11 +1750,11 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   const size_t tail = ((9 * G * G + 3) & ~3) + G + 4;
   // two samples per CTA share gamma/beta loads and double the warps that walk the staging rows
   static int s_env = -1;
-  if (s_env < 0) { const char* e = getenv("CNF_GC_S"); s_env = e ? atoi(e) : 2; }
+  if (s_env < 0) s_env = knob_int("GC_S", 2);
   const bool two = s_env >= 2 && a.B >= 2 && (2 * in_sz + tail) * sizeof(float) <= 110 * 1024 && 2 * best_nt <= 320;
   if (!two && best_nt < 64) best_nt = 64;
   const size_t smem = ((two ? 2 : 1) * in_sz + tail) * sizeof(float);
-  if (smem > 227 * 1024) return 1;
+  if (smem > 227 * 1024) return CNF_NOT_ELIGIBLE;
   if (two) {
     switch (G) {
       case 1: return launch_gconv3_g<1, 2>(a, best_px, best_nt, smem, st);
@@ -2090,78 +1771,6 @@ static int launch_gconv3_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   }
 }
 
-template <int G, int PX>
-static int launch_gconv4_t(const GconvArgs& a, int NT, size_t smem, cudaStream_t st) {
-  auto kern = gconv4_kernel<G, PX>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
-  dim3 grid(a.br[0].groups * a.tiles_y * a.tiles_x, a.B, 2);
-  kern<<<grid, NT, smem, st>>>(a);
-  return (int)cudaGetLastError();
-}
-
-template <int G>
-static int launch_gconv4_g(const GconvArgs& a, int PX, int NT, size_t smem, cudaStream_t st) {
-  switch (PX) {
-    case 1: return launch_gconv4_t<G, 1>(a, NT, smem, st);
-    case 2: return launch_gconv4_t<G, 2>(a, NT, smem, st);
-    case 3: return launch_gconv4_t<G, 3>(a, NT, smem, st);
-    case 4: return launch_gconv4_t<G, 4>(a, NT, smem, st);
-    case 5: return launch_gconv4_t<G, 5>(a, NT, smem, st);
-    case 6: return launch_gconv4_t<G, 6>(a, NT, smem, st);
-    case 7: return launch_gconv4_t<G, 7>(a, NT, smem, st);
-    default: return launch_gconv4_t<G, 8>(a, NT, smem, st);
-  }
-}
-
-// One branch (gin == gout in {1,2,4,8}, ksize 3) with asynchronous staging.  Returns 1 if not eligible.
-static int launch_gconv4_branch(const GconvArgs& g, int bi, cudaStream_t st) {
-  const GconvBranch& br = g.br[bi];
-  const int G = br.gin;
-  if (g.ks != 3 || br.gin != br.gout || !(G == 1 || G == 2 || G == 4 || G == 8) || g.B > 65535) return 1;
-  if ((G >= 4 && g.Cin % 4) || (G == 2 && g.Cin % 2)) return 1;
-  GconvArgs a = g;
-  a.n_br = 1;
-  a.br[0] = br;
-  a.br[0].first_item = 0;
-  const int halo = br.dil;
-  const int GS = G + ((G % 8) == 0 ? 4 : 0);
-  // row bands: three raw tiles (x, gamma, beta) of (TH+2*halo) x (w+2*halo) x GS floats, target <= ~72 KB
-  a.TW = std::min(a.w, 32);
-  a.tiles_x = (a.w + a.TW - 1) / a.TW;
-  static int band_env = -1;
-  if (band_env < 0) { const char* e = getenv("CNF_GC_BAND_KB"); band_env = e ? atoi(e) : 72; }
-  int n_bands = 1;
-  for (;; ++n_bands) {
-    const int thb = (std::min(a.h, 32) + n_bands - 1) / n_bands;
-    const size_t bytes = (size_t)3 * (thb + 2 * halo) * (a.TW + 2 * halo) * GS * 4;
-    if (bytes <= (size_t)band_env * 1024 || thb <= 2) break;
-  }
-  a.TH = (std::min(a.h, 32) + n_bands - 1) / n_bands;
-  a.tiles_y = (a.h + a.TH - 1) / a.TH;
-  const int TP = a.TH * a.TW;
-  int best_px = 8, best_nt = 128, best_waste = 1 << 30;
-  for (int px = 8; px >= 1; --px) {
-    int nt = ((TP + px - 1) / px + 31) / 32 * 32;
-    if (nt < 64) nt = 64;
-    if (nt > 256) continue;
-    const int waste = nt * px - TP;
-    if (waste < best_waste) { best_waste = waste; best_px = px; best_nt = nt; }
-  }
-  const size_t in_sz = (((size_t)(a.TH + 2 * halo) * (a.TW + 2 * halo) * GS) + 3) & ~(size_t)3;
-  const size_t smem = (3 * in_sz + ((9 * G * G + 3) & ~3) + G + 4) * sizeof(float);
-  if (smem > 227 * 1024) return 1;
-  switch (G) {
-    case 1: return launch_gconv4_g<1>(a, best_px, best_nt, smem, st);
-    case 2: return launch_gconv4_g<2>(a, best_px, best_nt, smem, st);
-    case 4: return launch_gconv4_g<4>(a, best_px, best_nt, smem, st);
-    default: return launch_gconv4_g<8>(a, best_px, best_nt, smem, st);
-  }
-}
-
 static int launch_gconv_ffma(GconvArgs a, cudaStream_t st);
 
 }  // namespace cnf
@@ -2169,22 +1778,16 @@ static int launch_gconv_ffma(GconvArgs a, cudaStream_t st);
 namespace cnf {
 
 static int launch_gconv(GconvArgs a, cudaStream_t st) {
-  const bool tc = use_tensor_cores_gconv();
-  static int v2 = -1;
-  if (v2 < 0) { const char* e = getenv("CNF_GC_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
-  if (v2) return launch_gconv_ffma(a, st);
-  if (!tc) {
+  if (!(a.paths & CNF_PATH_NO_OCTET)) {
     // all dilation branches in one persistent launch (gconv_oct.cuh); shapes it does not cover fall through
     const int rc = launch_gconv_oct(a, st);
-    if (rc != 1) return rc;
+    if (rc != CNF_NOT_ELIGIBLE) return rc;
   }
   GconvArgs rest = a;
   rest.n_br = 0;
   for (int i = 0; i < a.n_br; ++i) {
-    static int v4 = -1;
-    if (v4 < 0) { const char* e = getenv("CNF_GC_V4"); v4 = (e && e[0] == '1') ? 1 : 0; }   // async-staging variant: correct but slower (opt-in)
-    const int rc = tc ? launch_gconv_tc_branch(a, i, st) : v4 ? launch_gconv4_branch(a, i, st) : launch_gconv3_branch(a, i, st);
-    if (rc == 1) rest.br[rest.n_br++] = a.br[i];
+    const int rc = (a.paths & CNF_PATH_NO_BRANCH) ? CNF_NOT_ELIGIBLE : launch_gconv3_branch(a, i, st);
+    if (rc == CNF_NOT_ELIGIBLE) rest.br[rest.n_br++] = a.br[i];
     else if (rc != 0) return rc;
   }
   if (rest.n_br) return launch_gconv_ffma(rest, st);
@@ -2192,7 +1795,7 @@ static int launch_gconv(GconvArgs a, cudaStream_t st) {
 }
 
 static int launch_gconv_ffma(GconvArgs a, cudaStream_t st) {
-  bool v2 = true;
+  bool v2 = !(a.paths & CNF_PATH_NO_GCONV2);
   for (int i = 0; i < a.n_br; ++i) {
     const int g = a.br[i].gin;
     if (a.br[i].gin != a.br[i].gout || !(g == 1 || g == 2 || g == 4 || g == 8)) v2 = false;
@@ -2216,21 +1819,13 @@ static int launch_gconv_ffma(GconvArgs a, cudaStream_t st) {
   if (smem > 227 * 1024) return (int)cudaErrorInvalidConfiguration;
   dim3 grid(items, a.B, 2);
   if (v2) {
-    static size_t configured2 = 0;
-    if (smem > configured2) {
-      CU_TRY(cudaFuncSetAttribute(gconv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)std::max(smem, (size_t)48 * 1024)));
-      configured2 = std::max(smem, (size_t)48 * 1024);
-    }
+    static SmemAttrCache cache2;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)gconv2_kernel, smem, cache2));
     gconv2_kernel<<<grid, GC2_NT, smem, st>>>(a);
     return (int)cudaGetLastError();
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(gconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)gconv_kernel, smem, cache));
   gconv_kernel<<<grid, GC_NT, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
@@ -2242,11 +1837,8 @@ static int launch_head_t(const HeadArgs& a, cudaStream_t st) {
   const size_t smem = (2 * in_sz + 2 * (size_t)a.ks * a.ks * C2T * a.CC) * sizeof(float);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidConfiguration;
   auto kern = head_kernel<C2T>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   dim3 grid((a.h + a.TH - 1) / a.TH, a.B);
   kern<<<grid, HD_NT, smem, st>>>(a);
   return (int)cudaGetLastError();
@@ -2256,19 +1848,15 @@ template <int C2T>
 static int launch_head2_t(const HeadArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)2 * a.h * a.w * 9 * C2T * sizeof(float);
   auto kern = head2_kernel<C2T>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-    configured = std::max(smem, (size_t)48 * 1024);
-  }
+  static SmemAttrCache cache;
+  CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   kern<<<a.B, 256, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
 static int launch_head(HeadArgs a, cudaStream_t st) {
   // narrow heads (channel-mask layers): streaming kernel, every activation row read once
-  static int h2 = -1;
-  if (h2 < 0) { const char* e = getenv("CNF_HEAD2"); h2 = (e && e[0] == '0') ? 0 : 1; }
+  const bool h2 = !(a.paths & CNF_PATH_NO_HEAD2);
   if (h2 && a.ks == 3 && a.c2 <= 2 && (a.nk == 16 || a.nk == 32 || a.nk == 64) &&
       (size_t)2 * a.h * a.w * 9 * (a.c2 <= 1 ? 1 : 2) * sizeof(float) <= 100 * 1024)
     return a.c2 <= 1 ? launch_head2_t<1>(a, st) : launch_head2_t<2>(a, st);
@@ -2290,12 +1878,13 @@ static int launch_head(HeadArgs a, cudaStream_t st) {
 // u2 is read and v2 written (the same buffer for the in-place flow).  mode: HeadMode.
 int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
                  int B, int mode, double* logdet_acc, float* outA, float* outB, void* ws, void* stream,
-                 const CouplingSaved* sv) {
+                 const CouplingSaved* sv, int extra_excluded_paths) {
   cudaStream_t st = (cudaStream_t)stream;
   if (B <= 0) return 0;
-  if (!sv && c->fuse && (mode == HEAD_FWD || mode == HEAD_INV)) {
+  const int paths = c->paths | extra_excluded_paths;
+  if (!sv && !(paths & CNF_PATH_NO_RESIDENT) && (mode == HEAD_FWD || mode == HEAD_INV)) {
     const int rc = launch_fused_coupling(c, params, in_view, in_mask, out_view, B, mode, logdet_acc, ws, stream);
-    if (rc != -1) return rc;
+    if (rc != CNF_NOT_ELIGIBLE) return rc;
   }
   CouplingWorkspace W = {};
   if (!sv) W = carve_ws(c, B, ws);
@@ -2317,7 +1906,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
     a.params = params; a.net_stride = c->net_stride; a.w_off = c->stem_w; a.b_off = c->stem_b;
     a.stats_out = stats(0);
     a.out = Xb(0); a.out_net_stride = (long long)B * hw * nk;
-    a.B = B; a.hw = hw; a.K = c->ks * c->ks * c->c1; a.N = nk; a.ln = 0;
+    a.B = B; a.hw = hw; a.K = c->ks * c->ks * c->c1; a.N = nk; a.ln = 0; a.paths = paths;
     CU_TRY((cudaError_t)launch_gemm<true>(a, st));
   }
   for (int r = 0; r < c->R; ++r) {
@@ -2329,7 +1918,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
       a.g_off = L.ln1_g; a.be_off = L.ln1_b;
       a.stats_in = stats(3 * r); a.stats_out = stats(3 * r + 1);
       a.out = Y1b(r); a.out_net_stride = (long long)B * hw * nk;
-      a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln;
+      a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln; a.paths = paths;
       CU_TRY((cudaError_t)launch_pw(a, st));
     }
     {  // grouped dilated convs: Y1 -> Y2
@@ -2338,7 +1927,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
       a.out = Y2b(r); a.out_net_stride = (long long)B * hw * cat; a.Cout = cat;
       a.params = params; a.net_stride = c->net_stride; a.g_off = L.ln2_g; a.be_off = L.ln2_b;
       a.stats_in = stats(3 * r + 1); a.stats_out = stats(3 * r + 2);
-      a.B = B; a.h = c->h; a.w = c->w; a.ln = c->ln; a.ks = c->ks;
+      a.B = B; a.h = c->h; a.w = c->w; a.ln = c->ln; a.ks = c->ks; a.paths = paths;
       a.n_br = (int)L.br.size();
       for (int i = 0; i < a.n_br; ++i) {
         const Branch& s = L.br[i];
@@ -2354,7 +1943,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
       a.g_off = L.ln3_g; a.be_off = L.ln3_b;
       a.stats_in = stats(3 * r + 2); a.stats_out = stats(3 * r + 3);
       a.out = Xb(r + 1); a.res = Xb(r); a.out_net_stride = (long long)B * hw * nk;
-      a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln;
+      a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln; a.paths = paths;
       CU_TRY((cudaError_t)launch_pw(a, st));
     }
   }
@@ -2364,7 +1953,7 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
     a.params = params; a.net_stride = c->net_stride; a.g_off = c->lnf_g; a.be_off = c->lnf_b;
     a.w_off = c->head_w; a.b_off = c->head_b; a.tanh_off = c->tanh_w;
     a.stats_in = stats(3 * c->R);
-    a.B = B; a.h = c->h; a.w = c->w; a.nk = nk; a.c2 = c->c2; a.ln = c->ln; a.ks = c->ks; a.mode = mode;
+    a.B = B; a.h = c->h; a.w = c->w; a.nk = nk; a.c2 = c->c2; a.ln = c->ln; a.ks = c->ks; a.mode = mode; a.paths = paths;
     a.view = out_view; a.mask_c = c->mask_c;
     a.logdet = logdet_acc; a.outA = outA; a.outB = outB;
     CU_TRY((cudaError_t)launch_head(a, st));
@@ -2387,7 +1976,7 @@ int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, vo
   const ResBlockLayout& L = c->rb[0];
   GemmArgs a = {};
   a.params = params; a.net_stride = c->net_stride;
-  a.B = B; a.hw = hw; a.N = nk; a.ln = c->ln;
+  a.B = B; a.hw = hw; a.N = nk; a.ln = c->ln; a.paths = c->paths;
   a.out_net_stride = (long long)B * hw * nk;
   // the statistics outputs go to the spare slot (index n_ln) so that repeated launches do not disturb the layer
   double* spare = c->n_ln() ? W.stats + slot * c->n_ln() : nullptr;
@@ -2398,7 +1987,7 @@ int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, vo
     g.out = W.Y2; g.out_net_stride = (long long)B * hw * cat; g.Cout = cat;
     g.params = params; g.net_stride = c->net_stride; g.g_off = L.ln2_g; g.be_off = L.ln2_b;
     g.stats_in = c->n_ln() ? W.stats + slot : nullptr; g.stats_out = spare;
-    g.B = B; g.h = c->h; g.w = c->w; g.ln = c->ln; g.ks = c->ks;
+    g.B = B; g.h = c->h; g.w = c->w; g.ln = c->ln; g.ks = c->ks; g.paths = c->paths;
     g.n_br = (int)L.br.size();
     for (int i = 0; i < g.n_br; ++i) {
       const Branch& s = L.br[i];
@@ -2455,7 +2044,7 @@ int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* 
   }
   for (int i = 0; i < a.n_br; ++i) {
     const int rc = launch_gconv3_branch(a, i, st);
-    if (rc == 1) return (int)cudaErrorInvalidConfiguration;
+    if (rc == CNF_NOT_ELIGIBLE) return (int)cudaErrorInvalidConfiguration;
     if (rc) return rc;
   }
   return 0;

@@ -132,199 +132,7 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-// ---------------------------------------------------------------------------------------------
-template <int N>
-__global__ void __launch_bounds__(256, 2) pw_tc_kernel(const GemmArgs a) {
-  constexpr int NT = 256;
-  constexpr int S = 4, PT = 32, M = 128;
-  constexpr int KC = 32;                       // K chunk (floats) per pipeline stage
-  constexpr int A_ST = M * KC;                 // floats per A operand image (hi or lo)
-  constexpr int B_ST = N * KC;
-  constexpr int STAGE = 2 * A_ST + 2 * B_ST;   // floats per stage
-  constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
-  constexpr int NC = N / 2;                    // accumulator columns per thread in the epilogue
-  extern __shared__ __align__(128) float tc_smem[];
-  float* smem = tc_smem;
-  __shared__ __align__(8) uint64_t bar_free[2];
-  __shared__ __align__(8) uint64_t bar_done;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float mr[S][2];
-  __shared__ float red[NT / 32][2];
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int p0 = blockIdx.x * PT;
-  const int s0 = blockIdx.y * S, net = blockIdx.z;
-  const int ns = min(S, a.B - s0);
-
-  const float* P = a.params + (long long)net * a.net_stride;
-  const float* Wg = P + a.w_off;
-  const float* gam = P + a.g_off;
-  const float* bet = P + a.be_off;
-  const float* src_n = a.in + (long long)net * a.in_net_stride;
-
-  if (tid == 0) {
-    mbar_init(&bar_free[0], 1);
-    mbar_init(&bar_free[1], 1);
-    mbar_init(&bar_done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (tid < S) {
-    float mean = 0.f, rstd = 1.f;
-    if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
-    mr[tid][0] = mean;
-    mr[tid][1] = rstd;
-  }
-  if (wid == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = tmem_slot;
-
-  const int nchunks = (a.K + KC - 1) / KC;
-  // A staging role of this thread: row r of an 8-row group, K quad kq (16 B) of the chunk
-  const int ar = lane & 7, akq = (lane >> 3) + 4 * (wid >> 2);  // kq in 0..7
-  const int ap = 8 * (wid & 3) + ar;                            // pixel inside the tile, 0..31
-  const int gp = p0 + ap;
-  const bool pv = gp < a.hw;
-  // B staging role: n row nr of an 8-row group, k = 4*kq + (lane>>3)
-  const int bnr = lane & 7, bkr = lane >> 3;
-
-  for (int c = 0; c < nchunks; ++c) {
-    const int stage = c & 1;
-    float* As_hi = smem + stage * STAGE;
-    float* As_lo = As_hi + A_ST;
-    float* Bs_hi = As_lo + A_ST;
-    float* Bs_lo = Bs_hi + B_ST;
-    const int k0 = c * KC;
-    const int kc = min(KC, a.K - k0);   // multiple of 8 (launch precondition)
-    if (c >= 2) mbar_wait(&bar_free[stage], ((c >> 1) - 1) & 1);   // MMAs of chunk c-2 have drained this stage
-
-    // ---- A: LReLU + LayerNorm + split, canonical K-major layout
-    if (akq * 4 < kc) {
-      const long long e = (long long)gp * a.K + k0 + akq * 4;
-      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 xv[S];
-      if (pv) {
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-          if (s < ns) xv[s] = ld4(src_n + ((long long)(s0 + s) * a.hw) * a.K + e);
-        if (a.ln) {
-          g = ld4(gam + e);
-          be = ld4(bet + e);
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (pv && s < ns) {
-          const float mean = mr[s][0], rstd = mr[s][1];
-          v[0] = lrelu(xv[s].x); v[1] = lrelu(xv[s].y); v[2] = lrelu(xv[s].z); v[3] = lrelu(xv[s].w);
-          if (a.ln) {
-            v[0] = (v[0] - mean) * rstd * g.x + be.x;
-            v[1] = (v[1] - mean) * rstd * g.y + be.y;
-            v[2] = (v[2] - mean) * rstd * g.z + be.z;
-            v[3] = (v[3] - mean) * rstd * g.w + be.w;
-          }
-        }
-        float h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tf32_split(v[i], h[i], l[i]);
-        // row m = s*32 + ap -> 8-row group (m >> 3), row (m & 7) = ar; 16-B unit = ar + 8*akq + 64*group
-        const int unit = ar + 8 * akq + 64 * ((s * PT + ap) >> 3);
-        st4(As_hi + 4 * unit, make_float4(h[0], h[1], h[2], h[3]));
-        st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
-      }
-    }
-    // ---- B: W[k][n] -> K-major [n][k] images (hi / lo)
-    for (int it = wid; it < (N / 8) * (KC / 4); it += NT / 32) {
-      const int ng = it % (N / 8), kq = it / (N / 8);
-      const int n = ng * 8 + bnr, k = kq * 4 + bkr;
-      float w = 0.f;
-      if (k < kc) w = Wg[(long long)(k0 + k) * a.N + n];
-      float h, l;
-      tf32_split(w, h, l);
-      const int off = 4 * (bnr + 8 * kq + (KC / 4) * 8 * ng) + bkr;
-      Bs_hi[off] = h;
-      Bs_lo[off] = l;
-    }
-    fence_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idesc = umma_idesc_tf32(N);
-      const uint32_t a_hi = smem_u32(As_hi), a_lo = smem_u32(As_lo), b_hi = smem_u32(Bs_hi), b_lo = smem_u32(Bs_lo);
-      constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
-      for (int ks = 0; ks < kc / 8; ++ks) {
-        const uint32_t adv = ks * 2 * LBO;    // 8 tf32 = two 16-B K chunks per MMA
-        const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
-        const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
-        umma_tf32(tmem_d, dah, dbh, idesc, (c | ks) != 0);
-        umma_tf32(tmem_d, dal, dbh, idesc, 1);
-        umma_tf32(tmem_d, dah, dbl, idesc, 1);
-      }
-      umma_commit(&bar_free[stage]);
-      if (c == nchunks - 1) umma_commit(&bar_done);
-    }
-  }
-
-  // ---- epilogue
-  mbar_wait(&bar_done, 0);
-  tc_fence_after();
-  const int quarter = wid & 3, half = wid >> 2;
-  const int m = quarter * 32 + lane;           // accumulator row == TMEM lane
-  const int es = m / PT, ep = m % PT;          // sample / pixel of this row (PT == 32: es == quarter)
-  float v[NC];
-  tmem_ld<NC>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC), v);
-  const int egp = p0 + ep;
-  float s1 = 0.f, s2 = 0.f;
-  if (egp < a.hw && es < ns) {
-    const long long row = ((long long)(s0 + es) * a.hw + egp) * a.N + half * NC;
-    float* out_r = a.out + (long long)net * a.out_net_stride + row;
-    const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
-    const float* bias = P + a.b_off + half * NC;
-#pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-      const float4 bb = ld4(bias + j);
-      float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
-      if (res_r) {
-        const float4 rr = ld4(res_r + j);
-        o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
-      }
-      st4(out_r + j, make_float4(o0, o1, o2, o3));
-      float l;
-      l = lrelu(o0); s1 += l; s2 += l * l;
-      l = lrelu(o1); s1 += l; s2 += l * l;
-      l = lrelu(o2); s1 += l; s2 += l * l;
-      l = lrelu(o3); s1 += l; s2 += l * l;
-    }
-  }
-  if (a.stats_out) {
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      red[wid][0] = s1;
-      red[wid][1] = s2;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (a.stats_out && tid < 2 * S && (tid >> 1) < ns) {
-    // sample s is covered by warps s (columns [0, N/2)) and s + 4 (columns [N/2, N))
-    const int s = tid >> 1, which = tid & 1;
-    const double t = (double)red[s][which] + (double)red[s + 4][which];
-    atomicAdd(a.stats_out + 2 * ((long long)net * a.B + s0 + s) + which, t);
-  }
-  if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks a list of 128-row tiles.  Raw activations / gamma / beta are
-// streamed with cp.async (16 B per thread, thread-private slots) into a DEPTH-deep shared-memory ring
-// that runs ahead across chunk AND tile boundaries, so ~70 KB of loads stay in flight per SM while the
-// warps do LReLU + LayerNorm + hi/lo split, the tensor core runs, and the epilogue stores.
-// ---------------------------------------------------------------------------------------------
+// cp.async helpers
 __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -334,245 +142,6 @@ __device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int N>
-__global__ void __launch_bounds__(256, 1) pw_tc2_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
-  constexpr int NT = 256;
-  constexpr int S = 4, PT = 32, M = 128;
-  constexpr int KC = 32;
-  constexpr int DEPTH = 3;                     // cp.async ring depth (chunks in flight)
-  constexpr int A_ST = M * KC, B_ST = N * KC;
-  constexpr int RAW = 6 * NT * 4;              // floats per ring entry: 4 x-slots + gamma + beta per thread
-  constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
-  constexpr int NC = N / 2;
-  extern __shared__ __align__(128) float tc2_smem[];
-  const int nchunks = (a.K + KC - 1) / KC;
-  float* opsA = tc2_smem;                      // [2 stages][hi, lo][A_ST]
-  float* raw = opsA + 4 * A_ST;                // [DEPTH][6][NT] float4
-  float* Bres = raw + DEPTH * RAW;             // [nchunks][hi, lo][B_ST]  (resident for the whole kernel)
-  __shared__ __align__(8) uint64_t bar_free[2];
-  __shared__ __align__(8) uint64_t bar_done;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float mr[2][S][2];                // (rstd, -mean*rstd) per sample, double-buffered by tile parity
-  __shared__ float red[NT / 32][2];
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // one net per CTA (even CTAs: net A, odd: net b) so that W stays resident
-  const int net = blockIdx.x & 1;
-  const int cta = blockIdx.x >> 1, ncta = (gridDim.x + 1 - net) >> 1;
-  const int ntiles = tiles_p * tiles_s;        // tiles of one net
-  const int my_tiles = cta < ntiles ? (ntiles - 1 - cta) / ncta + 1 : 0;
-  const int total = my_tiles * nchunks;
-
-  const float* P = a.params + (long long)net * a.net_stride;
-  const float* src_n = a.in + (long long)net * a.in_net_stride;
-  const float* gam = P + a.g_off;
-  const float* bet = P + a.be_off;
-
-  if (tid == 0) {
-    mbar_init(&bar_free[0], 1);
-    mbar_init(&bar_free[1], 1);
-    mbar_init(&bar_done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (wid == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
-
-  // staging roles: row ar of an 8-row group, K quad akq, pixel ap (see pw_tc_kernel)
-  const int ar = lane & 7, akq = (lane >> 3) + 4 * (wid >> 2);
-  const int ap = 8 * (wid & 3) + ar;
-
-  // prefetch cursor (tile, chunk) of the next chunk to issue; advanced without divisions
-  int pf_tl = 0, pf_c = 0, pf_r = cta;
-  int pf_s0 = (pf_r / tiles_p) * S, pf_p0 = (pf_r % tiles_p) * PT;
-  int pf_slot = 0;
-  auto issue = [&]() {
-    if (pf_tl < my_tiles) {
-      const int k0 = pf_c * KC, kc = min(KC, a.K - k0);
-      const int gp = pf_p0 + ap;
-      if (akq * 4 < kc && gp < a.hw) {
-        float* dst = raw + pf_slot * RAW;
-        const long long e = (long long)gp * a.K + k0 + akq * 4;
-        const int ns = min(S, a.B - pf_s0);
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-          if (s < ns) cp_async16_cg(dst + (s * NT + tid) * 4, src_n + ((long long)(pf_s0 + s) * a.hw) * a.K + e);
-        if (a.ln) {
-          cp_async16_ca(dst + (4 * NT + tid) * 4, gam + e);
-          cp_async16_ca(dst + (5 * NT + tid) * 4, bet + e);
-        }
-      }
-      if (++pf_c == nchunks) {
-        pf_c = 0;
-        ++pf_tl;
-        pf_r += ncta;
-        pf_s0 = (pf_r / tiles_p) * S;
-        pf_p0 = (pf_r % tiles_p) * PT;
-      }
-    }
-    pf_slot = pf_slot + 1 == DEPTH ? 0 : pf_slot + 1;
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int i = 0; i < DEPTH; ++i) issue();
-
-  // resident B operand: W[k][n] -> K-major hi/lo images per chunk
-  {
-    const float* Wg = P + a.w_off;
-    const int bnr = lane & 7, bkr = lane >> 3;
-    for (int it = wid; it < nchunks * (N / 8) * (KC / 4); it += NT / 32) {
-      const int c = it / ((N / 8) * (KC / 4)), r = it % ((N / 8) * (KC / 4));
-      const int ng = r % (N / 8), kq = r / (N / 8);
-      const int n = ng * 8 + bnr, k = c * KC + kq * 4 + bkr;
-      float w = 0.f;
-      if (k < a.K) w = Wg[(long long)k * a.N + n];
-      float h, l;
-      tf32_split(w, h, l);
-      const int off = c * 2 * B_ST + 4 * (bnr + 8 * kq + (KC / 4) * 8 * ng) + bkr;
-      Bres[off] = h;
-      Bres[off + B_ST] = l;
-    }
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = tmem_slot;
-
-  int gi = 0, slot = 0;
-  int r = cta;
-  for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
-    const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
-    const int ns = min(S, a.B - s0);
-    if (tid < S) {
-      float mean = 0.f, rstd = 1.f;
-      if (a.ln && tid < ns) ln_coeffs(a.stats_in, (long long)net * a.B + s0 + tid, (double)a.hw * (double)a.K, mean, rstd);
-      mr[tl & 1][tid][0] = rstd;
-      mr[tl & 1][tid][1] = -mean * rstd;
-    }
-    __syncthreads();
-    const bool pv = (p0 + ap) < a.hw;
-    const int quarter = wid & 3, half = wid >> 2;
-    const int m = quarter * 32 + lane;
-    const int es = m / PT, egp = p0 + (m % PT);
-    const bool erow = egp < a.hw && es < ns;
-    const long long row = ((long long)(s0 + es) * a.hw + egp) * a.N + half * NC;
-    float4 resv[NC / 4];
-
-    for (int c = 0; c < nchunks; ++c, ++gi) {
-      const int stage = gi & 1;
-      float* As_hi = opsA + stage * 2 * A_ST;
-      float* As_lo = As_hi + A_ST;
-      const int kc = min(KC, a.K - c * KC);
-      if (c == nchunks - 1 && a.res && erow) {   // residual rows: in flight during the last chunk
-        const float* res_r = a.res + (long long)net * a.out_net_stride + row;
-#pragma unroll
-        for (int j = 0; j < NC / 4; ++j) resv[j] = ld4(res_r + 4 * j);
-      }
-      cp_async_wait<DEPTH - 1>();               // this thread's copies of chunk gi have landed
-      if (gi >= 2) mbar_wait(&bar_free[stage], ((gi >> 1) - 1) & 1);
-      if (akq * 4 < kc) {
-        const float* src = raw + slot * RAW;
-        float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pv && a.ln) {
-          g = ld4(src + (4 * NT + tid) * 4);
-          be = ld4(src + (5 * NT + tid) * 4);
-        }
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (pv && s < ns) {
-            const float4 xv = ld4(src + (s * NT + tid) * 4);
-            const float sc = mr[tl & 1][s][0], sh = mr[tl & 1][s][1];
-            v[0] = fmaxf(xv.x, CNF_LRELU_SLOPE * xv.x);
-            v[1] = fmaxf(xv.y, CNF_LRELU_SLOPE * xv.y);
-            v[2] = fmaxf(xv.z, CNF_LRELU_SLOPE * xv.z);
-            v[3] = fmaxf(xv.w, CNF_LRELU_SLOPE * xv.w);
-            if (a.ln) {   // ((v - mean) * rstd) * gamma + beta with (v - mean) * rstd = fma(v, rstd, -mean * rstd)
-              v[0] = fmaf(fmaf(v[0], sc, sh), g.x, be.x);
-              v[1] = fmaf(fmaf(v[1], sc, sh), g.y, be.y);
-              v[2] = fmaf(fmaf(v[2], sc, sh), g.z, be.z);
-              v[3] = fmaf(fmaf(v[3], sc, sh), g.w, be.w);
-            }
-          }
-          float h[4], l[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) tf32_split(v[i], h[i], l[i]);
-          const int unit = ar + 8 * akq + 64 * ((s * PT + ap) >> 3);
-          st4(As_hi + 4 * unit, make_float4(h[0], h[1], h[2], h[3]));
-          st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
-        }
-      }
-      issue();                                  // refill the ring entry this thread has just consumed
-      slot = slot + 1 == DEPTH ? 0 : slot + 1;
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc_tf32(N);
-        const uint32_t a_hi = smem_u32(As_hi), a_lo = smem_u32(As_lo);
-        const uint32_t b_hi = smem_u32(Bres + c * 2 * B_ST), b_lo = b_hi + B_ST * 4;
-        constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
-        for (int ks = 0; ks < kc / 8; ++ks) {
-          const uint32_t adv = ks * 2 * LBO;
-          const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
-          const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
-          umma_tf32(tmem_d, dah, dbh, idesc, (c | ks) != 0);
-          umma_tf32(tmem_d, dal, dbh, idesc, 1);
-          umma_tf32(tmem_d, dah, dbl, idesc, 1);
-        }
-        umma_commit(&bar_free[stage]);
-        if (c == nchunks - 1) umma_commit(&bar_done);
-      }
-    }
-
-    // ---- epilogue of this tile
-    mbar_wait(&bar_done, tl & 1);
-    tc_fence_after();
-    float v[NC];
-    tmem_ld<NC>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC), v);
-    float s1 = 0.f, s2 = 0.f;
-    if (erow) {
-      float* out_r = a.out + (long long)net * a.out_net_stride + row;
-      const float* bias = P + a.b_off + half * NC;
-#pragma unroll
-      for (int j = 0; j < NC; j += 4) {
-        const float4 bb = ld4(bias + j);
-        float o0 = v[j] + bb.x, o1 = v[j + 1] + bb.y, o2 = v[j + 2] + bb.z, o3 = v[j + 3] + bb.w;
-        if (a.res) {
-          const float4 rr = resv[j / 4];
-          o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
-        }
-        st4(out_r + j, make_float4(o0, o1, o2, o3));
-        float l;
-        l = fmaxf(o0, CNF_LRELU_SLOPE * o0); s1 += l; s2 = fmaf(l, l, s2);
-        l = fmaxf(o1, CNF_LRELU_SLOPE * o1); s1 += l; s2 = fmaf(l, l, s2);
-        l = fmaxf(o2, CNF_LRELU_SLOPE * o2); s1 += l; s2 = fmaf(l, l, s2);
-        l = fmaxf(o3, CNF_LRELU_SLOPE * o3); s1 += l; s2 = fmaf(l, l, s2);
-      }
-    }
-    if (a.stats_out) {
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      if (lane == 0) {
-        red[wid][0] = s1;
-        red[wid][1] = s2;
-      }
-    }
-    tc_fence_before();   // order this tile's tcgen05.ld before the next tile's first MMA (issued after a barrier)
-    __syncthreads();
-    if (a.stats_out && tid < 2 * S && (tid >> 1) < ns) {
-      const int s = tid >> 1, which = tid & 1;
-      const double t = (double)red[s][which] + (double)red[s + 4][which];
-      atomicAdd(a.stats_out + 2 * ((long long)net * a.B + s0 + s) + which, t);
-    }
-  }
-  cp_async_wait<0>();
-  tc_fence_before();
-  __syncthreads();
-  if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised persistent variant (the one the flow uses):
@@ -695,7 +264,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
     int gi = 0, slot = 0, r = cta;
     // LayerNorm coefficients: every thread keeps (rstd, -mean*rstd) of its own samples in registers; the (sum, sumsq)
     // pairs of tile tl+1 are loaded while tile tl is transformed (no shared copy, no barrier between tiles)
-    const float inv_n = 1.0f / ((float)a.hw * (float)a.K);
+    const double inv_n = 1.0 / ((double)a.hw * (double)a.K);   // mean and centred variance in fp64 (see ln_coeffs)
     double st_s[SPT], st_q[SPT];
     // tile index r = tq * tiles_p + tp is advanced by ncta without divisions
     const int dq = ncta / tiles_p, dp = ncta - dq * tiles_p;
@@ -723,8 +292,9 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
       for (int j = 0; j < SPT; ++j) {
         // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence: four ~200-instruction dependent chains per tile sat on
         // the critical path between tiles (measured 1400 cycles); the difference is ~1e-7 relative
-        const float m_ = (float)st_s[j] * inv_n;
-        const float var = fmaxf(fmaf(-m_, m_, (float)st_q[j] * inv_n), 0.f);
+        const double md = st_s[j] * inv_n;
+        const float m_ = (float)md;
+        const float var = fmaxf((float)(st_q[j] * inv_n - md * md), 0.f);
         const float sc = rsqrtf(var + (float)CNF_LN_EPS);
         cf[j] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
       }

@@ -260,12 +260,12 @@ def run_ours(args):
         br = _lib.Borrowed()
         pp, pw_ = br(layer.params), br(ws)
         for _ in range(3):
-            _lib.check(_lib.lib.cnf_debug_pw_conv(layer._h, pp, pw_, B, which, _lib.stream_ptr()))
+            _lib.check(_lib.lib.cnf_measure_stage(layer._h, pp, pw_, B, which, _lib.stream_ptr()))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            _lib.check(_lib.lib.cnf_debug_pw_conv(layer._h, pp, pw_, B, which, _lib.stream_ptr()))
+            _lib.check(_lib.lib.cnf_measure_stage(layer._h, pp, pw_, B, which, _lib.stream_ptr()))
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps

@@ -12,7 +12,8 @@
  *   - tensors are fp32, on the CUDA device that is current for the calling thread, compact
  *     row-major NHWC, 16-byte aligned; libcnf borrows them for the call and never frees them;
  *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no
- *     function synchronises, allocates device memory, or keeps global mutable state;
+ *     function synchronises or allocates device memory; the only process-wide state is the
+ *     per-device cache of kernel attributes (mutex-protected), so one thread per device is safe;
  *   - the caller allocates every output and the workspace (`cnf_*_workspace_bytes`).
  */
 #ifndef CNF_H_
@@ -114,6 +115,22 @@ int64_t cnf_plan_workspace_bytes(const cnf_plan* p, int64_t batch);
  * not thread-safe against concurrent calls that use the same plan.  Replaces nothing in the reference. */
 int cnf_plan_set_fusion(cnf_plan* p, int enable);
 int cnf_coupling_set_fusion(cnf_coupling* c, int enable);
+/* Kernel-family selection per stage of a coupling layer.  Every stage has a fastest kernel and one or more general ones
+ * that cover the shapes it does not; `excluded` is a set of CNF_PATH_* bits naming families this
+ * descriptor must NOT use, so that every shipped kernel can be exercised on any shape (tests/test_gpu_parity.py) and
+ * A/B-timed (bench.py).  0 (default) = the fastest eligible kernel everywhere.  All combinations give the same results to
+ * fp32 rounding.  Host-side flag, not thread-safe against concurrent calls on the same descriptor. */
+#define CNF_PATH_NO_RESIDENT 1  /* no activation-resident launch (fused_kernels.cu): layer-per-kernel path          */
+#define CNF_PATH_NO_TCGEN05 2   /* 1x1 convs: no tcgen05 3xTF32 kernel (pw_tc3_kernel) -> fp32 FFMA pw_kernel          */
+#define CNF_PATH_NO_PW_FFMA 4   /* 1x1 convs: no multi-sample FFMA kernel either -> generic gemm_kernel                */
+#define CNF_PATH_NO_OCTET 8     /* grouped convs: no all-branch octet kernel (gconv_oct_kernel) -> one launch per branch */
+#define CNF_PATH_NO_BRANCH 16   /* grouped convs: no per-branch gconv3_kernel -> gconv2_kernel / gconv_kernel          */
+#define CNF_PATH_NO_GCONV2 32   /* grouped convs: no register-blocked gconv2_kernel -> generic gconv_kernel            */
+#define CNF_PATH_NO_STEM2 64    /* stem: no per-sample stem2_kernel -> implicit-im2col gemm_kernel                     */
+#define CNF_PATH_NO_HEAD2 128   /* head: no streaming head2_kernel -> halo-tile head_kernel                           */
+#define CNF_PATH_ALL 255
+int cnf_plan_set_kernel_paths(cnf_plan* p, int excluded);
+int cnf_coupling_set_kernel_paths(cnf_coupling* c, int excluded);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* cFlow.call(xy, direction=+1) (M:1743-1772): zy in the ORIGINAL (H,W,D) layout plus the PER-SAMPLE
@@ -174,17 +191,6 @@ int cnf_coupling_backward(const cnf_coupling* c, const DLManagedTensor* v, const
 int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1_compressed,
                       const DLManagedTensor* params, DLManagedTensor* A, DLManagedTensor* b,
                       DLManagedTensor* workspace, void* stream);
-
-/* measurement hook: launches ONLY one kernel of residual block 0 (which = 0: pw1, X -> Y1 with
- * LayerNorm-on-load; which = 1: pw2, Y2 (+X) -> X; which = 2: the fused grouped dilated convs, Y1 -> Y2)
- * on the workspace state left by a
- * previous cnf_coupling_nets / cnf_coupling_forward call with the same batch.  Used by bench.py to time that
- * kernel alone with CUDA events (roofline).  Replaces nothing in the reference. */
-int cnf_debug_pw_conv(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace,
-                      int64_t batch, int which, void* stream);
-
-/* timing instrumentation of the 1x1-conv kernel (CNF_PW_DBG=128): clock64() stamps of CTA 0, [role][chunk][8] */
-int cnf_debug_read_clocks(long long* out, int n);
 
 /* fused standalone coupling law + mask addressing + per-sample log-det (M:1215-1253, M:1307-1326):
  * v = mask(u,m,False) + decompress(exp(s)*u2c + t, m_bar)   (inverse: (u2c - t) / exp(s)).

@@ -271,6 +271,44 @@ def test_resident_path_equals_per_kernel_path(dev, name, cfg, B):
     assert torch.equal(zy_k, out[1][0][:3])
 
 
+PATH_SETS = {   # CNF_PATH_* bits (include/cnf.h): which kernel serves each stage
+    "per-kernel": 1, "pw-ffma": 1 | 2, "pw-gemm": 1 | 2 | 4, "gconv-branch": 1 | 8, "gconv2": 1 | 8 | 16,
+    "gconv-generic": 1 | 8 | 16 | 32, "stem-gemm+head-tiles": 1 | 64 | 128, "all-general": 255,
+}
+
+
+@pytest.mark.parametrize("shape,m,card,nk,dil", [
+    ([28, 28, 2], 2, 8, 64, [1, 2, 4]), ([28, 28, 2], 0, 8, 64, [1, 2, 4]), ([14, 14, 4], 3, 4, 32, [1, 2]),
+    ([32, 32, 4], 2, 8, 64, [1, 2, 4]), ([64, 64, 6], 1, 4, 64, [1, 2, 4, 8]), ([12, 10, 3], 2, 2, 16, [1, 2]),
+], ids=lambda v: str(v))
+def test_every_kernel_family_gives_the_same_layer(dev, shape, m, card, nk, dil):
+    """Each stage of a coupling layer has a fastest kernel and general ones for the shapes it does not cover.  Excluding
+    kernel families (cnf_coupling_set_kernel_paths) must not change the layer: same v, log-det and inverse to fp32
+    rounding on every path, and the default path agrees with the oracle elsewhere in this file."""
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import coupling_layer
+    L = plan_coupling(shape, m, 2, card, nk, 3, dil)
+    W = init_weights({'layers': [L]}, 'rand', seed=13)[0]
+    layer = coupling_layer(shape, m, 2, card, nk, 3, None, LAYER_NORM=True, which_dilations=dil, device=dev)
+    layer.set_weights(W)
+    g = torch.Generator(device=dev).manual_seed(5)
+    u = torch.randn(5, *shape, device=dev, generator=g)
+    layer.set_kernel_paths(0)
+    v0, _, _ = layer.forward_and_Jacobian(u, 0.0, None)
+    ld0 = layer.last_logdet_per_sample.clone()
+    ui0, _ = layer.backward(u, None)
+    assert torch.isfinite(v0).all() and torch.isfinite(ui0).all()
+    for name, bits in PATH_SETS.items():
+        layer.set_kernel_paths(bits)
+        v, _, _ = layer.forward_and_Jacobian(u, 0.0, None)
+        ld = layer.last_logdet_per_sample
+        ui, _ = layer.backward(u, None)
+        for a, b_ in ((v, v0), (ld, ld0), (ui, ui0)):
+            err = float((a - b_).abs().max() / b_.abs().max())
+            assert err < 2e-5, (name, err)
+    with pytest.raises(AssertionError):
+        layer.set_kernel_paths(256)
+
+
 def test_flow_layerwise_equals_fused_call(dev):
     """Driving layers_list by hand exactly like cFlow.call (M:1743-1770) gives the fused in-place result."""
     m, _ = mk(MID, 'rand', seed=4)
