@@ -690,7 +690,11 @@ class cFlow:
         NCCL (sharding.allreduce_mean_gradients); the reported metrics are this rank's shard's."""
         if self.optimizer is None:
             raise RuntimeError("train_step: call model.compile(optimizer=Adam(...)) first")   # keras raises too
-        from .sharding import allreduce_mean_gradients
+        from .sharding import allreduce_mean_gradients, sync_replicas
+        if not getattr(self, '_replicas_synced', False):
+            # data-parallel replicas must start from the same weights / optimizer state (rank 0's); single process: no-op
+            sync_replicas(self)
+            self._replicas_synced = True
         four, grads = self.loss_and_grad(xy)
         allreduce_mean_gradients(grads, xy.shape[0])
         self.optimizer.apply_gradients(self.params, grads)

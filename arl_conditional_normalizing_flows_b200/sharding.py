@@ -36,6 +36,43 @@ def log_loss_sharded(model, xy_local, group=None):
     return global_loss(ps['ll_z'], ps['ll_y'], ps['logdet'], group)
 
 
+def sync_replicas(model, src=0, group=None):
+    """Make every rank's replica identical to rank `src`'s: the flat parameter buffer and, when the optimizer has
+    state, Adam's m / v / step count.  Data-parallel training only reproduces single-device training if the replicas
+    START identical (cFlow.__init__ draws its Orthogonal(0.1) kernels from an unseeded generator, so they do not), so
+    cFlow.train_step calls this once before its first data-parallel update.  No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return False
+    dist.broadcast(model.params, src=src, group=group)
+    opt = getattr(model, 'optimizer', None)
+    if opt is not None:
+        it = torch.tensor([int(getattr(opt, 'iterations', 0))], dtype=torch.int64, device=model.params.device)
+        dist.broadcast(it, src=src, group=group)
+        opt.iterations = int(it.item())
+        has = torch.tensor([0 if getattr(opt, '_m', None) is None else 1], dtype=torch.int64, device=model.params.device)
+        dist.broadcast(has, src=src, group=group)
+        if int(has.item()):
+            if opt._m is None or opt._m.shape != model.params.shape:
+                opt._m = torch.zeros_like(model.params)
+                opt._v = torch.zeros_like(model.params)
+            dist.broadcast(opt._m, src=src, group=group)
+            dist.broadcast(opt._v, src=src, group=group)
+    return True
+
+
+def replicas_checksum_equal(model, group=None):
+    """True iff every rank holds bit-identical parameters (max and min of a 64-bit fold of the buffer agree)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return True
+    h = model.params.detach().contiguous().view(torch.int32).to(torch.int64)
+    w = torch.arange(1, h.numel() + 1, dtype=torch.int64, device=h.device)
+    c = ((h * w) % 2147483629).sum().reshape(1)
+    lo, hi = c.clone(), c.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool((lo == hi).item())
+
+
 def allreduce_mean_gradients(grads, n_local, group=None):
     """In place: this rank's gradient of ITS shard's mean loss -> the gradient of the GLOBAL batch's mean loss,
     sum_r (n_r / N) g_r.  One sum all-reduce of the flat buffer plus an 8-byte one for N (shards may be uneven);

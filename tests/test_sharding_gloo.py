@@ -117,3 +117,48 @@ def test_two_rank_gradient_allreduce_equals_full_batch_gradient(B):
     for _, got in res:
         np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
     np.testing.assert_array_equal(res[0][1], res[1][1])      # every rank applies the identical update
+
+
+# ---- replicas that start different are made identical before the first data-parallel update -----------------
+def _sync_worker(rank, world, port, q):
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam, cFlow
+    from arl_conditional_normalizing_flows_b200.sharding import replicas_checksum_equal, sync_replicas
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    np.random.seed(100 + rank)
+    m = cFlow(**CFG, device="cpu")                  # default init: every rank draws different orthogonal kernels
+    m.params.add_(float(rank))                       # ... and make sure of it
+    m.compile(optimizer=Adam(3e-4))
+    if rank == 0:                                    # rank 0 has optimizer state, rank 1 has none
+        m.optimizer._m = torch.full_like(m.params, 0.25)
+        m.optimizer._v = torch.full_like(m.params, 0.5)
+        m.optimizer.iterations = 7
+    before = replicas_checksum_equal(m)
+    did = sync_replicas(m)
+    after = replicas_checksum_equal(m)
+    q.put((rank, before, did, after, m.params[:64].clone().numpy(), m.optimizer.iterations,
+           float(m.optimizer._m[0]), float(m.optimizer._v[-1])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_replicas_are_synchronised_before_training():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, before, did, after, _, it, m0, v0 in res:
+        assert before is False and did is True and after is True
+        assert it == 7 and m0 == 0.25 and v0 == 0.5
+    np.testing.assert_array_equal(res[0][4], res[1][4])
