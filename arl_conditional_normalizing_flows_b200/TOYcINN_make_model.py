@@ -37,6 +37,8 @@ class coupling_layer:
 
     def get_weights(self):
         """Flat list [W, b, W, b, ...] for net b then net A (Keras layer-creation order, T:52-93)."""
+        if self._owner is not None:
+            self._owner.sync_layer_weights()
         out = []
         for net in ("b", "A"):
             for W, b in self._w[net]:
@@ -46,6 +48,8 @@ class coupling_layer:
     def set_weights(self, weights):
         n = len(self._w["b"])
         assert len(weights) == 4 * n, f"expected {4 * n} arrays, got {len(weights)}"
+        if self._owner is not None:
+            self._owner.sync_layer_weights()       # keep what a previous train_step wrote into the other layers
         k = 0
         for net in ("b", "A"):
             for i in range(n):
@@ -198,5 +202,72 @@ class cINN_affine:
     def test_step(self, xy):
         return self._update_trackers(self.log_loss(xy))
 
+    # -- training (T:453-482) -----------------------------------------------------------------------------------
+    def loss_and_grad(self, xy):
+        """log_loss(xy) plus d loss / d params as ONE flat tensor with the layout of self.params (hand-written backward
+        kernel, csrc/toy_kernels.cu: no stored activations, layer inputs recovered with the inverse law).
+        Returns ((loss, z_loss, y_loss, detJ_loss), grads)."""
+        xy = require_cuda(xy, "xy")
+        if xy.dim() != 2 or xy.shape[1] != 3:
+            raise ValueError(f"xy: expected shape [B, 3], got {tuple(xy.shape)}")
+        if self._dirty or self.params is None:
+            self._pack()
+        B = xy.shape[0]
+        Bp = (B + 3) & ~3
+        zy = torch.empty_like(xy)
+        pers = torch.empty((3, Bp), dtype=torch.float32, device=xy.device)
+        loss4 = torch.empty(4, dtype=torch.float32, device=xy.device)
+        ll_z, ll_y, ld = pers[0, :B], pers[1, :B], pers[2, :B]
+        if getattr(self, '_grads', None) is None or self._grads.shape != self.params.shape:
+            self._grads = torch.empty_like(self.params)
+        br = Borrowed()
+        check(lib.cnf_toy_loss_and_grad(br(xy), br(self.params), self._order(), self.num_coupling_layers,
+                                        self.intermediate_dims, self.num_layers, int(self.x_d), float(self.lambda_y),
+                                        br(self._grads), br(zy), br(ll_z), br(ll_y), br(ld), br(loss4), stream_ptr()))
+        self.last_per_sample = {'ll_z': ll_z, 'll_y': ll_y, 'logdet': ld, 'zy': zy}
+        return (loss4[0], loss4[1], loss4[2], loss4[3]), self._grads
+
+    def _unpack(self, flat=None):
+        """flat device buffer (self.params, or a gradient buffer of the same layout) -> per-layer Keras-shaped lists
+        [{'A': [(W, b), ...], 'b': [...]}, ...]; with flat=None the layers' own weights are refreshed from self.params."""
+        I, L = self.intermediate_dims, self.num_layers
+        host = (self.params if flat is None else flat).detach().cpu().numpy()
+        net_sz = int(lib.cnf_toy_layer_offset(1, I, L)) // 2
+        out = []
+        for j, cl in enumerate(self.coupling_layers_list):
+            entry = {}
+            for k, net in enumerate(("A", "b")):
+                base = int(lib.cnf_toy_layer_offset(j, I, L)) + k * net_sz
+                d1, d2 = cl.u1_size, cl.u2_size
+                layers = [(host[base: base + d1 * I].reshape(d1, I).copy(), host[base + 2 * I: base + 3 * I].copy())]
+                p = base + 3 * I
+                for _ in range(L):
+                    layers.append((host[p: p + I * I].reshape(I, I).copy(), host[p + I * I: p + I * I + I].copy()))
+                    p += I * I + I
+                layers.append((host[p: p + 2 * I].reshape(I, 2)[:, :d2].copy(), host[p + 2 * I: p + 2 * I + d2].copy()))
+                entry[net] = layers
+            out.append(entry)
+        if flat is None:
+            for cl, entry in zip(self.coupling_layers_list, out):
+                for net in ("A", "b"):
+                    cl._w[net] = [[W, b] for W, b in entry[net]]
+        return out
+
+    def grad_views(self):
+        """the last gradient as [{'A': [(dW, db), ...], 'b': [...]}, ...] (same nesting as the oracle's weights)"""
+        return self._unpack(self._grads)
+
     def train_step(self, xy):
-        raise NotImplementedError("cINN_affine.train_step: backward kernels are not built in this round")
+        """cINN_affine.train_step (T:453-482): gradients of log_loss, optimizer.apply_gradients, metric trackers."""
+        if self.optimizer is None:
+            raise RuntimeError("train_step: call model.compile(optimizer=Adam(...)) first")
+        four, grads = self.loss_and_grad(xy)
+        self.optimizer.apply_gradients(self.params, grads)
+        self._layers_stale = True          # coupling_layer.get_weights() refreshes from the device buffer on demand
+        return self._update_trackers(four)
+
+    def sync_layer_weights(self):
+        """copy the trained flat buffer back into coupling_layers_list[i] (get_weights of the layers, Y:228-235)"""
+        if getattr(self, '_layers_stale', False):
+            self._unpack()
+            self._layers_stale = False

@@ -103,6 +103,7 @@ def _load():
         "cnf_coupling_backward": (I, [P, P, P, P, P, V]),
         "cnf_coupling_nets": (I, [P, P, P, P, P, P, V]),
         "cnf_coupling_law": (I, [P, P, P, I, I, P, P, V]),
+        "cnf_residual_block": (I, [P, I, P, P, P, P, V]),
         "cnf_measure_stage": (I, [P, P, P, I64, I, V]),
         "cnf_mask": (I, [P, I, I, P, V]),
         "cnf_decompress_mask": (I, [P, I, P, V]),
@@ -117,6 +118,7 @@ def _load():
         "cnf_toy_layer_offset": (I64, [I, I, I]),
         "cnf_toy_call": (I, [P, P, IP, I, I, I, I, P, P, V]),
         "cnf_toy_log_loss": (I, [P, P, IP, I, I, I, I, D, P, P, P, P, P, V]),
+        "cnf_toy_loss_and_grad": (I, [P, P, IP, I, I, I, I, D, P, P, P, P, P, P, V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch

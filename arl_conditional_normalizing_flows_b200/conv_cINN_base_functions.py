@@ -12,7 +12,7 @@ libcnf (csrc/data_kernels.cu) on torch CUDA tensors: `down` / `up` (F:74-164), `
 (F:174-231), `preprocess_dataset_SR` (F:233-279), `de_logitify` (F:287-318), `instance_noise` (F:635-653),
 `renew_noise` (F:660-676).  The reference maps them over a `tf.data.Dataset` element by element on the host; here the
 "dataset" is a batched tensor [N,H,W,D] (an un-batched [H,W,D] element is accepted where the reference accepts one).
-TFRecord parsing (F:26-65) stays out of scope.
+TFRecord parsing (F:26-65): `tfrecords.py`.
 """
 import torch
 
@@ -40,19 +40,53 @@ def residual_block_plan(nb_channels_in, _which_dilations=(1, 2, 4), cardinality=
 def dilated_residual_block(y, nb_channels_in, nb_channels_out, _strides=(1, 1), _project_shortcut=False,
                            _which_dilations=[1, 2, 4], ksize=(4, 4), cardinality=4, ln=False, do=False,
                            ln_axis=-1, init='glorot_uniform', weights=None):
-    """F:501-627 on a concrete torch CUDA tensor `y` [B,h,w,nb_channels_out].
+    """F:501-627 on a concrete torch CUDA tensor `y` [B,h,w,nb_channels_out]:
+    LN(LReLU) -> Conv1x1(nb_channels_in) -> LN(LReLU) -> grouped dilated convs, concatenated over `_which_dilations`
+    (branch d: nb_channels_in // d channels in `cardinality` groups that read the FIRST nb_channels_in // d channels)
+    -> LN(LReLU) -> Conv1x1(nb_channels_out) -> + y.
 
-    Runs one residual block through libcnf (`coupling_layer` machinery with a single block); `weights`
-    is the block's parameter dict (names as in coupling_layer.get_weights()['b'] with prefix 'rb0.').
-    Strided / projected shortcuts and dropout are never used by the reference model (M:1123-1130) and
-    are not built."""
+    The reference is a Keras graph builder: every call creates NEW layers initialised with `init`.  Here the block runs
+    through libcnf (`cnf_residual_block`, the launches a coupling layer issues for one of its blocks); `weights` is the
+    block's parameter dict {'ln1.gamma', 'ln1.beta', 'pw1.kernel', 'pw1.bias', 'ln2.*', 'gc.d<d>.g<j>.kernel/bias',
+    'ln3.*', 'pw2.kernel', 'pw2.bias'} (Keras shapes; the names `coupling_layer.get_weights()` uses after the 'rb<i>.'
+    prefix).  weights=None initialises a fresh block with `init`, like the reference.  Pass `weights={}` to receive the
+    freshly initialised parameters back in that dict.
+
+    Strided / projected shortcuts, dropout and a bottleneck width different from the block width are never used by the
+    reference model (M:1123-1130) and are not built; `ln_axis` must be -1 (the model's choice, M:1129)."""
+    from .conv_cINN_make_model import coupling_layer
     if tuple(_strides) != (1, 1) or _project_shortcut or do:
         raise NotImplementedError("only the configuration conv_cINN_make_model uses is built "
                                   "(strides (1,1), identity shortcut, no dropout; M:1123-1130)")
     if nb_channels_in != nb_channels_out:
         raise NotImplementedError("identity shortcut needs nb_channels_in == nb_channels_out (F:614-623)")
-    raise NotImplementedError("stand-alone residual blocks are not exposed yet; the block runs fused "
-                              "inside coupling_layer (see csrc/stnet_kernels.cu)")
+    if ln_axis != -1:
+        raise NotImplementedError("ln_axis must be -1 (whole-sample LayerNorm, F:350-360)")
+    ks = ksize if isinstance(ksize, int) else ksize[0]
+    if not isinstance(ksize, int) and ksize[0] != ksize[1]:
+        raise NotImplementedError("square kernels only")
+    y = require_cuda(y, "y")
+    if y.dim() != 4 or y.shape[3] != nb_channels_out:
+        raise ValueError(f"y: expected [B,h,w,{nb_channels_out}], got {tuple(y.shape)}")
+    B, h, w, _ = y.shape
+    # a checkerboard layer on a (2h, 2w, 1) tensor has the compressed shape (h, w, 2) and nk = num_kernels / 2 (M:420-423):
+    # its residual blocks are exactly this block for any h, w
+    layer = coupling_layer([2 * h, 2 * w, 1], 0, 1, cardinality, 2 * nb_channels_in, ks, init, LAYER_NORM=bool(ln),
+                           which_dilations=list(_which_dilations), device=y.device)
+    views = layer.weight_views()
+    block_names = [k for k in views['A'] if k.startswith('rb0.')]
+    if weights:
+        missing = [k[4:] for k in block_names if k[4:] not in weights]
+        if missing:
+            raise ValueError(f"dilated_residual_block: weights lack {missing}")
+        for k in block_names:
+            for net in ('A', 'b'):
+                src = torch.as_tensor(weights[k[4:]], dtype=torch.float32, device=y.device)
+                views[net][k].copy_(src.reshape(views[net][k].shape))
+    elif weights is not None:
+        for k in block_names:
+            weights[k[4:]] = views['A'][k].detach().cpu().numpy().copy()
+    return layer.residual_block(y, 0, net="A")
 
 
 # ---------------------------------------------------------------------------------------------------------------------

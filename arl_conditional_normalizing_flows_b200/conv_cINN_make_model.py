@@ -328,6 +328,29 @@ class coupling_layer(Layer):
                                     stream_ptr()))
         return A, b
 
+    def coupling_function(self):
+        """M:1076-1213: the two s/t networks of the layer as callables `(model_A, model_b)` on the compressed u1
+        [B,h,w,c1] -> [B,h,w,c2].  The reference builds and returns two Keras functional models here; the networks of
+        this layer already exist (flat parameter buffer + libcnf kernels), so the handles are returned, with
+        `.get_weights()` like the Keras models.  model_A includes the `w * tanh(.)` scaling layer (M:1198)."""
+        return self.model_A, self.model_b
+
+    def residual_block(self, x, block, net="both"):
+        """Residual block `block` (F:501-627) of this layer's networks on stand-alone activations.
+        x: [2,B,h,w,nk] (net A, net b) with net="both", or [B,h,w,nk] for net "A" / "b"."""
+        if net == "both":
+            x2 = require_cuda(x, "x")
+        else:
+            x1 = require_cuda(x, "x")
+            x2 = torch.stack([x1, x1]).contiguous()
+        if x2.dim() != 5:
+            raise ValueError(f"x: expected [2,B,h,w,nk] (or [B,h,w,nk] for one net), got {tuple(x.shape)}")
+        out = torch.empty_like(x2)
+        br = Borrowed()
+        check(lib.cnf_residual_block(self._h, int(block), br(x2), br(self.params), br(out),
+                                     br(self._workspace(x2.shape[1])), stream_ptr()))
+        return out if net == "both" else out[0 if net == "A" else 1]
+
     def A_wrapper(self, A_input):                            # M:452-461
         return self.model_A(A_input)
 

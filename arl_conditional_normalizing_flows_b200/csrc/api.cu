@@ -413,6 +413,25 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1c, const D
   return cuda_rc(run_coupling(c, P.p, v, MASK_DENSE, v, (int)B, HEAD_EMIT, nullptr, TA.p, TB.p, W.p, stream), "s/t networks");
 }
 
+int cnf_residual_block(const cnf_coupling* c, int block, const DLManagedTensor* x, const DLManagedTensor* params,
+                       DLManagedTensor* out, DLManagedTensor* workspace, void* stream) {
+  if (!c) return fail(CNF_ERR_ARG, "null coupling layer");
+  Ten X, P, O, W;
+  TRY(borrow(x, "x", 5, &X));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(out, "out", 5, &O));
+  TRY(borrow(workspace, "workspace", 1, &W, true));
+  if (block < 0 || block >= c->R) return fail(CNF_ERR_ARG, "block %d out of range (the layer has %d residual blocks)", block, c->R);
+  const int64_t B = X.shape[1];
+  for (const Ten* t : {&X, &O})
+    if (t->shape[0] != 2 || t->shape[1] != B || t->shape[2] != c->h || t->shape[3] != c->w || t->shape[4] != c->nk)
+      return fail(CNF_ERR_SHAPE, "x/out: expected shape [2,B,%d,%d,%d] (net A, net b)", c->h, c->w, c->nk);
+  if (P.numel < 2 * c->net_stride) return fail(CNF_ERR_SHAPE, "params: need %lld floats, got %lld", (long long)(2 * c->net_stride), (long long)P.numel);
+  if (W.bytes < cnf_coupling_workspace_bytes(c, B)) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)cnf_coupling_workspace_bytes(c, B), (long long)W.bytes);
+  if (B == 0) return CNF_OK;
+  return cuda_rc(run_residual_block(c, P.p, block, X.p, O.p, (int)B, W.p, stream), "residual block");
+}
+
 int cnf_measure_stage(const cnf_coupling* c, const DLManagedTensor* params, DLManagedTensor* workspace, int64_t batch,
                       int which, void* stream) {
   if (!c) return fail(CNF_ERR_ARG, "null coupling layer");
@@ -631,6 +650,25 @@ int cnf_toy_log_loss(const DLManagedTensor* xy, const DLManagedTensor* params, c
   if (A.shape[0] != B || Bt.shape[0] != B || F.shape[0] != 4) return fail(CNF_ERR_SHAPE, "ll_z/ll_y must be [B] and loss4 [4]");
   TRY(cnf_toy_call(xy, params, mask_indices, n, width, num_layers, -1, zy, logdet, stream));
   return cuda_rc(launch_toy_loss(Z.p, X.p, L.p, (int)B, x_d, lambda_y, A.p, Bt.p, F.p, stream), "toy loss");
+}
+
+int cnf_toy_loss_and_grad(const DLManagedTensor* xy, const DLManagedTensor* params, const int* mask_indices, int n, int width,
+                          int num_layers, int x_d, double lambda_y, DLManagedTensor* grads, DLManagedTensor* zy,
+                          DLManagedTensor* ll_z, DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
+                          void* stream) {
+  Ten X, P, G, Z;
+  TRY(borrow(xy, "xy", 2, &X));
+  TRY(borrow(params, "params", 1, &P));
+  TRY(borrow(grads, "grads", 1, &G));
+  TRY(borrow(zy, "zy", 2, &Z));
+  const int64_t need = cnf_toy_param_count(n, width, num_layers);
+  if (need <= 0) return fail(CNF_ERR_UNSUPPORTED, "toy configuration not built (width must be 8, 16, 32 or 64)");
+  if (P.numel < need || G.numel < need) return fail(CNF_ERR_SHAPE, "params/grads: need %lld floats", (long long)need);
+  if (X.p == Z.p) return fail(CNF_ERR_ARG, "zy must not alias xy");
+  TRY(cnf_toy_log_loss(xy, params, mask_indices, n, width, num_layers, x_d, lambda_y, zy, ll_z, ll_y, logdet, loss4, stream));
+  TRY(cuda_rc((int)cudaMemsetAsync(G.p, 0, sizeof(float) * need, (cudaStream_t)stream), "memset"));
+  return cuda_rc(launch_toy_grad(X.p, Z.p, P.p, G.p, mask_indices, n, width, num_layers, x_d, lambda_y, (int)X.shape[0], stream),
+                 "toy gradients");
 }
 
 }  // extern "C"

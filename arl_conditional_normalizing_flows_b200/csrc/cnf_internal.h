@@ -151,6 +151,8 @@ int launch_loss_grad(const float* zy, const float* xy, float* G, int64_t n, int 
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                 float gscale, void* stream);
 int read_tc3_clocks(long long* out, int n);
+int run_residual_block(const cnf_coupling* c, const float* params, int r, const float* Xin, float* Xout, int B, void* ws,
+                       void* stream);
 int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, void* ws, void* stream);
 int launch_copy(const float* src, float* dst, int64_t n, void* stream);
 int launch_logdet_finalize(const double* acc, float* out, int B, void* stream);
@@ -173,6 +175,8 @@ int launch_instance_noise(const float* x, float* out, long long n, double alpha,
                           unsigned long long offset, void* stream);
 int launch_toy(const float* u, const float* params, const int* mask_idx_host, int n_layers_c, int width,
                int num_layers, int direction, float* v, float* logdet, int B, void* stream);
+int launch_toy_grad(const float* xy, const float* zy, const float* params, float* grads, const int* mask_idx_host,
+                    int n_layers_c, int width, int num_layers, int x_d, double lambda_y, int B, void* stream);
 int launch_toy_loss(const float* zy, const float* xy, const float* logdet, int B, int x_d, double lambda_y,
                     float* ll_z, float* ll_y, float* loss4, void* stream);
 

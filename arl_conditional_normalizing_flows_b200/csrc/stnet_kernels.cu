@@ -1961,6 +1961,82 @@ int run_coupling(const cnf_coupling* c, const float* params, FlowView in_view, i
   return 0;
 }
 
+// (sum, sum of squares) of LReLU(x) per sample and net: the LayerNorm statistics a producing kernel would have left
+// behind (stand-alone residual block entry point).  x is [2][B][n]; stats [2][B][2] (overwritten).
+__global__ void __launch_bounds__(256) lrelu_stats_kernel(const float* __restrict__ x, long long n, int B, double* __restrict__ stats) {
+  __shared__ float red[64];
+  const int b = blockIdx.x, net = blockIdx.y;
+  const float* p = x + ((long long)net * B + b) * n;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float l = lrelu(p[i]);
+    s1 += l;
+    s2 = fmaf(l, l, s2);
+  }
+  double d1, d2;
+  block_sum2(s1, s2, red, d1, d2);
+  if (threadIdx.x == 0) {
+    stats[2 * ((long long)net * B + b)] = d1;
+    stats[2 * ((long long)net * B + b) + 1] = d2;
+  }
+}
+
+// One dilated residual block (F:501-627) of both nets on stand-alone activations: Xin, Xout are [2][B][hw][nk]
+// (net A first; Xout may alias Xin).  The same three launches run_coupling issues for block r.
+int run_residual_block(const cnf_coupling* c, const float* params, int r, const float* Xin, float* Xout, int B, void* ws,
+                       void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 0) return 0;
+  if (r < 0 || r >= c->R) return (int)cudaErrorInvalidValue;
+  CouplingWorkspace W = carve_ws(c, B, ws);
+  const int hw = c->hw(), nk = c->nk, cat = c->cat;
+  const long long slot = 2LL * B * 2;
+  const int n_ln = c->n_ln();
+  auto stats = [&](int i) -> double* { return n_ln ? W.stats + slot * i : nullptr; };
+  if (n_ln) {
+    CU_TRY(cudaMemsetAsync(W.stats, 0, sizeof(double) * slot * 4, st));
+    lrelu_stats_kernel<<<dim3(B, 2), 256, 0, st>>>(Xin, (long long)hw * nk, B, stats(0));
+    CU_TRY(cudaGetLastError());
+  }
+  const ResBlockLayout& L = c->rb[r];
+  {
+    GemmArgs a = {};
+    a.in = Xin; a.in_net_stride = (long long)B * hw * nk;
+    a.params = params; a.net_stride = c->net_stride; a.w_off = L.pw1_w; a.b_off = L.pw1_b;
+    a.g_off = L.ln1_g; a.be_off = L.ln1_b;
+    a.stats_in = stats(0); a.stats_out = stats(1);
+    a.out = W.Y1; a.out_net_stride = (long long)B * hw * nk;
+    a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln; a.paths = c->paths;
+    CU_TRY((cudaError_t)launch_pw(a, st));
+  }
+  {
+    GconvArgs a = {};
+    a.in = W.Y1; a.in_net_stride = (long long)B * hw * nk; a.Cin = nk;
+    a.out = W.Y2; a.out_net_stride = (long long)B * hw * cat; a.Cout = cat;
+    a.params = params; a.net_stride = c->net_stride; a.g_off = L.ln2_g; a.be_off = L.ln2_b;
+    a.stats_in = stats(1); a.stats_out = stats(2);
+    a.B = B; a.h = c->h; a.w = c->w; a.ln = c->ln; a.ks = c->ks; a.paths = c->paths;
+    a.n_br = (int)L.br.size();
+    for (int i = 0; i < a.n_br; ++i) {
+      const Branch& s = L.br[i];
+      a.br[i].dil = s.dil; a.br[i].groups = s.groups; a.br[i].gin = s.gin; a.br[i].gout = s.gout;
+      a.br[i].out_off = s.out_off; a.br[i].w_off = s.w_off; a.br[i].b_off = s.b_off;
+    }
+    CU_TRY((cudaError_t)launch_gconv(a, st));
+  }
+  {
+    GemmArgs a = {};
+    a.in = W.Y2; a.in_net_stride = (long long)B * hw * cat;
+    a.params = params; a.net_stride = c->net_stride; a.w_off = L.pw2_w; a.b_off = L.pw2_b;
+    a.g_off = L.ln3_g; a.be_off = L.ln3_b;
+    a.stats_in = stats(2); a.stats_out = stats(3);
+    a.out = Xout; a.res = Xin; a.out_net_stride = (long long)B * hw * nk;
+    a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln; a.paths = c->paths;
+    CU_TRY((cudaError_t)launch_pw(a, st));
+  }
+  return 0;
+}
+
 int read_tc3_clocks(long long* out, int n) {
   CU_TRY(cudaDeviceSynchronize());
   return (int)cudaMemcpyFromSymbol(out, g_tc3_clk, sizeof(long long) * std::min(n, 8192));

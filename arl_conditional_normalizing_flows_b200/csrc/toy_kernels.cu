@@ -170,6 +170,300 @@ int launch_toy(const float* u, const float* params, const int* mask_idx_host, in
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Training: gradient of the toy log_loss w.r.t. every Dense kernel / bias (the tf.GradientTape block of
+// cINN_affine.train_step, T:453-482).  One thread owns one sample, one CTA NS samples.  The backward pass walks the
+// coupling layers in the reverse of the forward order and needs NO stored activations: a coupling layer leaves u1
+// untouched, so its MLPs are re-evaluated from v1 and the layer input is recovered with the inverse law
+// u2 = (v2 - b) / exp(A) (T:369-375) - activation-free backward via invertibility.  Per net: forward MLP with the
+// hidden activations parked in shared memory, then delta back-propagation; every weight gradient dW_l = H_{l-1}^T D_l is
+// a CTA-wide [I x NS] x [NS x I] product from those shared tiles, added to the global buffer with one atomic per entry
+// and CTA.
+// ------------------------------------------------------------------------------------------------------------------
+struct ToyGradArgs {
+  const float* xy;
+  const float* zy;
+  const float* params;
+  float* grads;      // layout of params, zero-initialised by the caller
+  int B, n_layers_c, num_layers, x_d;
+  float lambda_y, inv_B;
+  unsigned char order[256];
+};
+
+__device__ __forceinline__ float lrelu_grad(float h) { return h > 0.f ? 1.f : CNF_LRELU_SLOPE; }   // sign(h) == sign(pre)
+
+// forward MLP of one net for this thread's sample; hidden activations h_0..h_L -> Hs[l][tid][.] (row stride I + 4)
+template <int I>
+__device__ __forceinline__ void toy_mlp_store(const float* __restrict__ P, int num_layers, int d1, int d2, const float* in,
+                                              float* __restrict__ Hs, int ns, float* out) {
+  constexpr int LD = I + 4;
+  float h[I], g[I];
+  const float* W0 = P;
+  const float* b0 = P + 2 * I;
+#pragma unroll
+  for (int o = 0; o < I; ++o) {
+    float a = b0[o];
+    a = fmaf(in[0], W0[o], a);
+    if (d1 > 1) a = fmaf(in[1], W0[I + o], a);
+    h[o] = lrelu(a);
+  }
+  float* row = Hs + (long long)threadIdx.x * LD;
+#pragma unroll
+  for (int o = 0; o < I; o += 4) st4(row + o, make_float4(h[o], h[o + 1], h[o + 2], h[o + 3]));
+  const float* Pl = P + 3 * I;
+  for (int l = 0; l < num_layers; ++l) {
+    const float* W = Pl;
+    const float* bb = Pl + I * I;
+#pragma unroll
+    for (int o = 0; o < I; ++o) g[o] = bb[o];
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+#pragma unroll
+      for (int o4 = 0; o4 < I; o4 += 4) {
+        const float4 w = ld4(W + i * I + o4);
+        g[o4] = fmaf(h[i], w.x, g[o4]);
+        g[o4 + 1] = fmaf(h[i], w.y, g[o4 + 1]);
+        g[o4 + 2] = fmaf(h[i], w.z, g[o4 + 2]);
+        g[o4 + 3] = fmaf(h[i], w.w, g[o4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < I; ++o) h[o] = lrelu(g[o]);
+    row = Hs + ((long long)(l + 1) * ns + threadIdx.x) * LD;
+#pragma unroll
+    for (int o = 0; o < I; o += 4) st4(row + o, make_float4(h[o], h[o + 1], h[o + 2], h[o + 3]));
+    Pl += I * I + I;
+  }
+  const float* WL = Pl;
+  const float* bL = Pl + 2 * I;
+  float o0 = bL[0], o1 = bL[1];
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    o0 = fmaf(h[i], WL[2 * i], o0);
+    o1 = fmaf(h[i], WL[2 * i + 1], o1);
+  }
+  out[0] = o0;
+  out[1] = d2 > 1 ? o1 : 0.f;
+}
+
+// backward of one net: dout[2] = dL/d(output) of this thread's sample (0 for absent outputs / padded samples).
+// Adds the CTA's weight-gradient contributions to G (global, layout of P) and returns din[2] = dL/d(input).
+template <int I>
+__device__ __forceinline__ void toy_mlp_backward(const float* __restrict__ P, float* __restrict__ G, int num_layers, int d1,
+                                                 const float* in, const float* dout, const float* __restrict__ Hs,
+                                                 float* __restrict__ Ds, float* __restrict__ Sm, int ns, float* din) {
+  constexpr int LD = I + 4;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long long offL = 3LL * I + (long long)num_layers * (I * I + I);   // WL, bL
+  float d[I];
+  // ---- output layer: WL [I][2], bL [2]
+  {
+    const float* WL = P + offL;
+    const float* hrow = Hs + ((long long)num_layers * ns + tid) * LD;
+#pragma unroll
+    for (int i = 0; i < I; ++i) d[i] = (WL[2 * i] * dout[0] + WL[2 * i + 1] * dout[1]) * lrelu_grad(hrow[i]);
+    Sm[2 * tid] = dout[0];
+    Sm[2 * tid + 1] = dout[1];
+    __syncthreads();
+    for (int e = tid; e < 2 * I + 2; e += nt) {          // dWL[i][c] = sum_s h_L[s][i] dout[s][c];  dbL[c] = sum_s dout[s][c]
+      float acc = 0.f;
+      if (e < 2 * I) {
+        const int i = e >> 1, c = e & 1;
+        const float* hcol = Hs + (long long)num_layers * ns * LD + i;
+        for (int s = 0; s < ns; ++s) acc = fmaf(hcol[(long long)s * LD], Sm[2 * s + c], acc);
+      } else {
+        const int c = e - 2 * I;
+        for (int s = 0; s < ns; ++s) acc += Sm[2 * s + c];
+      }
+      atomicAdd(G + offL + e, acc);
+    }
+    __syncthreads();
+  }
+  // ---- hidden layers l = L..1: W_l [I][I] maps h_{l-1} -> pre_l
+  for (int l = num_layers; l >= 1; --l) {
+    const long long off = 3LL * I + (long long)(l - 1) * (I * I + I);
+    float* drow = Ds + (long long)tid * LD;
+#pragma unroll
+    for (int o = 0; o < I; o += 4) st4(drow + o, make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]));
+    // delta_{l-1}[i] = (sum_o W_l[i][o] delta_l[o]) * lrelu'(h_{l-1}[i])
+    const float* W = P + off;
+    const float* hrow = Hs + ((long long)(l - 1) * ns + tid) * LD;
+    float dn[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int o4 = 0; o4 < I; o4 += 4) {
+        const float4 w = ld4(W + i * I + o4);
+        acc = fmaf(w.x, d[o4], fmaf(w.y, d[o4 + 1], fmaf(w.z, d[o4 + 2], fmaf(w.w, d[o4 + 3], acc))));
+      }
+      dn[i] = acc * lrelu_grad(hrow[i]);
+    }
+    __syncthreads();
+    // dW_l[i][o..o+3] = sum_s h_{l-1}[s][i] delta_l[s][o..o+3];  db_l[o] = sum_s delta_l[s][o]
+    const float* Hl = Hs + (long long)(l - 1) * ns * LD;
+    for (int e = tid; e < I * I / 4 + I; e += nt) {
+      if (e < I * I / 4) {
+        const int i = e / (I / 4), o4 = (e - i * (I / 4)) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < ns; ++s) {
+          const float hv = Hl[(long long)s * LD + i];
+          const float4 dv = ld4(Ds + (long long)s * LD + o4);
+          acc.x = fmaf(hv, dv.x, acc.x); acc.y = fmaf(hv, dv.y, acc.y);
+          acc.z = fmaf(hv, dv.z, acc.z); acc.w = fmaf(hv, dv.w, acc.w);
+        }
+        float* gp = G + off + i * I + o4;
+        atomicAdd(gp, acc.x); atomicAdd(gp + 1, acc.y); atomicAdd(gp + 2, acc.z); atomicAdd(gp + 3, acc.w);
+      } else {
+        const int o = e - I * I / 4;
+        float acc = 0.f;
+        for (int s = 0; s < ns; ++s) acc += Ds[(long long)s * LD + o];
+        atomicAdd(G + off + I * I + o, acc);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < I; ++i) d[i] = dn[i];
+  }
+  // ---- first layer: W0 [2][I] (rows >= d1 unused), b0 [I]
+  {
+    float* drow = Ds + (long long)tid * LD;
+#pragma unroll
+    for (int o = 0; o < I; o += 4) st4(drow + o, make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]));
+    Sm[2 * tid] = in[0];
+    Sm[2 * tid + 1] = d1 > 1 ? in[1] : 0.f;
+    const float* W0 = P;
+    float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+    for (int o = 0; o < I; ++o) {
+      g0 = fmaf(W0[o], d[o], g0);
+      g1 = fmaf(W0[I + o], d[o], g1);
+    }
+    din[0] = g0;
+    din[1] = d1 > 1 ? g1 : 0.f;
+    __syncthreads();
+    for (int e = tid; e < 3 * I; e += nt) {              // dW0[r][o] = sum_s in[s][r] delta_0[s][o];  db0[o] = sum_s delta_0[s][o]
+      const int r = e / I, o = e - r * I;
+      float acc = 0.f;
+      if (r < 2) {
+        if (r < d1)
+          for (int s = 0; s < ns; ++s) acc = fmaf(Sm[2 * s + r], Ds[(long long)s * LD + o], acc);
+      } else {
+        for (int s = 0; s < ns; ++s) acc += Ds[(long long)s * LD + o];
+      }
+      if (r >= 2 || r < d1) atomicAdd(G + (r < 2 ? r * I + o : 2 * I + o), acc);
+    }
+    __syncthreads();
+  }
+}
+
+template <int I>
+__global__ void __launch_bounds__(128) toy_grad_kernel(const ToyGradArgs a) {
+  extern __shared__ __align__(16) float sp[];
+  constexpr int LD = I + 4;
+  const int ns = blockDim.x;
+  const long long net_sz = toy_net_size(I, a.num_layers);
+  float* Wn = sp;                                              // one net's parameters
+  float* Hs = Wn + ((net_sz + 3) & ~3LL);                      // [L + 1][ns][LD]
+  float* Ds = Hs + (long long)(a.num_layers + 1) * ns * LD;    // [ns][LD]
+  float* Sm = Ds + (long long)ns * LD;                         // [ns][2]
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = s < a.B;
+  float x[3] = {0.f, 0.f, 0.f}, g[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      x[c] = a.zy[3 * s + c];
+      if (c < a.x_d) {
+        g[c] = x[c] * a.inv_B;                                 // d/dz of -mean(-z^2 / 2)
+      } else {
+        const float df = x[c] - a.xy[3 * s + c];
+        g[c] = a.lambda_y * a.inv_B * (df > 0.f ? 1.f : df < 0.f ? -1.f : 0.f);   // d/dy of mean(lambda |y - y'|)
+      }
+    }
+  }
+  const float g_ld = valid ? -a.inv_B : 0.f;                   // d/d(log_detJ) of -mean(log_detJ)
+  for (int i = 0; i < a.n_layers_c; ++i) {                     // reverse of the forward order n-1..0 (T:295)
+    const int j = a.order[i];
+    const int mk = j % 6;
+    const int d1 = mk < 3 ? 1 : 2, d2 = 3 - d1;
+    const float* Pj = a.params + 2 * net_sz * j;
+    float* Gj = a.grads + 2 * net_sz * j;
+    float v1[2] = {x[c_m1[mk][0]], x[c_m1[mk][1]]};
+    float v2[2] = {x[c_m2[mk][0]], x[c_m2[mk][1]]};
+    float g2[2] = {g[c_m2[mk][0]], d2 > 1 ? g[c_m2[mk][1]] : 0.f};
+    float bb[2], raw[2], din_b[2], din_A[2];
+    // ---- net b: t = b(u1); dL/db = dL/dv2
+    __syncthreads();
+    for (long long t = threadIdx.x; t < net_sz / 4; t += blockDim.x) st4(Wn + 4 * t, ld4(Pj + net_sz + 4 * t));
+    __syncthreads();
+    toy_mlp_store<I>(Wn, a.num_layers, d1, d2, v1, Hs, ns, bb);
+    __syncthreads();
+    toy_mlp_backward<I>(Wn, Gj + net_sz, a.num_layers, d1, v1, g2, Hs, Ds, Sm, ns, din_b);
+    // ---- net A: A = tanh(raw); u2 = (v2 - b) / exp(A); dL/dA = dL/dv2 exp(A) u2 + dL/dlogdet
+    for (long long t = threadIdx.x; t < net_sz / 4; t += blockDim.x) st4(Wn + 4 * t, ld4(Pj + 4 * t));
+    __syncthreads();
+    toy_mlp_store<I>(Wn, a.num_layers, d1, d2, v1, Hs, ns, raw);
+    __syncthreads();
+    float dA[2], u2[2], e[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float A = tanhf(raw[c]);
+      e[c] = (c < d2) ? expf(A) : 1.f;
+      u2[c] = __fmul_rn(__frcp_rn(e[c]), __fsub_rn(v2[c], bb[c]));
+      dA[c] = (c < d2) ? (g2[c] * e[c] * u2[c] + g_ld) * (1.f - A * A) : 0.f;
+    }
+    toy_mlp_backward<I>(Wn, Gj, a.num_layers, d1, v1, dA, Hs, Ds, Sm, ns, din_A);
+    // ---- state and gradient in front of this layer
+    x[c_m2[mk][0]] = u2[0];
+    g[c_m2[mk][0]] = g2[0] * e[0];
+    if (d2 > 1) {
+      x[c_m2[mk][1]] = u2[1];
+      g[c_m2[mk][1]] = g2[1] * e[1];
+    }
+    g[c_m1[mk][0]] += din_b[0] + din_A[0];
+    if (d1 > 1) g[c_m1[mk][1]] += din_b[1] + din_A[1];
+  }
+}
+
+int launch_toy_grad(const float* xy, const float* zy, const float* params, float* grads, const int* mask_idx_host,
+                    int n_layers_c, int width, int num_layers, int x_d, double lambda_y, int B, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_layers_c > 256) return (int)cudaErrorInvalidValue;
+  if (B <= 0) return 0;
+  ToyGradArgs a;
+  a.xy = xy; a.zy = zy; a.params = params; a.grads = grads;
+  a.B = B; a.n_layers_c = n_layers_c; a.num_layers = num_layers; a.x_d = x_d;
+  a.lambda_y = (float)lambda_y; a.inv_B = 1.0f / (float)B;
+  for (int i = 0; i < n_layers_c; ++i) a.order[i] = (unsigned char)mask_idx_host[i];
+  const long long net_sz = toy_net_size(width, num_layers);
+  // samples per CTA: as many (128, 64, 32) as keep one net's weights + the activation tiles inside shared memory
+  int ns = 128;
+  size_t smem = 0;
+  for (; ns >= 32; ns >>= 1) {
+    smem = (size_t)(((net_sz + 3) & ~3LL) + (long long)(num_layers + 2) * ns * (width + 4) + 2LL * ns) * sizeof(float);
+    if (smem <= 227 * 1024) break;
+  }
+  if (ns < 32) return (int)cudaErrorInvalidConfiguration;
+  const int grid = (B + ns - 1) / ns;
+#define TOY_GCASE(I)                                                                                       \
+  case I: {                                                                                                \
+    CU_TRY(cudaFuncSetAttribute(toy_grad_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                (int)(smem > 48 * 1024 ? smem : 48 * 1024)));                              \
+    toy_grad_kernel<I><<<grid, ns, smem, st>>>(a);                                                         \
+    break;                                                                                                 \
+  }
+  switch (width) {
+    TOY_GCASE(8)
+    TOY_GCASE(16)
+    TOY_GCASE(32)
+    TOY_GCASE(64)
+    default: return (int)cudaErrorInvalidConfiguration;
+  }
+#undef TOY_GCASE
+  return (int)cudaGetLastError();
+}
+
 // T:436-451: ll_z = log N(z; 0, I_{x_d}) per sample, ll_y = -lambda_y sum |y - y'|,
 // loss = -mean(ll_z + ll_y + log_detJ), plus the three component means.
 __global__ void __launch_bounds__(256) toy_loss_kernel(const float* __restrict__ zy, const float* __restrict__ xy,

@@ -192,6 +192,13 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1_compresse
                       const DLManagedTensor* params, DLManagedTensor* A, DLManagedTensor* b,
                       DLManagedTensor* workspace, void* stream);
 
+/* dilated_residual_block (F:501-627, with grouped_convolution F:364-413 and add_common_layers F:330-362) number `block`
+ * of the layer's two s/t networks on stand-alone activations: x, out are [2,B,h,w,nk] (net A first; out may alias x);
+ * LN -> 1x1 -> LN -> grouped dilated 3x3 (concat over dilations) -> LN -> 1x1 -> + x, the launches the layer itself
+ * issues for that block.  workspace: cnf_coupling_workspace_bytes(c, B). */
+int cnf_residual_block(const cnf_coupling* c, int block, const DLManagedTensor* x, const DLManagedTensor* params,
+                       DLManagedTensor* out, DLManagedTensor* workspace, void* stream);
+
 /* fused standalone coupling law + mask addressing + per-sample log-det (M:1215-1253, M:1307-1326):
  * v = mask(u,m,False) + decompress(exp(s)*u2c + t, m_bar)   (inverse: (u2c - t) / exp(s)).
  * u, v are [B,H,W,D]; s, t are [B,h,w,c2] in the compressed layout of the complement mask;
@@ -244,6 +251,14 @@ int cnf_toy_log_loss(const DLManagedTensor* xy, const DLManagedTensor* params, c
                      int num_coupling_layers, int intermediate_dims, int num_layers, int x_d,
                      double lambda_y, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
                      DLManagedTensor* logdet, DLManagedTensor* loss4, void* stream);
+
+/* the tf.GradientTape block of cINN_affine.train_step (T:453-482): cnf_toy_log_loss plus d loss4[0] / d params into
+ * grads (layout of params, overwritten).  The backward pass stores no activations: every coupling layer's input is
+ * recovered from its output with the inverse law (T:369-375) and its MLPs are re-evaluated. */
+int cnf_toy_loss_and_grad(const DLManagedTensor* xy, const DLManagedTensor* params, const int* mask_indices,
+                          int num_coupling_layers, int intermediate_dims, int num_layers, int x_d, double lambda_y,
+                          DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                          DLManagedTensor* logdet, DLManagedTensor* loss4, void* stream);
 
 #ifdef __cplusplus
 }
