@@ -45,6 +45,25 @@ def main():
                 for k, v in w[net].items():
                     out[f"w.{i}.{net}.{k}"] = np.asarray(v, np.float32)
         np.savez_compressed(os.path.join(OUT, f"flow_{name}.npz"), **out)
+    # BASELINE config 2 at its full batch (256): a digest instead of the full tensors (per-sample scalars, every 7th
+    # element of zy / of the samples, per-sample fp64 sums).  Inputs and weights are regenerated from their seeds.
+    cfg2 = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+                num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
+    o = FlowOracle(**cfg2, dtype=torch.float64)
+    o.set_weights(init_weights(o.plan, 'rand', seed=0))
+    B = 256
+    x = synth_inputs('cfg2', B, seed=0).astype(np.float64)
+    four, ps = o.log_loss(x)
+    z = synth_inputs('noise:28x28x2', B, seed=1).astype(np.float64)
+    z[..., 1:] = x[..., 1:]
+    xs = o.call(z, -1)
+    flat = lambda a: a.reshape(B, -1)
+    np.savez_compressed(os.path.join(OUT, "cfg2_b256_digest.npz"), config=np.array(json.dumps(cfg2)), weights_seed=0,
+                        xy_seed=0, z_seed=1, stride=7, loss4=np.array(four), logdet=ps['logdet'], ll_z=ps['ll_z'],
+                        ll_y=ps['ll_y'], zy_strided=flat(ps['zy'])[:, ::7].astype(np.float32),
+                        zy_sum=flat(ps['zy']).sum(1), zy_abs=np.abs(flat(ps['zy'])).sum(1),
+                        xs_strided=flat(xs)[:, ::7].astype(np.float32), xs_sum=flat(xs).sum(1),
+                        xs_abs=np.abs(flat(xs)).sum(1))
     # toy
     n, width, nl = 12, 16, 2
     W = toy_init_weights(n, width, nl, seed=5, scale=1.0)

@@ -71,3 +71,24 @@ def test_cuda_toy_matches_golden():
     np.testing.assert_allclose(m.last_per_sample['zy'].cpu().numpy(), d["zy"], rtol=1e-4, atol=1e-5)
     inv, _ = m(x, 1)
     np.testing.assert_allclose(inv.cpu().numpy(), d["inv"], rtol=1e-4, atol=1e-5)
+
+
+def test_cfg2_full_batch_digest_is_what_the_oracle_computes():
+    """tests/golden/cfg2_b256_digest.npz (config 2, batch 256): the oracle reproduces the first samples of the digest (every
+    op is per-sample, so a sub-batch gives the same per-sample numbers)."""
+    import json
+    import os
+    import torch
+    from oracle.flow_torch import FlowOracle
+    from oracle.weights import init_weights, synth_inputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_b256_digest.npz"))
+    cfg = json.loads(str(g['config']))
+    o = FlowOracle(**cfg, dtype=torch.float64)
+    o.set_weights(init_weights(o.plan, 'rand', seed=int(g['weights_seed'])))
+    n = 4
+    x = synth_inputs('cfg2', 256, seed=int(g['xy_seed'])).astype(np.float64)[:n]
+    _, ps = o.log_loss(x)
+    np.testing.assert_allclose(ps['logdet'], g['logdet'][:n], rtol=1e-10)
+    np.testing.assert_allclose(ps['ll_z'], g['ll_z'][:n], rtol=1e-10)
+    np.testing.assert_allclose(ps['zy'].reshape(n, -1)[:, ::int(g['stride'])], g['zy_strided'][:n], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ps['zy'].reshape(n, -1).sum(1), g['zy_sum'][:n], rtol=1e-10)

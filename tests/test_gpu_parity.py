@@ -25,6 +25,13 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def assert_close_elementwise(a, b, rtol=RTOL, what=""):
+    """element-wise gate next to the max-norm one: |a - b| <= rtol |b| + rtol rms(b) for EVERY element (the absolute floor
+    is the tensor's rms, not its maximum, so small entries are held to a small error too)"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * float(np.sqrt(np.mean(b * b))), err_msg=what)
+
+
 @pytest.fixture(scope="module")
 def dev():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
@@ -218,6 +225,7 @@ def test_flow_forward_inverse_loss_vs_oracle(dev, name, cfg, B, kind):
 
     zy, ld = m(xt, 1)
     assert rel(zy.cpu().numpy(), ps['zy']) < RTOL
+    assert_close_elementwise(zy.cpu().numpy(), ps['zy'], what="zy")
     ld_ps = m.last_logdet_per_sample.cpu().numpy()
     np.testing.assert_allclose(ld_ps, ps['logdet'], rtol=RTOL, atol=RTOL * np.abs(ps['logdet']).mean())
     np.testing.assert_allclose(float(ld), ps['logdet'].mean(), rtol=RTOL, atol=RTOL * np.abs(ps['logdet']).mean())
@@ -241,6 +249,7 @@ def test_flow_forward_inverse_loss_vs_oracle(dev, name, cfg, B, kind):
     xs_want = o.call(z.astype(np.float64), -1)
     xs = m(torch.from_numpy(z).to(dev), -1)
     assert rel(xs.cpu().numpy(), xs_want) < RTOL
+    assert_close_elementwise(xs.cpu().numpy(), xs_want, what="samples")
     # default direction is -1 (M:1725)
     assert torch.equal(m(torch.from_numpy(z).to(dev)), xs)
 
@@ -331,6 +340,40 @@ def test_flow_layerwise_equals_fused_call(dev):
     for layer in reversed(m.layers_list):
         vu, zy = layer.backward(vu, zy)
     assert torch.equal(vu, m(fused, -1))
+
+
+def test_cfg2_full_batch_against_the_fp64_oracle(dev):
+    """BASELINE config 2 at its FULL batch (256) against the fp64 oracle: tests/golden/cfg2_b256_digest.npz
+    (oracle/make_golden.py) holds the four loss scalars, every per-sample log-det / ll_z / ll_y, every 7th element of zy
+    and of the samples drawn from a fixed latent, and per-sample fp64 sums of both tensors."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_b256_digest.npz"))
+    cfg = json.loads(str(g['config']))
+    m, _ = mk(cfg, 'rand', seed=int(g['weights_seed']), dtype=torch.float32)
+    B, stride = 256, int(g['stride'])
+    x = synth_inputs('cfg2', B, seed=int(g['xy_seed']))
+    four = [float(t) for t in m.log_loss(torch.from_numpy(x).to(dev))]
+    np.testing.assert_allclose(four, g['loss4'], rtol=RTOL)
+    ps = m.last_per_sample
+    for k in ('logdet', 'll_z', 'll_y'):
+        np.testing.assert_allclose(ps[k].cpu().numpy(), g[k], rtol=RTOL, atol=RTOL * np.abs(g[k]).mean(), err_msg=k)
+    zy = ps['zy'].cpu().numpy().reshape(B, -1).astype(np.float64)
+    assert rel(zy[:, ::stride], g['zy_strided']) < RTOL
+    assert_close_elementwise(zy[:, ::stride], g['zy_strided'], what="zy")
+    np.testing.assert_allclose(zy.sum(1), g['zy_sum'], rtol=RTOL, atol=RTOL * g['zy_abs'].mean())
+    z = synth_inputs('noise:28x28x2', B, seed=int(g['z_seed']))
+    z[..., 1:] = x[..., 1:]
+    xs = m(torch.from_numpy(z).to(dev), -1).cpu().numpy().reshape(B, -1).astype(np.float64)
+    assert rel(xs[:, ::stride], g['xs_strided']) < RTOL
+    assert_close_elementwise(xs[:, ::stride], g['xs_strided'], what="samples")
+    np.testing.assert_allclose(xs.sum(1), g['xs_sum'], rtol=RTOL, atol=RTOL * g['xs_abs'].mean())
+    # the same on the layer-per-kernel path
+    m.set_fusion(0)
+    four0 = [float(t) for t in m.log_loss(torch.from_numpy(x).to(dev))]
+    np.testing.assert_allclose(four0, g['loss4'], rtol=RTOL)
+    np.testing.assert_allclose(m.last_per_sample['logdet'].cpu().numpy(), g['logdet'], rtol=RTOL,
+                               atol=RTOL * np.abs(g['logdet']).mean())
 
 
 def test_full_size_roundtrip_cfg2(dev):

@@ -15,12 +15,18 @@ kind = sys.argv[1] if len(sys.argv) > 1 else 'init'
 layers = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 and sys.argv[2] != '-' else None
 cfgname = sys.argv[3] if len(sys.argv) > 3 else 'cfg2'
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-cfg = CFG2_R1 if cfgname == 'cfg2' else ONE
-m = cFlow(**cfg, device='cuda:0')
-o = FlowOracle(**cfg, dtype=torch.float64)
+CFG2_FULL = dict(CFG2_R1, ResNeXt_block_list=[3] * 4)
+ONE3 = dict(ONE, ResNeXt_block_list=[3])
+ONE2 = dict(ONE, ResNeXt_block_list=[2])
+cfg = {'cfg2': CFG2_R1, 'cfg2full': CFG2_FULL, 'one': ONE, 'one3': ONE3, 'one2': ONE2}[cfgname]
+lam = float(os.environ.get('LAMBDA_Y', 100))
+m = cFlow(**cfg, lambda_y=lam, device='cuda:0')
+o = FlowOracle(**cfg, lambda_y=lam, dtype=torch.float64)
 W = init_weights(o.plan, kind, seed=1)
 o.set_weights(W); m.set_weights(W)
-xy = synth_inputs('cfg2', B, seed=0) if cfgname == 'cfg2' else synth_inputs('noise:14x14x4', B, seed=0)
+xy = synth_inputs('cfg2', B, seed=0) if cfgname.startswith('cfg2') else synth_inputs('noise:14x14x4', B, seed=0)
+if os.environ.get('PERTURB'):
+    xy = (xy + float(os.environ['PERTURB']) * np.random.default_rng(9).standard_normal(xy.shape)).astype(np.float32)
 f64, g64 = loss_and_grads(o, xy.astype(np.float64))
 f32, g32 = loss_and_grads(o, xy, dtype=torch.float32)
 four, _ = m.loss_and_grad(torch.from_numpy(xy).cuda())
@@ -34,8 +40,14 @@ for li in range(len(g64)):
             b = np.asarray(g32[li][net][k], np.float64).reshape(np.shape(ref))
             s = max(np.abs(ref).max(), 1e-30)
             rows.append((np.abs(a - ref).max() / s, np.abs(b - ref).max() / s, li, net, k, s))
+import collections
+per = collections.defaultdict(float)
+for r in rows:
+    per[(r[2], r[3])] = max(per[(r[2], r[3])], r[0])
+print('max gpu_err per (layer, net):', {k: float('%.1e' % v) for k, v in sorted(per.items())})
 rows.sort(reverse=True)
-for r in rows[:12]:
+print('tensors with gpu_err > 2e-3:', sum(r[0] > 2e-3 for r in rows), ' with fp32 autograd err > 2e-3:', sum(r[1] > 2e-3 for r in rows), 'of', len(rows))
+for r in rows[:25]:
     print("gpu_err %.2e  fp32_err %.2e  L%d %s %-22s scale %.3e" % r)
 if layers:
     for r in sorted(rows, key=lambda r: (r[2], r[3], r[4])):
