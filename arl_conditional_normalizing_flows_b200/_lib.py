@@ -90,6 +90,7 @@ def _load():
         "cnf_coupling_set_fusion": (I, [P, I]),
         "cnf_plan_set_kernel_paths": (I, [P, I]),
         "cnf_coupling_set_kernel_paths": (I, [P, I]),
+        "cnf_coupling_resident_eligible": (I, [P]),
         "cnf_flow_forward": (I, [P, P, P, P, P, P, V]),
         "cnf_flow_inverse": (I, [P, P, P, P, P, V]),
         "cnf_flow_log_loss": (I, [P, P, P, P, P, P, P, P, P, V]),

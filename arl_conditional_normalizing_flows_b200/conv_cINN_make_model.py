@@ -286,6 +286,25 @@ class coupling_layer(Layer):
         return {net: {k: v.detach().cpu().numpy().copy() for k, v in d.items()}
                 for net, d in self.weight_views().items()}
 
+    def randomize_weights(self, generator=None):
+        """"Trained-like" random state for benchmarks and stress tests (no reference counterpart; SURVEY 8d W-rand): kernels
+        N(0, 1/fan_in), biases and beta N(0, 0.1), gamma and the tanh scale U[0.5, 1.5], drawn on the device."""
+        dev = self.params.device
+        for net, d in self.weight_views().items():
+            for name, v in d.items():
+                role = name.rsplit('.', 1)[-1]
+                if role == 'kernel':
+                    fan_in = int(np.prod(v.shape[:-1]))
+                    v.copy_(torch.randn(v.shape, device=dev, generator=generator) / math.sqrt(fan_in))
+                elif role == 'gamma' or name == 'tanh_scale':
+                    v.copy_(0.5 + torch.rand(v.shape, device=dev, generator=generator))
+                else:
+                    v.copy_(0.1 * torch.randn(v.shape, device=dev, generator=generator))
+
+    def resident_kernel_eligible(self):
+        """True iff inference runs this layer as ONE activation-resident launch (csrc/fused_kernels.cu)."""
+        return bool(lib.cnf_coupling_resident_eligible(self._h))
+
     def set_weights(self, weights):
         names = {net: set(d) for net, d in self.weight_views().items()}
         for net in ("A", "b"):
@@ -552,6 +571,17 @@ class cFlow:
 
     def compile(self, optimizer=None):
         self.optimizer = optimizer
+
+    def randomize_weights(self, seed=0):
+        """"Trained-like" random weights for every coupling layer (see coupling_layer.randomize_weights)."""
+        g = torch.Generator(device=self.params.device)
+        g.manual_seed(int(seed))
+        for layer in self.coupling_layers:
+            layer.randomize_weights(g)
+
+    def launches_per_pass(self):
+        """kernel launches of one pass of the flow (forward or inverse) through the coupling layers"""
+        return sum(1 if l.resident_kernel_eligible() else 2 + 3 * l._info.R for l in self.coupling_layers)
 
     def set_fusion(self, enable):
         """Inference path selection for every coupling layer (see coupling_layer.set_fusion)."""

@@ -413,6 +413,12 @@ int cnf_coupling_nets(const cnf_coupling* c, const DLManagedTensor* u1c, const D
   return cuda_rc(run_coupling(c, P.p, v, MASK_DENSE, v, (int)B, HEAD_EMIT, nullptr, TA.p, TB.p, W.p, stream), "s/t networks");
 }
 
+int cnf_coupling_resident_eligible(const cnf_coupling* c) {
+  if (!c || (c->paths & CNF_PATH_NO_RESIDENT)) return 0;
+  FlowView v = make_view(nullptr, c->H, c->W, c->D, 0);
+  return launch_fused_coupling(c, nullptr, v, c->mask, v, 1, HEAD_FWD, nullptr, nullptr, nullptr, true) == 0 ? 1 : 0;
+}
+
 int cnf_residual_block(const cnf_coupling* c, int block, const DLManagedTensor* x, const DLManagedTensor* params,
                        DLManagedTensor* out, DLManagedTensor* workspace, void* stream) {
   if (!c) return fail(CNF_ERR_ARG, "null coupling layer");

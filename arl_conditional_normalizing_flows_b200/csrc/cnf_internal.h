@@ -130,7 +130,7 @@ int64_t coupling_bwd_scratch_bytes(const cnf_coupling* c, int64_t B);
 // fused_kernels.cu: one launch per coupling layer, s/t-net activations resident in shared memory (inference only).
 // Returns -1 when the layer does not fit that kernel (never a cudaError value), else a cudaError as int.
 int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
-                          int B, int mode, double* logdet_acc, void* ws, void* stream);
+                          int B, int mode, double* logdet_acc, void* ws, void* stream, bool dry_run = false);
 
 int64_t coupling_ws_bytes(const cnf_coupling* c, int64_t B);
 CouplingWorkspace carve_ws(const cnf_coupling* c, int64_t B, void* ws);

@@ -752,7 +752,7 @@ static bool fz_matches(const cnf_coupling* c) {
 
 // CNF_NOT_ELIGIBLE: this layer is not covered by the activation-resident kernel (the caller runs the layer-per-kernel path)
 int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView in_view, int in_mask, FlowView out_view,
-                          int B, int mode, double* logdet_acc, void* ws, void* stream) {
+                          int B, int mode, double* logdet_acc, void* ws, void* stream, bool dry_run) {
   if (mode != HEAD_FWD && mode != HEAD_INV) return CNF_NOT_ELIGIBLE;
   if (!c->ln || c->ks != 3 || c->R < 1 || c->R > FZ_MAXR) return CNF_NOT_ELIGIBLE;
   if (in_mask < 0 || in_mask > 3) return CNF_NOT_ELIGIBLE;
@@ -807,6 +807,7 @@ int launch_fused_coupling(const cnf_coupling* c, const float* params, FlowView i
   a.div_qcat_m = recip32((unsigned)(cat / 4));
   a.div_c1_m = recip32((unsigned)c->c1);
   a.div_sw_m = recip32((unsigned)(c->w + 2));
+  if (dry_run) return 0;   // eligibility query
   cudaStream_t st = (cudaStream_t)stream;
   const bool two = 2 * (smem + kFzStatic + 1024) <= 228 * 1024;   // two CTAs per SM fit
   if (two && fz_matches<FzCfg2A>(c)) return fz_launch<FzCfg2A, 256, 2>(a, B, 256, smem, st);

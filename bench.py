@@ -2,15 +2,19 @@
 """Benchmark of the conditional RealNVP hot path (BASELINE.json metric: images/sec for log-likelihood
 eval and sampling).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config 2|3|4|4-heavy|5|5-heavy]   # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...                                       # the reference's CPU path (oracle port)
 
-Workload (N=1): BASELINE config 2 — conv_cINN class-conditioned 28x28x1 image + 1 label plane
+Default workload (N=1): BASELINE config 2 - conv_cINN class-conditioned 28x28x1 image + 1 label plane
 (io_shape [28,28,2], x_d 1, lists [0,1,0,0]/[3,3,3,3]/[64,64,32,32]/[8,8,4,4]), batch 256 per GPU,
-synthetic inputs and "trained-like" random weights (SURVEY §8d).  One STEP = one log-likelihood
+synthetic inputs and "trained-like" random weights (SURVEY 8d).  One STEP = one log-likelihood
 evaluation (`log_loss`) of a batch + one sampling pass (`call(zy,-1)`) of a batch; images/sec counts the
 images through both (2*B per step).  N>1: one process per GPU (torchrun), the batch dimension is sharded
-(weak scaling: 256 images per GPU), no data-path collective; time is the max over ranks.
+(weak scaling: the config's batch per GPU), no data-path collective; time is the max over ranks.
+--config selects the other BASELINE configs (builder-chosen hyper-parameters where the reference
+wires none): 3 = 32x32x4 class-conditioned, 4 = 64x64x6 super-resolution (light lists; 4-heavy: 128/64 kernels),
+5 = 128x128x4 noise pre-training (light; 5-heavy: 256/128 kernels).  Their line has the same keys; `config.train_step`
+is the training throughput (the named workload of configs 4 and 5).
 """
 import argparse
 import json
@@ -25,10 +29,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CFG2 = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3, 3, 3, 3],
-            num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
-WORKLOAD = "cfg2: conv_cINN class-conditioned 28x28x1 + label plane (io 28x28x2), batch 256/GPU, log_loss + sampling"
+_L = dict(squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3, 3, 3, 3])
+CONFIGS = {
+    "2": dict(cfg=dict(io_shape=[28, 28, 2], x_d=1, num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4], **_L),
+              batch=256, synth="cfg2",
+              workload="cfg2: conv_cINN class-conditioned 28x28x1 + label plane (io 28x28x2), batch 256/GPU, log_loss + sampling"),
+    "3": dict(cfg=dict(io_shape=[32, 32, 4], x_d=3, num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4], **_L),
+              batch=256, synth="cfg3",
+              workload="cfg3: conv_cINN class-conditioned 32x32x3 + label plane (io 32x32x4), batch 256/GPU, log_loss + sampling"),
+    "4": dict(cfg=dict(io_shape=[64, 64, 6], x_d=3, num_kernels_list=[64, 64, 32, 32], cardinality_list=[4, 4, 2, 2], **_L),
+              batch=64, synth="cfg4",
+              workload="cfg4 (light lists 64/32 kernels, cardinality 4/2): conv_cINN super-resolution 64x64x3 with 8x8 condition "
+                       "(io 64x64x6), batch 64/GPU, log_loss + sampling; training in config.train_step"),
+    "4-heavy": dict(cfg=dict(io_shape=[64, 64, 6], x_d=3, num_kernels_list=[128, 128, 64, 64], cardinality_list=[8, 8, 4, 4], **_L),
+                    batch=32, synth="cfg4",
+                    workload="cfg4 heavy (128/64 kernels, cardinality 8/4): super-resolution 64x64x3 (io 64x64x6), batch 32/GPU"),
+    "5": dict(cfg=dict(io_shape=[128, 128, 4], x_d=3, num_kernels_list=[64, 64, 32, 32], cardinality_list=[2, 2, 2, 2], **_L),
+              batch=16, synth="cfg5",
+              workload="cfg5 (light lists 64/32 kernels, cardinality 2): noise pre-training 128x128x3 + label plane (io 128x128x4), "
+                       "batch 16/GPU, log_loss + sampling; training in config.train_step"),
+    "5-heavy": dict(cfg=dict(io_shape=[128, 128, 4], x_d=3, num_kernels_list=[256, 256, 128, 128], cardinality_list=[8, 8, 4, 4], **_L),
+                    batch=4, synth="cfg5",
+                    workload="cfg5 heavy (256/128 kernels, cardinality 8/4): noise pre-training 128x128x4, batch 4/GPU"),
+}
 METRIC = "images/sec (log-likelihood eval + sampling)"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # FFMA2: 128 fp32 FMA lanes per SM and clock; computed, not measured
 
 
 def parse():
@@ -37,9 +62,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--cpu-sample-batch", type=int, default=32)
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     return ap.parse_args()
 
 
@@ -101,22 +127,53 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu capture
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` report); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    e = d.get(kernel)
+    return (e["dram_bytes"], e["source"]) if e else (None, None)
+
+
+def synth_host(kind, cfg, B, seed):
+    """synthetic xy batch as a host tensor, generated with torch (the product's bench owns its inputs)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    H, W, D = cfg["io_shape"]
+    xd = cfg["x_d"]
+    if kind in ("cfg2", "cfg3"):
+        img = 0.98 * torch.rand((B, H, W, xd), generator=g) + 0.02 * torch.randn((B, H, W, xd), generator=g)
+        label = float(torch.randint(0, 10, (1,), generator=g)) / 9.0
+        lab = 0.98 * torch.full((B, H, W, D - xd), label) + 0.02 * torch.randn((B, H, W, D - xd), generator=g)
+        return torch.cat([img, lab], 3).contiguous()
+    if kind == "cfg4":
+        hr = torch.rand((B, H, W, xd), generator=g)
+        y = hr.reshape(B, H // 8, 8, W // 8, 8, xd).mean((2, 4), keepdim=True).expand(B, H // 8, 8, W // 8, 8, xd).reshape(B, H, W, xd)
+        xy = torch.cat([hr - y, y], 3)
+        return (0.98 * xy + 0.02 * torch.randn(xy.shape, generator=g)).contiguous()
+    return torch.randn((B, H, W, D), generator=g)
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(batch, steps, warmup):
-    import numpy as np
+def cpu_reference_run(key, batch, steps, warmup, budget_s=150.0):
     import torch
     from oracle.flow_torch import FlowOracle
-    from oracle.weights import init_weights, synth_inputs
+    from oracle.weights import init_weights
+    C = CONFIGS[key]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    o = FlowOracle(**CFG2, dtype=torch.float32)
+    o = FlowOracle(**C["cfg"], dtype=torch.float32)
     o.set_weights(init_weights(o.plan, 'rand', seed=0))
-    x = synth_inputs('cfg2', batch, seed=0)
-    z = synth_inputs('noise:28x28x2', batch, seed=1)
-    z[..., 1:] = x[..., 1:]
+    x = synth_host(C["synth"], C["cfg"], batch, 0).numpy()
+    z = torch.randn(x.shape, generator=torch.Generator().manual_seed(1)).numpy()
+    z[..., C["cfg"]["x_d"]:] = x[..., C["cfg"]["x_d"]:]
     times = []
+    t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         o.log_loss(x)
@@ -124,26 +181,30 @@ def cpu_reference_run(batch, steps, warmup):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        if times and time.perf_counter() - t_start > budget_s:
+            break
     total = sum(times)
-    return {"value": 2 * batch * steps / total, "ms_per_step": 1e3 * total / steps, "cores": cores,
-            "torch_threads": torch.get_num_threads(),
-            "sample": f"{steps} steps of log_loss + call(-1) on a batch of {batch} cfg2 images "
-                      f"(oracle port, torch {torch.__version__} CPU fp32, {warmup} warm-up)"}
+    return {"value": 2 * batch * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "steps": len(times), "torch_threads": torch.get_num_threads(),
+            "sample": f"{len(times)} steps of log_loss + call(-1) on a batch of {batch} {C['synth']} images, the bench's own "
+                      f"config and batch (oracle port, torch {torch.__version__} CPU fp32, {cores} threads, {warmup} warm-up)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    r = cpu_reference_run(args.cpu_sample_batch, steps, 1)
+    C = CONFIGS[args.config]
+    B = args.batch or C["batch"]
+    r = cpu_reference_run(args.config, B, max(1, min(args.steps, 3)), 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path: TensorFlow is not installable here, so this is "
-                   "the repo's oracle port of the reference (restated reference on CPU, not TensorFlow); each step is "
-                   f"a bounded sample of {args.cpu_sample_batch} images"},
+        "config": {"workload": C["workload"], "batch_per_gpu": B, "images_per_step": 2 * B,
+                   "note": "reference CPU path: TensorFlow is not installable here, so this is the repo's oracle port of the "
+                           "reference (restated reference on CPU, not TensorFlow) on the bench's own config and batch; the "
+                           "number of timed steps is bounded (at most 3, at most ~150 s)"},
         "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -155,13 +216,10 @@ def run_reference(args):
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
     from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import cFlow
     from arl_conditional_normalizing_flows_b200 import _lib
-    from oracle.weights import init_weights, synth_inputs
-    from oracle.planner import plan_flow
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,22 +232,23 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
-    H, W, D = CFG2["io_shape"]
-    model = cFlow(**CFG2, device=dev)
-    plan = plan_flow(CFG2["io_shape"], CFG2["x_d"], CFG2["squeeze_factor_block_list"], CFG2["ResNeXt_block_list"],
-                     CFG2["num_kernels_list"], CFG2["cardinality_list"])
-    model.set_weights(init_weights(plan, 'rand', seed=0))
+    C = CONFIGS[args.config]
+    CFG = C["cfg"]
+    B = args.batch or C["batch"]
+    H, W, D = CFG["io_shape"]
+    xd = CFG["x_d"]
+    model = cFlow(**CFG, device=dev)
+    model.randomize_weights(seed=0)          # trained-like random weights, identical on every rank
 
     # rotating synthetic inputs (different batch every step; shards differ per rank)
-    NBUF = 8
+    NBUF = 8 if B * H * W * D * 4 < (64 << 20) else 3
     xs, zs = [], []
     for i in range(NBUF):
-        x = synth_inputs('cfg2', B, seed=1000 * rank + i)
-        z = synth_inputs('noise:28x28x2', B, seed=5000 + 1000 * rank + i)
-        z[..., 1:] = x[..., 1:]
-        xs.append(torch.from_numpy(x))
-        zs.append(torch.from_numpy(z))
+        x = synth_host(C["synth"], CFG, B, 1000 * rank + i)
+        z = torch.randn(x.shape, generator=torch.Generator().manual_seed(5000 + 1000 * rank + i))
+        z[..., xd:] = x[..., xd:]
+        xs.append(x)
+        zs.append(z)
     xs_d = [t.to(dev) for t in xs]
     zs_d = [t.to(dev) for t in zs]
     xs_h = [t.pin_memory() for t in xs]
@@ -245,18 +304,25 @@ def run_ours(args):
     ms_eval = timed(lambda i: model.log_loss(xs_d[i % NBUF]), K, 1)
     ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
     ms_e2e = timed(step_e2e, K, 2)
+    # the same step with every layer on the layer-per-kernel path (what the activation-resident launches replace)
+    model.set_fusion(0)
+    ms_unfused = timed(step_device, K, 1)
+    model.set_fusion(1)
+    # strong scaling: the config's batch as the GLOBAL batch, split over the ranks
+    Bs = max(1, B // world)
+    ms_strong = timed(lambda i: (model.log_loss(xs_d[i % NBUF][:Bs]), model(zs_d[i % NBUF][:Bs], -1)), K, 1)
 
-    # ---- dominant kernel (profiles/r01i_summary.md: 42 % of the step): the fused grouped dilated 3x3 convs of the 28x28x64
-    # channel layers (gconv_oct_kernel, all dilation branches in one launch), timed ALONE with CUDA events on the stream it
-    # is launched on; the 1x1-conv kernel (pw_tc3_kernel<64>, tcgen05 3xTF32) is timed the same way and reported beside it.
-    layer = model.coupling_layers[2]        # block 0, mask 2: h,w,nk = 28,28,64
+    # ---- dominant kernel: the grouped dilated 3x3 convs of the first full-resolution channel layer (config 2: 28x28x64,
+    # gconv_oct_kernel, all dilation branches in one launch; profiles/r02_summary.md), timed ALONE with CUDA events on the
+    # stream it is launched on; the 1x1-conv kernel (pw_tc3_kernel, tcgen05 3xTF32) is timed the same way beside it.
+    layer = model.coupling_layers[2]        # block 0, mask 2: full resolution, nk = num_kernels_list[0]
     info = layer._info
     hw, nk, cat = info.h * info.w, info.nk, info.cat
     u1c = torch.randn(B, info.h, info.w, info.c1, device=dev)
     layer.A_wrapper(u1c)                    # fills the layer workspace (X, Y1, Y2, LayerNorm statistics)
     ws = layer._workspace(B)
 
-    def time_pw(which, reps=20):
+    def time_stage(which, reps=20):
         br = _lib.Borrowed()
         pp, pw_ = br(layer.params), br(ws)
         for _ in range(3):
@@ -270,11 +336,11 @@ def run_ours(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    ms_pw1 = time_pw(0)
-    ms_pw2 = time_pw(1)
-    ms_gc = time_pw(2)
+    ms_pw1 = time_stage(0)
+    ms_pw2 = time_stage(1)
+    ms_gc = time_stage(2)
     # algorithmic bytes per launch (both nets): read the input once, write the output once (+ residual read);
-    # gamma/beta (0.4 MB per net, L2-resident across the batch) and W (16-28 KB) are not counted
+    # gamma/beta (L2-resident across the batch) and W are not counted
     pw1_bytes = 2 * B * hw * (nk + nk) * 4
     pw2_bytes = 2 * B * hw * (cat + nk + nk) * 4
     pw_flops = 2 * 2 * B * hw * nk * (nk + cat)
@@ -282,23 +348,31 @@ def run_ours(args):
     gc_macs = 2 * B * hw * sum(info.groups[i] * info.group_in[i] * info.group_out[i] * 9 for i in range(info.n_branches))
     hbm_peak, peak_src = peaks()
     pw_gbs = (pw1_bytes + pw2_bytes) / ((ms_pw1 + ms_pw2) * 1e-3) / 1e9
-    ach = gc_bytes / (ms_gc * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "gconv_oct_kernel: grouped dilated 3x3 convs (d = 1, 2, 4; 64 -> 112 channels) of a 28x28x64 "
-            "channel layer with LReLU+LayerNorm-on-load, fp32 FFMA2, both nets, B=256, one launch",
-            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01i_gconv_oct_ncu_full_summary.csv);
-            # below the algorithmic bytes because part of the written tensor is still in the 126 MB L2 when the kernel ends
-            "traffic": 235.8e6 if B == 256 else None,
-            "peak_source": peak_src, "ms_per_launch": ms_gc, "algorithmic_bytes_per_launch": gc_bytes,
-            "note": "this kernel is bound by fp32 FFMA issue / shared-memory operand traffic, not by HBM (DESIGN.md section 3): "
-                    "fp32 rate below, against 148 SMs x 128 FMA/clk x 2 x 1.965 GHz = 74.5 TFLOP/s",
-            "tflops_fp32": 2 * gc_macs / (ms_gc * 1e-3) / 1e12, "frac_of_fp32_ffma_peak": 2 * gc_macs / (ms_gc * 1e-3) / 74.5e12,
-            "pw_tc3_kernel<64>": {"what": "1x1 convs (64->64 and 112->64 + residual), tcgen05 3xTF32, timed alone",
-                                  "GB/s": pw_gbs, "frac_of_hbm_peak": pw_gbs / hbm_peak,
-                                  "ms_per_launch": {"pw1_64to64": ms_pw1, "pw2_112to64_res": ms_pw2},
-                                  "algorithmic_bytes_per_launch": {"pw1": pw1_bytes, "pw2": pw2_bytes},
-                                  "traffic": {"pw1": 165.2e6, "pw2": 357.4e6},
-                                  "tflops_fp32_equivalent": pw_flops / ((ms_pw1 + ms_pw2) * 1e-3) / 1e12}}
+    gc_gbs = gc_bytes / (ms_gc * 1e-3) / 1e9
+    gc_tflops = 2 * gc_macs / (ms_gc * 1e-3) / 1e12
+    is_cfg2 = args.config == "2" and B == 256
+    tr_gc, tr_src = ncu_traffic("gconv_oct_kernel") if is_cfg2 else (None, None)
+    tr_pw1, _ = ncu_traffic("pw_tc3_kernel<64> pw1") if is_cfg2 else (None, None)
+    tr_pw2, _ = ncu_traffic("pw_tc3_kernel<64> pw2") if is_cfg2 else (None, None)
+    roof = {"bound": "fp32-issue",
+            "kernel": f"grouped dilated 3x3 convs ({info.n_branches} dilation branches, {nk} -> {cat} channels) of the {info.h}x{info.w}x{nk} "
+                      "channel layer with LReLU+LayerNorm-on-load, fp32 FFMA2, both nets, one stage of one coupling layer "
+                      "(gconv_oct_kernel where the image tile fits shared memory, else one gconv3_kernel launch per branch)",
+            "achieved": gc_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gc_tflops / FP32_PEAK_TFLOPS,
+            "peak_source": "computed: 148 SMs x 128 fp32 FMA lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 figure; the "
+                           "kernel is bound by fp32 issue / shared-memory operand traffic, not by HBM or the tensor pipe, "
+                           "DESIGN.md section 3)",
+            "traffic": tr_gc, "traffic_source": tr_src,
+            "ms_per_launch": ms_gc, "algorithmic_flops_per_launch": 2 * gc_macs,
+            "hbm": {"achieved": gc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gc_gbs / hbm_peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": gc_bytes},
+            "pw_tc3_kernel": {"what": f"1x1 convs ({nk}->{nk} and {cat}->{nk} + residual) of the same layer, tcgen05 3xTF32 where N is "
+                                      "16/32/64, timed alone; bound: HBM",
+                              "GB/s": pw_gbs, "frac_of_hbm_peak": pw_gbs / hbm_peak,
+                              "ms_per_launch": {"pw1": ms_pw1, "pw2_res": ms_pw2},
+                              "algorithmic_bytes_per_launch": {"pw1": pw1_bytes, "pw2": pw2_bytes},
+                              "traffic": {"pw1": tr_pw1, "pw2": tr_pw2},
+                              "tflops_fp32_equivalent": pw_flops / ((ms_pw1 + ms_pw2) * 1e-3) / 1e12}}
 
     # ---- the stand-alone fused coupling-law kernel (mask addressing + affine law + per-sample log-det), the
     # HBM-bound kernel the north star names: 12 bytes per element of u
@@ -327,15 +401,24 @@ def run_ours(args):
 
     # ---- training step: loss_and_grad + gradient all-reduce (NCCL, N>1) + fused Adam on the same
     # batch shape.  Reported in `config` beside the headline metric; run last because it updates the weights.
-    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam
-    model.compile(optimizer=Adam(3e-4))
-    Kt = max(1, min(K, 10))
-    ms_train = timed(lambda i: model.train_step(xs_d[i % NBUF]), Kt, 2)
-    train_ws_gib = model._train_ws.numel() / 2 ** 30
+    train = None
+    if not args.no_train:
+        from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam
+        model.compile(optimizer=Adam(3e-4))
+        Kt = max(1, min(K, 10))
+        try:
+            ms_train = timed(lambda i: model.train_step(xs_d[i % NBUF]), Kt, 2)
+            train = {"images_per_s": B * world * Kt / (ms_train * 1e-3), "ms_per_step": ms_train / Kt, "steps": Kt,
+                     "what": "cFlow.train_step: forward with saved activations, hand-written backward, flat-gradient "
+                             f"all-reduce (NCCL when N>1), fused Adam; batch {B}/GPU",
+                     "activation_workspace_GiB": model._train_ws.numel() / 2 ** 30}
+        except NotImplementedError as e:      # e.g. group widths above 8 (config 5): backward kernels not built
+            train = {"unsupported": str(e)}
 
-    n_coupling = len(model.coupling_layers)
-    launches_per_dir = sum(2 + 3 * l._info.R for l in model.coupling_layers)
-    launches_step = (launches_per_dir + 3) + launches_per_dir     # fwd (+logdet, prior, finalize) + inverse
+    # kernels of this repo launched per step: per pass one launch per activation-resident layer, 2 + 3R per other layer; the
+    # forward pass adds the state copy, log-det finalize, prior/L1 and loss-finalize kernels, the inverse pass the state copy
+    per_pass = model.launches_per_pass()
+    launches_step = (per_pass + 4) + (per_pass + 1)
 
     if rank == 0:
         imgs = 2 * B * world
@@ -343,18 +426,20 @@ def run_ours(args):
             "metric": METRIC, "value": imgs * K / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "images_per_step": imgs,
-                       "weights": "trained-like random (SURVEY 8d W-rand), seed 0",
-                       "l2": "no explicit flush: each step streams ~52 MB of weights and >300 MB of s/t-net activations "
-                             "(> 126 MB L2) and inputs rotate over 8 distinct batches",
+            "config": {"workload": C["workload"], "batch_per_gpu": B, "images_per_step": imgs,
+                       "weights": "trained-like random (SURVEY 8d W-rand; cFlow.randomize_weights, seed 0)",
+                       "l2": "no explicit flush: each step streams the model's weights and the s/t-net activations of the "
+                             f"full-resolution layers (> 126 MB L2 at this batch) and inputs rotate over {NBUF} distinct batches",
                        "eval_images_per_s": B * world * K / (ms_eval * 1e-3),
                        "sample_images_per_s": B * world * K / (ms_samp * 1e-3),
+                       "layer_per_kernel_path_images_per_s": imgs * K / (ms_unfused * 1e-3),
+                       "resident_layers": f"{sum(l.resident_kernel_eligible() for l in model.coupling_layers)} of "
+                                          f"{len(model.coupling_layers)} coupling layers run as one activation-resident launch",
+                       "strong_scaling": {"global_batch": Bs * world, "batch_per_gpu": Bs,
+                                          "images_per_s": 2 * Bs * world * K / (ms_strong * 1e-3)},
                        "coupling_law_kernel": {"shape": [512, 128, 128, 4], "ms": ms_law, "GB/s": law_gbs,
                                                "frac_of_hbm_peak": law_gbs / hbm_peak, "bytes_per_element": 12},
-                       "train_step": {"images_per_s": B * world * Kt / (ms_train * 1e-3), "ms_per_step": ms_train / Kt,
-                                      "steps": Kt, "what": "cFlow.train_step: forward with saved activations, hand-written "
-                                      "backward, flat-gradient all-reduce (NCCL when N>1), fused Adam; batch "
-                                      f"{B}/GPU", "activation_workspace_GiB": train_ws_gib},
+                       "train_step": train,
                        "parallelism": f"batch-sharded x{world}; eval/sampling: no collective; training: one gradient "
                                       "all-reduce per step"},
             "e2e": {"value": imgs * K / (ms_e2e * 1e-3), "unit": "images/s",
@@ -364,7 +449,7 @@ def run_ours(args):
             "roofline": roof,
         }
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_reference_run(args.cpu_sample_batch, 2, 1)
+            r = cpu_reference_run(args.config, B, 2, 1, budget_s=60.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)

@@ -129,6 +129,8 @@ int cnf_coupling_set_fusion(cnf_coupling* c, int enable);
 #define CNF_PATH_NO_STEM2 64    /* stem: no per-sample stem2_kernel -> implicit-im2col gemm_kernel                     */
 #define CNF_PATH_NO_HEAD2 128   /* head: no streaming head2_kernel -> halo-tile head_kernel                           */
 #define CNF_PATH_ALL 255
+/* 1 iff inference runs this layer as one activation-resident launch (shape covered and not excluded), else 0 */
+int cnf_coupling_resident_eligible(const cnf_coupling* c);
 int cnf_plan_set_kernel_paths(cnf_plan* p, int excluded);
 int cnf_coupling_set_kernel_paths(cnf_coupling* c, int excluded);
 
