@@ -286,20 +286,33 @@ class coupling_layer(Layer):
         return {net: {k: v.detach().cpu().numpy().copy() for k, v in d.items()}
                 for net, d in self.weight_views().items()}
 
-    def randomize_weights(self, generator=None):
-        """"Trained-like" random state for benchmarks and stress tests (no reference counterpart; SURVEY 8d W-rand): kernels
-        N(0, 1/fan_in), biases and beta N(0, 0.1), gamma and the tanh scale U[0.5, 1.5], drawn on the device."""
-        dev = self.params.device
-        for net, d in self.weight_views().items():
-            for name, v in d.items():
-                role = name.rsplit('.', 1)[-1]
-                if role == 'kernel':
-                    fan_in = int(np.prod(v.shape[:-1]))
-                    v.copy_(torch.randn(v.shape, device=dev, generator=generator) / math.sqrt(fan_in))
-                elif role == 'gamma' or name == 'tanh_scale':
-                    v.copy_(0.5 + torch.rand(v.shape, device=dev, generator=generator))
+    def _random_state_spec(self):
+        """per-element (std, is_uniform) of the "trained-like" random state (SURVEY 8d W-rand): kernels N(0, 1/fan_in), biases
+        and beta N(0, 0.1), gamma and the tanh scale U[0.5, 1.5]; unused padding stays 0"""
+        std = np.zeros(2 * self._net_stride, np.float32)
+        uni = np.zeros(2 * self._net_stride, bool)
+        for n, net in enumerate(("A", "b")):
+            base = n * self._net_stride
+            for name, off, shape, role in self._entries:
+                if role == 4 and net == "b":
+                    continue
+                cnt = int(np.prod(shape))
+                if role == 0:
+                    std[base + off: base + off + cnt] = 1.0 / math.sqrt(int(np.prod(shape[:-1])))
+                elif role in (2, 4):
+                    uni[base + off: base + off + cnt] = True
                 else:
-                    v.copy_(0.1 * torch.randn(v.shape, device=dev, generator=generator))
+                    std[base + off: base + off + cnt] = 0.1
+        return std, uni
+
+    def randomize_weights(self, generator=None):
+        """"Trained-like" random state for benchmarks and stress tests (no reference counterpart), drawn on the device."""
+        std, uni = self._random_state_spec()
+        dev = self.params.device
+        n = self.params.numel()
+        p = torch.randn(n, device=dev, generator=generator) * torch.from_numpy(std).to(dev)
+        u = torch.from_numpy(uni).to(dev)
+        self.params.copy_(torch.where(u, 0.5 + torch.rand(n, device=dev, generator=generator), p))
 
     def resident_kernel_eligible(self):
         """True iff inference runs this layer as ONE activation-resident launch (csrc/fused_kernels.cu)."""
