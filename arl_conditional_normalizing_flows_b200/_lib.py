@@ -99,6 +99,8 @@ def _load():
         "cnf_flow_loss_and_grad": (I, [P, P, P, P, P, P, P, P, P, P, V]),
         "cnf_plan_train_workspace_bytes_recompute": (I64, [P, I64]),
         "cnf_flow_loss_and_grad_recompute": (I, [P, P, P, P, P, P, P, P, P, P, V]),
+        "cnf_plan_train_workspace_bytes_invert": (I64, [P, I64]),
+        "cnf_flow_loss_and_grad_invert": (I, [P, P, P, P, P, P, P, P, P, P, V]),
         "cnf_adam_step": (I, [P, P, P, P, I64, D, D, D, D, D, V]),
         "cnf_coupling_forward": (I, [P, P, P, P, P, P, V]),
         "cnf_coupling_backward": (I, [P, P, P, P, P, V]),

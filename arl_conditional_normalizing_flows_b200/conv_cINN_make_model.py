@@ -711,10 +711,20 @@ class cFlow:
     #: True: keep only the per-layer flow states in the forward pass and re-compute each layer's s/t-net activations during
     #: the backward pass (same gradients, ~1/n_layers of the activation memory, one extra forward pass)
     recompute_activations = False
+    #: True: keep NOTHING in the forward pass; the backward pass recovers each layer's input state from its output with the
+    #: inverse law (M:1333-1394) and re-computes the activations from it (least memory; gradients carry the flow's fp32
+    #: round-trip error, see cnf.h)
+    recover_states_by_inverse = False
+
+    def _train_fns(self):
+        if self.recover_states_by_inverse:
+            return lib.cnf_plan_train_workspace_bytes_invert, lib.cnf_flow_loss_and_grad_invert
+        if self.recompute_activations:
+            return lib.cnf_plan_train_workspace_bytes_recompute, lib.cnf_flow_loss_and_grad_recompute
+        return lib.cnf_plan_train_workspace_bytes, lib.cnf_flow_loss_and_grad
 
     def _train_workspace(self, B):
-        need = int((lib.cnf_plan_train_workspace_bytes_recompute if self.recompute_activations
-                    else lib.cnf_plan_train_workspace_bytes)(self._plan, B))
+        need = int(self._train_fns()[0](self._plan, B))
         ws = getattr(self, '_train_ws', None)
         if ws is None or ws.numel() < need or ws.device != self.params.device:
             self._train_ws = ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
@@ -734,7 +744,7 @@ class cFlow:
         if getattr(self, '_grads', None) is None or self._grads.device != self.params.device:
             self._grads = torch.empty_like(self.params)
         br = Borrowed()
-        fn = lib.cnf_flow_loss_and_grad_recompute if self.recompute_activations else lib.cnf_flow_loss_and_grad
+        fn = self._train_fns()[1]
         check(fn(self._plan, br(xy), br(self.params), br(self._grads), br(zy), br(ll_z), br(ll_y), br(ld), br(loss4),
                  br(self._train_workspace(B)), stream_ptr()))
         self.last_logdet_per_sample = ld

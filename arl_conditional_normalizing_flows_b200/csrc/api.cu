@@ -203,13 +203,17 @@ struct TrainLayout {
   std::vector<int64_t> saved_off;
   int64_t ld2_off = 0, tmp_off = 0;   // recompute mode: dummy log-det accumulator, scratch flow buffer
 };
-TrainLayout train_layout(const cnf_plan* p, int64_t B, bool recompute = false) {
+// mode 0: every activation of every layer kept; 1: per-layer input states kept, activations re-computed layer by layer in
+// the backward pass; 2: nothing kept but zy - each layer's input state is recovered from its output with the inverse law
+// (M:1333-1394) and its activations are re-computed from that
+TrainLayout train_layout(const cnf_plan* p, int64_t B, int mode = 0) {
+  const bool recompute = mode != 0;
   auto al = [](int64_t x) { return (x + 255) & ~int64_t(255); };
   TrainLayout t;
   const int n = (int)p->couplings.size();
   t.state_bytes = al(B * p->H * p->W * p->D * 4);
   int64_t off = 0;
-  t.states_off = off; off += t.state_bytes * n;
+  t.states_off = off; off += t.state_bytes * (mode == 2 ? 1 : n);
   t.G_off = off; off += t.state_bytes;
   t.ld_off = off; off += al(B * 8);
   int64_t scratch = 0;
@@ -239,13 +243,19 @@ int64_t cnf_plan_train_workspace_bytes(const cnf_plan* p, int64_t batch) {
 
 int64_t cnf_plan_train_workspace_bytes_recompute(const cnf_plan* p, int64_t batch) {
   if (!p || batch < 0) return -1;
-  return train_layout(p, batch, true).total;
+  return train_layout(p, batch, 1).total;
+}
+
+int64_t cnf_plan_train_workspace_bytes_invert(const cnf_plan* p, int64_t batch) {
+  if (!p || batch < 0) return -1;
+  return train_layout(p, batch, 2).total;
 }
 
 static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
                               DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
                               DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream,
-                              bool recompute) {
+                              int mode) {
+  const bool recompute = mode != 0, invert = mode == 2;
   if (!p) return fail(CNF_ERR_ARG, "null plan");
   Ten X, P, Gd, Z, A, Bt, L, F, W;
   TRY(borrow(xy, "xy", 4, &X));
@@ -266,7 +276,7 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
   if (P.numel < p->param_count || Gd.numel < p->param_count)
     return fail(CNF_ERR_SHAPE, "params/grads: need %lld floats", (long long)p->param_count);
   if (X.p == Z.p) return fail(CNF_ERR_ARG, "zy must not alias xy");
-  const TrainLayout T = train_layout(p, B, recompute);
+  const TrainLayout T = train_layout(p, B, mode);
   if (W.bytes < T.total) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)T.total, (long long)W.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)W.p;
@@ -279,7 +289,20 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
   TRY(cuda_rc((int)cudaMemsetAsync(Gd.p, 0, sizeof(float) * p->param_count, st), "memset"));
   std::vector<CouplingSaved> saved;
   // ---- forward: state[l+1] = layer_l(state[l]); the last state is zy
-  for (int li = 0; li < n; ++li) {
+  if (invert) {
+    // nothing is kept: the inference path (activation-resident launches where a layer fits them) in place on zy
+    TRY(cuda_rc(launch_copy(X.p, Z.p, B * per, stream), "copy"));
+    for (int li = 0; li < n; ++li) {
+      const cnf_coupling* c = p->couplings[li];
+      saved.push_back(carve_saved(c, B, base + T.saved_off[li]));
+      saved.back().state = (float*)(base + T.states_off);
+      FlowView v = make_view(Z.p, p->H, p->W, p->D, p->level[li]);
+      TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], v, c->mask, v, (int)B, HEAD_FWD, ldacc, nullptr, nullptr,
+                               base + T.saved_off[li], stream), "coupling layer"));
+    }
+    if (n) TRY(cuda_rc(launch_copy(Z.p, (float*)(base + T.states_off), B * per, stream), "copy"));
+  }
+  for (int li = 0; li < n && !invert; ++li) {
     const cnf_coupling* c = p->couplings[li];
     saved.push_back(carve_saved(c, B, base + T.saved_off[li]));
     CouplingSaved& sv = saved.back();
@@ -303,9 +326,16 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
   TRY(cuda_rc(launch_loss_grad(Z.p, X.p, G, B * per, p->D, p->x_d, (float)p->lambda_y, invB, stream), "loss gradient"));
   for (int li = n - 1; li >= 0; --li) {
     const cnf_coupling* c = p->couplings[li];
+    if (invert) {
+      // the running state is this layer's OUTPUT: the inverse law turns it into the layer's input (u1 is untouched by the
+      // layer, so the s/t nets see the same values; u2 = (v2 - b) / exp(A))
+      FlowView cv = make_view(saved[li].state, p->H, p->W, p->D, p->level[li]);
+      TRY(cuda_rc(run_coupling(c, P.p + p->param_off[li], cv, c->mask, cv, (int)B, HEAD_INV, nullptr, nullptr, nullptr,
+                               base + T.saved_off[li], stream), "coupling layer (inverse)"));
+    }
     if (recompute) {
-      // re-run this layer's forward from its kept input state with every activation saved (same kernels, same reduction
-      // orders: the activations are the ones the first pass produced)
+      // re-run this layer's forward from its input state with every activation saved (mode 1: same kernels, same
+      // reduction orders as the first pass, so the activations are the ones it produced)
       float* tmp = (float*)(base + T.tmp_off);
       double* ld2 = (double*)(base + T.ld2_off);
       TRY(cuda_rc(launch_copy(saved[li].state, tmp, B * per, stream), "copy"));
@@ -324,14 +354,20 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
 int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
                            DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
                            DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream) {
-  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, false);
+  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, 0);
 }
 
 int cnf_flow_loss_and_grad_recompute(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
                                      DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
                                      DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace,
                                      void* stream) {
-  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, true);
+  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, 1);
+}
+
+int cnf_flow_loss_and_grad_invert(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                                  DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                                  DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream) {
+  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, 2);
 }
 
 int cnf_adam_step(DLManagedTensor* params, const DLManagedTensor* grads, DLManagedTensor* m, DLManagedTensor* v,

@@ -174,6 +174,17 @@ int cnf_flow_loss_and_grad_recompute(const cnf_plan* p, const DLManagedTensor* x
                                      DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
                                      DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
                                      DLManagedTensor* workspace, void* stream);
+/* Activation-free backward via invertibility (coupling_layer.backward, M:1333-1394): the forward pass keeps
+ * nothing but zy (and runs the inference kernels); the backward pass recovers every layer's input state from its output
+ * with the inverse law and re-computes the layer's activations from it.  Memory: one flow state + one layer's activations.
+ * Accuracy: the recovered states carry the fp32 round-trip error of the flow (1e-6 at the reference's initial state, up to
+ * 1e-3 with ill-conditioned trained-like weights), so the gradients are those of the other two modes
+ * only to that accuracy.  workspace: cnf_plan_train_workspace_bytes_invert bytes. */
+int64_t cnf_plan_train_workspace_bytes_invert(const cnf_plan* p, int64_t batch);
+int cnf_flow_loss_and_grad_invert(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                                  DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
+                                  DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
+                                  DLManagedTensor* workspace, void* stream);
 /* optimizer.apply_gradients with keras Adam (M:1874; C:567 / P:130: lr 3e-4, beta 0.9/0.999, eps 1e-7):
  * one fused update of the flat parameter buffer; `step` counts from 1; grads are multiplied by
  * grad_scale first (1/world_size after a data-parallel sum all-reduce). */
