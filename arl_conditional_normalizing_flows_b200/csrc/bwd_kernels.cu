@@ -1422,7 +1422,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
       a.g_off = L.ln3_g; a.be_off = L.ln3_b; a.stats = stats(3 * r + 2);
       a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln;
       CU_TRY(launch_wgrad_pw(a, st));
-      CU_TRY(dgrad_pw(params, ns, L.pw2_w, GX, GA, B, hw, cat, nk, st));
+      CU_TRY(dgrad_pw(params, ns, L.pw2_w, GX, GA, B, hw, cat, nk, st, c->paths));
       CU_TRY(ln_backward(GA, sv.Y2[r], GY, params, grads, ns, L.ln3_g, L.ln3_b, stats(3 * r + 2), bst, B,
                          (long long)hw * cat, c->ln, 0, st));
     }
@@ -1454,7 +1454,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
       a.g_off = L.ln1_g; a.be_off = L.ln1_b; a.stats = stats(3 * r);
       a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln;
       CU_TRY(launch_wgrad_pw(a, st));
-      CU_TRY(dgrad_pw(params, ns, L.pw1_w, GY, GA, B, hw, nk, nk, st));
+      CU_TRY(dgrad_pw(params, ns, L.pw1_w, GY, GA, B, hw, nk, nk, st, c->paths));
       CU_TRY(ln_backward(GA, sv.X[r], GX, params, grads, ns, L.ln1_g, L.ln1_b, stats(3 * r), bst, B, (long long)hw * nk,
                          c->ln, 1, st));
     }

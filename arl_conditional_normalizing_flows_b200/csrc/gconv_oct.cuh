@@ -70,6 +70,21 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
   d = *reinterpret_cast<float2*>(&dd);
 }
 
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {   // a.xy * b.xy in one issue slot
+  unsigned long long dd;
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(aa), "l"(bb));
+  return *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+  unsigned long long dd;
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(aa), "l"(bb));
+  return *reinterpret_cast<float2*>(&dd);
+}
+
 // position of weight (ci, co) of a tap inside its quad block (ci & 4 selects the block): rows of G outputs per input channel
 #ifndef OCT_PACKED
 #define OCT_PACKED 1   // 1: FFMA2 over output-channel pairs with the activation as broadcast scalar operand; 0: scalar FFMA
@@ -85,25 +100,38 @@ __device__ __forceinline__ int oct_xoff(int P, int hq) { return P * 8 + ((hq ^ (
 template <int G>
 __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const float* __restrict__ wb,
                                            const float* __restrict__ bias, int P0, int Pmax, int rstep, int dil,
-                                           float* __restrict__ dst, long long jstride, int vmask, bool vec8, float& s1,
-                                           float& s2, bool wskip = false) {
+                                           float* __restrict__ dst, long long jstride, int vmask, bool vec8, float2& s1,
+                                           float2& s2, bool wskip = false) {
   constexpr int HS = 4 * G + 4;                 // floats per (tap, quad) weight block (4 of them padding)
-  // acc[j][p] = output channels (2p, 2p+1) of pixel j.  A three-register FFMA issues every other cycle on this part; FFMA2
-  // (two FMAs per issue, the activation as broadcast scalar operand, the weight pair straight from a 128-bit load) is
-  // what reaches the fp32 peak.
+  // acc[j][p] = output channels (2p, 2p+1) of pixel j, started at the bias.  A three-register FFMA issues every other cycle
+  // on this part; FFMA2 (two FMAs per issue, the activation as broadcast scalar operand, the weight pair straight from a
+  // 128-bit load) is what reaches the fp32 peak.
   float2 acc[OCT_PX][4];
+  {
+    const float4 b0 = ld4(bias), b1 = ld4(bias + 4);
 #pragma unroll
-  for (int j = 0; j < OCT_PX; ++j)
+    for (int j = 0; j < OCT_PX; ++j) {
+      acc[j][0] = make_float2(b0.x, b0.y); acc[j][1] = make_float2(b0.z, b0.w);
+      acc[j][2] = make_float2(b1.x, b1.y); acc[j][3] = make_float2(b1.z, b1.w);
+    }
+  }
+  // float offset of pixel (row m, kx = 0) of the segment, clamped ONCE per row so that the kx = 1, 2 pixels (+ dil, + 2 dil)
+  // stay inside the tile; every load that feeds a stored output is below the clamp (the last valid pixel of a row is the
+  // kx = 2 one).  The swizzle term is bit 2 of the pixel index = bit 5 of the float offset.
+  int row8[OCT_PX + 2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[j][c] = make_float2(0.f, 0.f);
+  for (int m = 0; m < OCT_PX + 2; ++m) row8[m] = min(P0 + m * rstep, Pmax - 2 * dil) * 8;
 #pragma unroll 1
   for (int kx = 0; kx < 3; ++kx) {
-    const int Pk = P0 + kx * dil;
+    const int k8 = kx * dil * 8;
 #pragma unroll
     for (int hq = 0; hq < 2; ++hq) {
       float4 xw[OCT_PX + 2];                     // logical quad hq of the OCT_PX + 2 input rows
 #pragma unroll
-      for (int m = 0; m < OCT_PX + 2; ++m) xw[m] = ld4(xb + oct_xoff(min(Pk + m * rstep, Pmax), hq));
+      for (int m = 0; m < OCT_PX + 2; ++m) {
+        const int p8 = row8[m] + k8;
+        xw[m] = ld4(xb + p8 + (((p8 >> 3) & 4) ^ (hq << 2)));
+      }
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float* wr = wb + ((ky * 3 + kx) * 2 + hq) * HS;
@@ -153,28 +181,26 @@ __device__ __forceinline__ void oct_branch(const float* __restrict__ xb, const f
       }
     }
   }
-  float bq[8];
-  {
-    const float4 b0 = ld4(bias), b1 = ld4(bias + 4);
-    bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
-  }
+  // epilogue: LReLU statistics of the outputs in packed form (one issue slot per channel pair), one 256-bit store per
+  // pixel (32 lanes = 32 different lines either way; half the store instructions and tag look-ups)
+  const float2 slope = make_float2(CNF_LRELU_SLOPE, CNF_LRELU_SLOPE);
 #pragma unroll
   for (int j = 0; j < OCT_PX; ++j) {
     if (!((vmask >> j) & 1)) continue;
     float* d = dst + j * jstride;
-    float o[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      o[c] = ((c & 1) ? acc[j][c >> 1].y : acc[j][c >> 1].x) + bq[c];
-      const float l = fmaxf(o[c], CNF_LRELU_SLOPE * o[c]);
-      s1 += l;
-      s2 = fmaf(l, l, s2);
+    for (int c = 0; c < 4; ++c) {
+      const float2 t = fmul2(acc[j][c], slope);
+      const float2 l = make_float2(fmaxf(acc[j][c].x, t.x), fmaxf(acc[j][c].y, t.y));
+      s1 = fadd2(s1, l);
+      ffma2(s2, l, l);
     }
-    // one 256-bit store per pixel (32 lanes = 32 different lines either way; half the store instructions and tag look-ups)
-    if (vec8) st8(d, o);
-    else {
-      st4(d, make_float4(o[0], o[1], o[2], o[3]));
-      st4(d + 4, make_float4(o[4], o[5], o[6], o[7]));
+    if (vec8) {
+      const float o[8] = {acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y, acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y};
+      st8(d, o);
+    } else {
+      st4(d, make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y));
+      st4(d + 4, make_float4(acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y));
     }
   }
 }
@@ -204,7 +230,8 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
   float* b_s = w_s + wtot;                                  // [n_br][8]
   float* mr = b_s + a.n_br * 8;                             // [2][S][2]  (rstd, -mean rstd) per buffer parity
   float* red = mr + 4 * a.S;                                // [NT][2] per-thread, or [NT/32][4] per-warp partial sums
-  unsigned short* pt = reinterpret_cast<unsigned short*>(red + 2 * NT);    // [hw] pixel offset inside a sample tile
+  unsigned* segtab = reinterpret_cast<unsigned*>(red + 2 * NT);            // [n_br][NT] this thread's column segment per branch
+  unsigned short* pt = reinterpret_cast<unsigned short*>(segtab + a.n_br * NT);   // [hw] pixel offset inside a sample tile
 
   const float* P = a.params + (long long)net * a.net_stride;
   const float* src_n = a.in + (long long)net * a.in_net_stride + o * 8;
@@ -262,6 +289,23 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
   // depend on the batch size or on the sample's position inside the item)
   const int q = tid / a.tps, sl = tid - q * a.tps;
   const bool tactive = q < a.S && sl < a.nsps;
+  const int seg_t = sl / a.w, seg_x = sl - seg_t * a.w;
+  // slot -> (column x, row residue r mod dil, segment k): rows y0 + j dil with y0 = r + OCT_PX k dil.  The map does not depend
+  // on the item, so it is packed once per branch: bit 31 = the thread has work, bits 8-14 = valid rows, bits 0-7 = y0
+  for (int b = 0; b < a.n_br; ++b) {
+    const OctBranch& br = a.br[b];
+    const int d = br.dil;
+    const int r = seg_t / br.nsr, k = seg_t - r * br.nsr;
+    const int y0 = r + OCT_PX * k * d;
+    unsigned e = 0;
+    if (tactive && o < br.noct && r < d && y0 < a.h) {
+      int vmask = 0;
+#pragma unroll
+      for (int j = 0; j < OCT_PX; ++j) vmask |= (y0 + j * d < a.h && !(a.dbg & 8)) ? (1 << j) : 0;
+      e = 0x80000000u | ((unsigned)vmask << 8) | (unsigned)y0;
+    }
+    segtab[b * NT + tid] = e;     // read back by this thread only
+  }
   const double inv_n = 1.0 / ((double)hw * (double)a.Cin);   // mean and centred variance in fp64 (see ln_coeffs)
   auto coeffs = [&](int item, int par) {   // LayerNorm coefficients of the samples of `item` -> mr[par]
     if (tid < a.S) {
@@ -392,34 +436,29 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
     OCT_STAMP(4);
     // ---- the branches that read this octet ----
     const bool live = tactive && q < ns && !(a.dbg & 1);
-    float s1 = 0.f, s2 = 0.f;
+    float2 s1p = make_float2(0.f, 0.f), s2p = make_float2(0.f, 0.f);
     if (live) {
       const int Pmax = (q + 1) * a.SHW - 1;
       for (int b = 0; b < a.n_br; ++b) {
+        const unsigned e = segtab[b * NT + tid];
+        if (!(e >> 31)) continue;
         const OctBranch& br = a.br[b];
-        if (o >= br.noct) continue;
-        // slot -> (column x, row residue r mod dil, segment k): rows y0 + j dil with y0 = r + 4 k dil
-        const int d = br.dil;
-        const int t = sl / a.w, x = sl - t * a.w;
-        const int r = t / br.nsr, k = t - r * br.nsr;
-        const int y0 = r + OCT_PX * k * d;
-        if (r >= d || y0 >= a.h) continue;
-        int vmask = 0;
-#pragma unroll
-        for (int j = 0; j < OCT_PX; ++j) vmask |= (y0 + j * d < a.h && !(a.dbg & 8)) ? (1 << j) : 0;
+        const int d = br.dil, x = seg_x;
+        const int y0 = (int)(e & 255u), vmask = (int)((e >> 8) & 127u);
         const int P0 = q * a.SHW + (y0 - d + a.halo) * a.SW + x - d + a.halo;
         const float* wb = w_s + br.w_smem;
         float* dptr = out_n + ((long long)(b0 + q) * hw + (long long)y0 * a.w + x) * a.Cout + br.out_off;
         const long long jstride = (long long)d * a.w * a.Cout;
         const bool vec8 = a.vec8 && !(br.out_off & 7);
         switch (br.G) {
-          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2, (a.dbg & 32) != 0); break;
-          case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
-          case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
-          default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1, s2); break;
+          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p, (a.dbg & 32) != 0); break;
+          case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
+          case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
+          default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
         }
       }
     }
+    const float s1 = s1p.x + s1p.y, s2 = s2p.x + s2p.y;
     if (dbl && ctid >= 0 && ctid < a.S && next < a.n_items && !(a.dbg & 16)) {
       float sc = 1.f, sh = 0.f;
       if (a.ln && next * a.S + ctid < a.B) {
@@ -520,7 +559,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (n_oct > OCT_MAX || n_oct < 1) return CNF_NOT_ELIGIBLE;
   const int hw = g.h * g.w;
   a.halo = halo; a.SW = g.w + 2 * halo; a.SHW = (g.h + 2 * halo) * a.SW; a.n_oct = n_oct;
-  if ((long long)a.SHW >= 65536 / 1) return CNF_NOT_ELIGIBLE;                 // pt[] is 16 bit
+  if ((long long)a.SHW >= 65536 / 1 || g.h > 255) return CNF_NOT_ELIGIBLE;     // pt[] is 16 bit, y0 of a segment 8 bit
   a.nsps = 0;
   for (int i = 0; i < g.n_br; ++i) {
     const int d = a.br[i].dil;
@@ -534,7 +573,8 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (!nbuf_env) nbuf_env = knob_int("OCT_NBUF", 2) == 1 ? 1 : 2;
   a.nbuf = nbuf_env;
   auto smem_for = [&](int S) {
-    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * OCT_MAXT;
+    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * OCT_MAXT +
+               (size_t)g.n_br * OCT_MAXT;
     return f * sizeof(float) + (((size_t)hw * 2 + 15) & ~(size_t)15);
   };
   if (a.tps > OCT_MAXT || smem_for(1) > budget) return CNF_NOT_ELIGIBLE;

@@ -1648,12 +1648,12 @@ static int launch_pw_t(GemmArgs a, cudaStream_t st) {
 }
 
 // warp-specialised persistent tcgen05 1x1 conv; CNF_NOT_ELIGIBLE when the resident-W image does not fit
-template <int N, int TW, int NST>
+template <int N, int TW, int NST, bool PADN>
 static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   const int nchunks = (a.K + 31) / 32;
   const size_t smem = ((size_t)NST * 2 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
   if (smem > 225 * 1024) return CNF_NOT_ELIGIBLE;
-  auto kern = pw_tc3_kernel<N, TW, NST>;
+  auto kern = pw_tc3_kernel<N, TW, NST, PADN>;
   static SmemAttrCache cache;
   CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   int n_sm = 0;
@@ -1667,22 +1667,38 @@ static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
 }
 
 // more operand stages decouple the transform warps from the MMA round trip; use as many as shared memory allows
-template <int N>
-static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
+template <int N, bool PADN>
+static int launch_pw_tc3_p(const GemmArgs& a, cudaStream_t st) {
   static int nst = -1;
   if (nst < 0) nst = knob_int("PW_NST", 4);
   int rc = CNF_NOT_ELIGIBLE;
-  if (nst >= 4) rc = launch_pw_tc3_tw<N, 8, 4>(a, st);
-  if (rc == CNF_NOT_ELIGIBLE && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3>(a, st);
-  if (rc == CNF_NOT_ELIGIBLE) rc = launch_pw_tc3_tw<N, 8, 2>(a, st);
+  if (nst >= 4) rc = launch_pw_tc3_tw<N, 8, 4, PADN>(a, st);
+  if (rc == CNF_NOT_ELIGIBLE && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3, PADN>(a, st);
+  if (rc == CNF_NOT_ELIGIBLE) rc = launch_pw_tc3_tw<N, 8, 2, PADN>(a, st);
   return rc;
 }
 
-// 1x1 conv dispatcher: tcgen05 3xTF32 kernel when the shape fits its UMMA tile family (N in {16,32,64}, K % 8 == 0);
-// otherwise (or when a.paths excludes it) the FFMA multi-sample kernel (K % 4 == 0), then the generic GEMM kernel.
+template <int N>
+static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
+  return a.N == N ? launch_pw_tc3_p<N, false>(a, st) : launch_pw_tc3_p<N, true>(a, st);
+}
+
+// tcgen05 3xTF32 kernel on the smallest UMMA tile (N = 16, 32, 64, 128 columns) that holds the a.N outputs (the extra
+// columns are zero weights and are not stored); CNF_NOT_ELIGIBLE when the shape is outside the tile family
+static int launch_pw_tc3(const GemmArgs& a, cudaStream_t st) {
+  if (a.K % 8 || a.N % 8 || a.N < 8 || a.N > 128) return CNF_NOT_ELIGIBLE;
+  if (a.N <= 16) return a.N == 16 ? launch_pw_tc3_t<16>(a, st) : CNF_NOT_ELIGIBLE;   // N = 8: no 8-column epilogue split
+  if (a.N <= 32) return launch_pw_tc3_t<32>(a, st);
+  if (a.N <= 64) return launch_pw_tc3_t<64>(a, st);
+  return launch_pw_tc3_t<128>(a, st);
+}
+
+// 1x1 conv dispatcher: tcgen05 3xTF32 kernel when the shape fits its UMMA tile family (N <= 128, K % 8 == 0, resident
+// weights fit shared memory); otherwise (or when a.paths excludes it) the FFMA multi-sample kernel (K % 4 == 0), then
+// the generic GEMM kernel.
 static int launch_pw(const GemmArgs& a, cudaStream_t st) {
-  if (!(a.paths & CNF_PATH_NO_TCGEN05) && a.K % 8 == 0 && (a.N == 64 || a.N == 32 || a.N == 16)) {
-    const int rc = a.N == 64 ? launch_pw_tc3_t<64>(a, st) : a.N == 32 ? launch_pw_tc3_t<32>(a, st) : launch_pw_tc3_t<16>(a, st);
+  if (!(a.paths & CNF_PATH_NO_TCGEN05)) {
+    const int rc = launch_pw_tc3(a, st);
     if (rc != CNF_NOT_ELIGIBLE) return rc;
   }
   if (!(a.paths & CNF_PATH_NO_PW_FFMA) && a.K % 4 == 0 && a.B <= 65535 * 8) {
@@ -2090,13 +2106,17 @@ int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, vo
 // ---- backward-pass uses of the forward kernels (data gradients), called from bwd_kernels.cu ----
 // 1x1 conv: dA[2][B][hw][K] = dY[2][B][hw][N] * W^T   (W is [K][N] at w_off)
 int dgrad_pw(const float* params, long long net_stride, long long w_off, const float* dY, float* dA, int B, int hw,
-             int K, int N, void* stream) {
+             int K, int N, void* stream, int paths) {
   GemmArgs a = {};
   a.in = dY; a.in_net_stride = (long long)B * hw * N;
   a.params = params; a.net_stride = net_stride; a.w_off = w_off;
   a.out = dA; a.out_net_stride = (long long)B * hw * K;
   a.B = B; a.hw = hw; a.K = N; a.N = K; a.ln = 0;
-  a.raw_in = 1; a.w_trans = 1; a.ldw = N; a.no_bias = 1;
+  a.raw_in = 1; a.w_trans = 1; a.ldw = N; a.no_bias = 1; a.paths = paths;
+  if (!(paths & CNF_PATH_NO_TCGEN05)) {   // the forward tensor-core kernel with the weights read transposed
+    const int rc = launch_pw_tc3(a, (cudaStream_t)stream);
+    if (rc != CNF_NOT_ELIGIBLE) return rc;
+  }
   return launch_gemm<false>(a, (cudaStream_t)stream);
 }
 

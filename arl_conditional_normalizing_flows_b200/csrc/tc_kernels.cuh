@@ -121,6 +121,16 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 columns without the wait (pair with tmem_ld_wait): lets two loads be in flight
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 template <>
 __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
   tmem_ld<16>(taddr, v);
@@ -182,17 +192,23 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {   // 256-bit loa
                : "l"(p));
 }
 
-template <int N, int TW, int NST>   // TW transform warps: 8 (4 samples per thread) or 16 (2 per thread); NST operand stages
+// TW = 8 transform warps (one 16-byte unit of each of the 4 samples per thread and K-chunk); NST operand stages; PADN:
+// a.N < N outputs (the other columns of the UMMA tile are zero weights and are not stored).
+// Measured and dropped (profiles/r02_summary.md): two transform groups on alternate K-chunks (16 + 1 + 4 + 2 warps): the four
+// epilogue warps then hold a TMEM buffer across their first store pass and the tile period grows from 6.0 k to 7.5 k cycles.
+template <int N, int TW, int NST, bool PADN = false>
 __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
   constexpr int NTT = 256;                     // 16-byte units per sample and K-chunk (32 rows x 8 quads)
   constexpr int NTH = TW * 32;                 // transform threads
   constexpr int SPT = 4 * 256 / NTH;           // samples per transform thread
+  static_assert(SPT == 4, "8 transform warps");
   constexpr int S = 4, PT = 32, M = 128;
   constexpr int KC = 32;
   constexpr int DEPTH = 3;
   constexpr int A_ST = M * KC, B_ST = N * KC;
   constexpr int RAW = 6 * NTT * 4;
-  constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  // one accumulator buffer = 2 N columns: [0, N) hi*hi + lo*hi, [N, 2N) hi*lo (the epilogue adds the halves); two buffers
+  constexpr uint32_t TMEM_COLS = 4 * N < 32 ? 32 : 4 * N;
   extern __shared__ __align__(128) float tc3_smem[];
   const int nchunks = (a.K + KC - 1) / KC;
   float* opsA = tc3_smem;                      // [NST stages][hi, lo][A_ST]
@@ -202,7 +218,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
   constexpr int EWARPS = 8;                     // epilogue warps: two per TMEM lane quarter, half of the columns each
   __shared__ __align__(8) uint64_t bar_full[NST], bar_free[NST], bar_tfull[2], bar_tempty[2], raw_full[DEPTH], raw_free[DEPTH];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) float mr[2][S][2];
+  __shared__ __align__(16) float2 cf_s[DEPTH][S];   // LayerNorm coefficients (rstd, -mean rstd) of the tile whose first chunk sits in raw slot i
   __shared__ __align__(16) float bias_s[N];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -229,7 +245,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (wid == TW) tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid < N) bias_s[tid] = P[a.b_off + tid];
+  if (tid < N) bias_s[tid] = (tid < a.N && !a.no_bias) ? P[a.b_off + tid] : 0.f;   // N >= a.N: zero-padded output columns
   // resident B operand (all threads help)
   {
     const float* Wg = P + a.w_off;
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
       const int ng = r % (N / 8), kq = r / (N / 8);
       const int n = ng * 8 + bnr, k = c * KC + kq * 4 + bkr;
       float w = 0.f;
-      if (k < a.K) w = Wg[(long long)k * a.N + n];
+      if (k < a.K && n < a.N) w = a.w_trans ? Wg[(long long)n * a.ldw + k] : Wg[(long long)k * a.N + n];
       float h, l;
       tf32_split(w, h, l);
       const int off = c * 2 * B_ST + 4 * (bnr + 8 * kq + (KC / 4) * 8 * ng) + bkr;
@@ -255,52 +271,27 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
 
   if (wid < TW) {
     // =============================== transform warps ===============================
-    const int wl = wid & 7, sh0 = (wid >> 3) * SPT;   // warp inside its group of 8; first sample this thread handles
+    const int wl = wid & 7, sh0 = 0;           // transform warp index; first sample this thread handles
     const int ar = lane & 7, akq = (lane >> 3) + 4 * (wl >> 2);
     const int ap = 8 * (wl & 3) + ar;
     // unit (row ap, quad akq) was written by a producer thread at the swizzled position below (bank-conflict-free
     // for 8 lanes = 8 rows of one quad)
     const int runit = ap * 8 + (akq ^ (ap & 7));
+    const float slope = a.raw_in ? 1.f : CNF_LRELU_SLOPE;   // data-gradient use: the operand is taken as it is
     int gi = 0, slot = 0, r = cta;
-    // LayerNorm coefficients: every thread keeps (rstd, -mean*rstd) of its own samples in registers; the (sum, sumsq)
-    // pairs of tile tl+1 are loaded while tile tl is transformed (no shared copy, no barrier between tiles)
-    const double inv_n = 1.0 / ((double)a.hw * (double)a.K);   // mean and centred variance in fp64 (see ln_coeffs)
-    double st_s[SPT], st_q[SPT];
+    // LayerNorm coefficients (rstd, -mean rstd) of the tile's samples: computed once per tile by four producer threads (fp64
+    // mean / centred variance) and handed over in shared memory with the tile's first chunk -- no global loads, no fp64 and
+    // no extra live registers in the transform warps (the per-thread version cost ~1400 cycles per tile, clock stamps)
     // tile index r = tq * tiles_p + tp is advanced by ncta without divisions
     const int dq = ncta / tiles_p, dp = ncta - dq * tiles_p;
     int tq = cta / tiles_p, tp = cta - tq * tiles_p;
-    auto load_stats = [&](int tq_next) {
-      const int s0n = tq_next * S;
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) {
-        st_s[j] = 0.0; st_q[j] = 1.0;
-        if (a.ln && s0n + sh0 + j < a.B) {
-          const double* sp = a.stats_in + 2 * ((long long)net * a.B + s0n + sh0 + j);
-          st_s[j] = sp[0];
-          st_q[j] = sp[1];
-        }
-      }
-    };
-    if (my_tiles > 0) load_stats(tq);
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
       const int s0 = tq * S, p0 = tp * PT;
       const int ns = min(S, a.B - s0);
       tq += dq; tp += dp;
       if (tp >= tiles_p) { tp -= tiles_p; ++tq; }
-      float2 cf[SPT];
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) {
-        // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence: four ~200-instruction dependent chains per tile sat on
-        // the critical path between tiles (measured 1400 cycles); the difference is ~1e-7 relative
-        const double md = st_s[j] * inv_n;
-        const float m_ = (float)md;
-        const float var = fmaxf((float)(st_q[j] * inv_n - md * md), 0.f);
-        const float sc = rsqrtf(var + (float)CNF_LN_EPS);
-        cf[j] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
-      }
+      float2 cf[SPT] = {};
       if (tid == 0) TC3_STAMP(0, gi, 1);
-      if (tl + 1 < my_tiles) load_stats(tq);        // in flight during this tile
-      if (tid == 0) TC3_STAMP(0, gi, 2);
       const bool pv = (p0 + ap) < a.hw;
       for (int c = 0; c < nchunks; ++c, ++gi) {
         const int stage = gi % NST;
@@ -309,8 +300,13 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
         const int kc = min(KC, a.K - c * KC);
         if (tid == 0) TC3_STAMP(0, gi, 0);
         mbar_wait(&raw_full[slot], (gi / DEPTH) & 1);   // the producer warps' copies of chunk gi have landed
+        if (c == 0) {
+          const float4 c01 = *reinterpret_cast<const float4*>(&cf_s[slot][0]), c23 = *reinterpret_cast<const float4*>(&cf_s[slot][2]);
+          cf[0] = make_float2(c01.x, c01.y); cf[1] = make_float2(c01.z, c01.w);
+          cf[2] = make_float2(c23.x, c23.y); cf[3] = make_float2(c23.z, c23.w);
+        }
         if (tid == 0) TC3_STAMP(0, gi, 3);
-        if (gi >= NST) mbar_wait(&bar_free[stage], ((gi / NST) - 1) & 1);
+        if (gi >= NST) mbar_wait(&bar_free[stage], ((gi / NST) - 1) & 1);   // the MMAs that read this operand stage are done
         if (tid == 0) TC3_STAMP(0, gi, 4);
         if (akq * 4 < kc && !(a.dbg & 32)) {
           // every shared-memory read of this chunk is issued up front into its own registers (no branches between
@@ -330,10 +326,10 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
             const bool ok = pv && s < ns && !(a.dbg & 8);
             const float sc = cf[j].x, sh = cf[j].y;
             float v[4];
-            v[0] = fmaxf(xv[j].x, CNF_LRELU_SLOPE * xv[j].x);
-            v[1] = fmaxf(xv[j].y, CNF_LRELU_SLOPE * xv[j].y);
-            v[2] = fmaxf(xv[j].z, CNF_LRELU_SLOPE * xv[j].z);
-            v[3] = fmaxf(xv[j].w, CNF_LRELU_SLOPE * xv[j].w);
+            v[0] = fmaxf(xv[j].x, slope * xv[j].x);
+            v[1] = fmaxf(xv[j].y, slope * xv[j].y);
+            v[2] = fmaxf(xv[j].z, slope * xv[j].z);
+            v[3] = fmaxf(xv[j].w, slope * xv[j].w);
             v[0] = fmaf(fmaf(v[0], sc, sh), g.x, be.x);
             v[1] = fmaf(fmaf(v[1], sc, sh), g.y, be.y);
             v[2] = fmaf(fmaf(v[2], sc, sh), g.z, be.z);
@@ -370,11 +366,34 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
     const float* bet = P + a.be_off;
     const int pt = tid - (TW + 1 + EWARPS) * 32;
     int idx = 0, pslot = 0, r = cta;
+    // threads 0-3: (sum, sumsq) of sample pt of the NEXT tile, loaded one tile ahead
+    const double inv_n = 1.0 / ((double)a.hw * (double)a.K);   // mean and centred variance in fp64 (see ln_coeffs)
+    double st_s = 0.0, st_q = 1.0;
+    auto load_stats = [&](int rt) {
+      st_s = 0.0; st_q = 1.0;
+      const int sn = (rt / tiles_p) * S + pt;
+      if (a.ln && pt < S && rt < ntiles && sn < a.B) {
+        const double* sp = a.stats_in + 2 * ((long long)net * a.B + sn);
+        st_s = sp[0];
+        st_q = sp[1];
+      }
+    };
+    load_stats(r);
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
       const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
       const int ns = min(S, a.B - s0);
       for (int c = 0; c < nchunks; ++c, ++idx) {
         if (idx >= DEPTH) mbar_wait(&raw_free[pslot], ((idx / DEPTH) - 1) & 1);
+        if (c == 0 && pt < S) {
+          // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence; the difference is ~1e-7 relative
+          const double md = st_s * inv_n;
+          const float m_ = (float)md;
+          const float var = fmaxf((float)(st_q * inv_n - md * md), 0.f);
+          const float sc = rsqrtf(var + (float)CNF_LN_EPS);
+          cf_s[pslot][pt] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
+          load_stats(r + ncta);
+          __threadfence_block();   // ordered before this thread's arrival on raw_full[pslot] below
+        }
         const int k0 = c * KC, kc = min(KC, a.K - k0);
         float* dst = raw + pslot * RAW;
 #pragma unroll
@@ -402,7 +421,10 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
   } else if (wid == TW) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(N);
+      // B = [hi rows | lo rows] is one K-major operand of 2 N rows (the two blocks are adjacent and share the layout), so
+      // hi(A) * [hi(B) | lo(B)] is ONE instruction of width 2 N and the A operand is read twice per K-step instead of
+      // three times; lo(A) * hi(B) accumulates into the first N columns
+      constexpr uint32_t idesc2 = umma_idesc_tf32(2 * N), idesc1 = umma_idesc_tf32(N);
       constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
       const uint32_t a_base = smem_u32(opsA), b_base = smem_u32(Bres);
       int gi = 0;
@@ -410,7 +432,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
         const int buf = tl & 1;
         if (tl >= 2) mbar_wait(&bar_tempty[buf], ((tl >> 1) - 1) & 1);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t d_addr = tmem_d + buf * N;
+        const uint32_t d_addr = tmem_d + buf * 2 * N;
         for (int c = 0; c < nchunks; ++c, ++gi) {
           const int stage = gi % NST;
           const int kc = min(KC, a.K - c * KC);
@@ -419,14 +441,14 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           TC3_STAMP(1, gi, 1);
           tc_fence_after();
           const uint32_t a_hi = a_base + stage * 2 * A_ST * 4, a_lo = a_hi + A_ST * 4;
-          const uint32_t b_hi = b_base + c * 2 * B_ST * 4, b_lo = b_hi + B_ST * 4;
+          const uint32_t b_hi = b_base + c * 2 * B_ST * 4;
+          // the descriptors of a K-step differ from those of step 0 only in the start-address field (16-byte units;
+          // shared-memory addresses stay below 2^18, so the 14-bit field never carries): one 64-bit add each
+          const uint64_t dah0 = umma_desc(a_hi, LBO, SBO), dal0 = umma_desc(a_lo, LBO, SBO), dbh0 = umma_desc(b_hi, LBO, SBO);
           for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : kc / 8); ++ks) {
-            const uint32_t adv = ks * 2 * LBO;
-            const uint64_t dah = umma_desc(a_hi + adv, LBO, SBO), dal = umma_desc(a_lo + adv, LBO, SBO);
-            const uint64_t dbh = umma_desc(b_hi + adv, LBO, SBO), dbl = umma_desc(b_lo + adv, LBO, SBO);
-            umma_tf32(d_addr, dah, dbh, idesc, (c | ks) != 0);
-            umma_tf32(d_addr, dal, dbh, idesc, 1);
-            umma_tf32(d_addr, dah, dbl, idesc, 1);
+            const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);
+            umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, (c | ks) != 0);
+            umma_tf32(d_addr, dal0 + adv, dbh0 + adv, idesc1, 1);
           }
           TC3_STAMP(1, gi, 2);
           umma_commit(&bar_free[stage]);
@@ -439,10 +461,12 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
     // =============================== epilogue warps ===============================
     // warp e: TMEM lane quarter (wid & 3) == sample index (PT == 32), column half e >> 2.  The accumulator values are
     // pulled into registers and the TMEM buffer is released BEFORE bias / residual / statistics / 256-bit stores.
-    constexpr int NH = N >= 32 ? N / 2 : N;      // columns per epilogue warp
+    constexpr bool SPLIT = EWARPS == 8 && N >= 32;   // two warps per lane quarter, half of the columns each
+    constexpr int NH = SPLIT ? N / 2 : N;        // columns per epilogue warp
+    constexpr int CH = NH > 32 ? 32 : NH;        // ... handled CH at a time (registers)
     const int quarter = wid & 3, half = (wid - (TW + 1)) >> 2;
-    const bool has_cols = N >= 32 || half == 0;
-    const int c0 = N >= 32 ? half * NH : 0;
+    const bool has_cols = SPLIT || half == 0;
+    const int c0 = SPLIT ? half * NH : 0;
     int r = cta;
     for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
       const int buf = tl & 1;
@@ -453,39 +477,65 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
       const long long row = ((long long)(s0 + quarter) * a.hw + egp) * a.N + c0;
       float* out_r = a.out + (long long)net * a.out_net_stride + row;
       const float* res_r = a.res ? a.res + (long long)net * a.out_net_stride + row : nullptr;
-      float rr[NH];                                // residual row segment: in flight while the MMAs of this tile run
+      // acc starts as the residual row segment (in flight while the MMAs of this tile run) or zero; the two accumulator
+      // halves are added to it 16 columns at a time (two tcgen05.ld in flight)
+      float acc[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) acc[j] = 0.f;
       if (res_r && erow) {
 #pragma unroll
-        for (int j = 0; j < NH; j += 8) ld8(res_r + j, rr + j);
+        for (int j = 0; j < CH; j += 8)
+          if (!PADN || c0 + j < a.N) ld8(res_r + j, acc + j);
       }
       if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 0);
       mbar_wait(&bar_tfull[buf], (tl >> 1) & 1);
       if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 1);
       tc_fence_after();
-      float v[NH];
-      if (has_cols && !(a.dbg & 16)) {
-#pragma unroll
-        for (int cb = 0; cb < NH; cb += 16)
-          tmem_ld<16>(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0 + cb), v + cb);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[buf]);   // accumulator buffer may be overwritten
-      if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 2);
       float s1 = 0.f, s2 = 0.f;
-      if (erow && !(a.dbg & 16)) {
 #pragma unroll
-        for (int j = 0; j < NH; j += 8) {
-          float o[8];
+      for (int cc = 0; cc < NH; cc += CH) {
+        if (cc > 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            o[i] = v[j + i] + bias_s[c0 + j + i];
-            if (res_r) o[i] += rr[j + i];
-            const float l = fmaxf(o[i], CNF_LRELU_SLOPE * o[i]);
-            s1 += l;
-            s2 = fmaf(l, l, s2);
+          for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+          if (res_r && erow) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 8)
+              if (!PADN || c0 + cc + j < a.N) ld8(res_r + cc + j, acc + j);
           }
-          if (!(a.dbg & 1)) st8(out_r + j, o);
+        }
+        if (has_cols && !(a.dbg & 16)) {
+          const uint32_t t0 = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 2 * N + c0 + cc);
+#pragma unroll
+          for (int cb = 0; cb < CH; cb += 16) {
+            uint32_t u0[16], u1[16];
+            tmem_ld16_nowait(t0 + cb, u0);
+            tmem_ld16_nowait(t0 + N + cb, u1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[cb + i] += __uint_as_float(u0[i]) + __uint_as_float(u1[i]);
+          }
+        }
+        if (cc + CH >= NH) {
+          // the accumulator values are in registers: release the TMEM buffer BEFORE bias / statistics / stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[buf]);   // accumulator buffer may be overwritten
+          if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 2);
+        }
+        if (erow && !(a.dbg & 16)) {
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            if (PADN && c0 + cc + j >= a.N) continue;      // zero-padded columns of the UMMA tile
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i] = acc[j + i] + bias_s[c0 + cc + j + i];
+              const float l = fmaxf(o[i], CNF_LRELU_SLOPE * o[i]);
+              s1 += l;
+              s2 = fmaf(l, l, s2);
+            }
+            if (!(a.dbg & 1)) st8(out_r + cc + j, o);
+          }
         }
       }
       if (a.stats_out) {
