@@ -127,6 +127,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_metric(kernel, key):
+    """one metric of the committed ncu capture of `kernel` (profiles/r02_traffic.json), or None"""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get(key)
+
+
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu capture
     (profiles/r02_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` report); None if absent."""
@@ -372,6 +380,14 @@ def run_ours(args):
                               "ms_per_launch": {"pw1": ms_pw1, "pw2_res": ms_pw2},
                               "algorithmic_bytes_per_launch": {"pw1": pw1_bytes, "pw2": pw2_bytes},
                               "traffic": {"pw1": tr_pw1, "pw2": tr_pw2},
+                              # tensor-pipe duty of the committed ncu capture (the north star's metric for the convs): the
+                              # kernel is paced by its operand hand-offs and HBM, not by the tensor pipe
+                              "ncu_tensor_pipe_active_pct_of_peak": {
+                                  w: ncu_metric(f"pw_tc3_kernel<64> {w}", "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed")
+                                  for w in ("pw1", "pw2")} if is_cfg2 else None,
+                              "ncu_umma_operand_read_active_pct": {
+                                  w: ncu_metric(f"pw_tc3_kernel<64> {w}", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
+                                  for w in ("pw1", "pw2")} if is_cfg2 else None,
                               "tflops_fp32_equivalent": pw_flops / ((ms_pw1 + ms_pw2) * 1e-3) / 1e12}}
 
     # ---- the stand-alone fused coupling-law kernel (mask addressing + affine law + per-sample log-det), the
