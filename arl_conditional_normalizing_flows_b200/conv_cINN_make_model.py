@@ -655,12 +655,12 @@ class cFlow:
             xy = self._check_io(uv, "xy")
             B = xy.shape[0]
             zy = torch.empty_like(xy)
-            ld = torch.empty(B, dtype=torch.float32, device=xy.device)
+            ld = torch.empty(B + 1, dtype=torch.float32, device=xy.device)   # [B] per sample + their batch mean
             br = Borrowed()
             check(lib.cnf_flow_forward(self._plan, br(xy), br(self.params), br(zy), br(ld),
                                        br(self._workspace(B)), stream_ptr()))
-            self.last_logdet_per_sample = ld
-            return zy, ld.mean()                             # Q1: scalar = batch mean of per-sample log-dets
+            self.last_logdet_per_sample = ld[:B]
+            return zy, ld[B]                                 # Q1: scalar = batch mean of per-sample log-dets (same launch)
         elif direction == -1:
             zy = self._check_io(uv, "zy")
             B = zy.shape[0]

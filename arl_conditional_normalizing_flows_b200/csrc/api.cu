@@ -133,7 +133,9 @@ int cnf_flow_forward(const cnf_plan* p, const DLManagedTensor* xy, const DLManag
   TRY(check_flow_tensor(p, X, "xy"));
   TRY(check_flow_tensor(p, Z, "zy"));
   const int64_t B = X.shape[0];
-  if (Z.shape[0] != B || L.shape[0] != B) return fail(CNF_ERR_SHAPE, "zy/logdet batch size differs from xy (%lld)", (long long)B);
+  const bool with_mean = L.shape[0] == B + 1;   // [B + 1]: the last element receives the batch mean (the reference's scalar)
+  if (Z.shape[0] != B || (L.shape[0] != B && !with_mean))
+    return fail(CNF_ERR_SHAPE, "zy/logdet batch size differs from xy (%lld; logdet may be [B] or [B + 1])", (long long)B);
   if (P.numel < p->param_count) return fail(CNF_ERR_SHAPE, "params: need %lld floats, got %lld", (long long)p->param_count, (long long)P.numel);
   if (W.bytes < cnf_plan_workspace_bytes(p, B)) return fail(CNF_ERR_WORKSPACE, "workspace: need %lld bytes, got %lld", (long long)cnf_plan_workspace_bytes(p, B), (long long)W.bytes);
   if (B == 0) return CNF_OK;
@@ -141,7 +143,7 @@ int cnf_flow_forward(const cnf_plan* p, const DLManagedTensor* xy, const DLManag
   double* ldacc = (double*)((char*)W.p + max_coupling_ws(p, B) + 256);
   TRY(cuda_rc((int)cudaMemsetAsync(ldacc, 0, sizeof(double) * B, (cudaStream_t)stream), "memset"));
   TRY(run_flow(p, P.p, Z.p, (int)B, 1, ldacc, W.p, stream));
-  return cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream), "logdet");
+  return cuda_rc(launch_logdet_finalize(ldacc, L.p, (int)B, stream, with_mean ? 1 : 0), "logdet");
 }
 
 int cnf_flow_inverse(const cnf_plan* p, const DLManagedTensor* zy, const DLManagedTensor* params, DLManagedTensor* xy,

@@ -155,7 +155,7 @@ int run_residual_block(const cnf_coupling* c, const float* params, int r, const 
                        void* stream);
 int run_pw_only(const cnf_coupling* c, const float* params, int B, int which, void* ws, void* stream);
 int launch_copy(const float* src, float* dst, int64_t n, void* stream);
-int launch_logdet_finalize(const double* acc, float* out, int B, void* stream);
+int launch_logdet_finalize(const double* acc, float* out, int B, void* stream, int with_mean = 0);
 int launch_prior_loss(const float* zy, const float* xy, const float* logdet, int B, int64_t HW, int D,
                       int x_d, double lambda_y, float* ll_z, float* ll_y, float* loss4, void* stream);
 int launch_coupling_law(const float* u, const float* s, const float* t, float* v, float* logdet, int B,

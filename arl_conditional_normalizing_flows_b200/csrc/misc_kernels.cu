@@ -283,13 +283,28 @@ int launch_prior_loss(const float* zy, const float* xy, const float* logdet, int
   return 0;
 }
 
-__global__ void logdet_finalize_kernel(const double* __restrict__ acc, float* __restrict__ out, int B) {
+// out[b] = per-sample log-det; with_mean: out[B] = their batch mean (the reference's scalar, M:1325-1326 / Q1), summed
+// in fp64 in a fixed order by block 0
+__global__ void __launch_bounds__(256) logdet_finalize_kernel(const double* __restrict__ acc, float* __restrict__ out, int B,
+                                                              int with_mean) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) out[i] = (float)acc[i];
+  if (with_mean && blockIdx.x == 0) {
+    __shared__ double part[256];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) s += (double)(float)acc[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[B] = (float)(part[0] / (double)B);
+  }
 }
 
-int launch_logdet_finalize(const double* acc, float* out, int B, void* stream) {
-  logdet_finalize_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(acc, out, B);
+int launch_logdet_finalize(const double* acc, float* out, int B, void* stream, int with_mean) {
+  logdet_finalize_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(acc, out, B, with_mean);
   return (int)cudaGetLastError();
 }
 

@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline (+ training) only: skips the eval-only / "
+                    "sampling-only / layer-per-kernel / strong-scaling side measurements (multi-GPU lines of the other configs)")
     return ap.parse_args()
 
 
@@ -309,16 +311,18 @@ def run_ours(args):
         sampler.start()
     ms_total = timed(step_device, K, Wm)
     clocks = sampler.stop() if rank == 0 else None
-    ms_eval = timed(lambda i: model.log_loss(xs_d[i % NBUF]), K, 1)
-    ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
     ms_e2e = timed(step_e2e, K, 2)
-    # the same step with every layer on the layer-per-kernel path (what the activation-resident launches replace)
-    model.set_fusion(0)
-    ms_unfused = timed(step_device, K, 1)
-    model.set_fusion(1)
-    # strong scaling: the config's batch as the GLOBAL batch, split over the ranks
     Bs = max(1, B // world)
-    ms_strong = timed(lambda i: (model.log_loss(xs_d[i % NBUF][:Bs]), model(zs_d[i % NBUF][:Bs], -1)), K, 1)
+    ms_eval = ms_samp = ms_unfused = ms_strong = float("nan")
+    if not args.quick:
+        ms_eval = timed(lambda i: model.log_loss(xs_d[i % NBUF]), K, 1)
+        ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
+        # the same step with every layer on the layer-per-kernel path (what the activation-resident launches replace)
+        model.set_fusion(0)
+        ms_unfused = timed(step_device, K, 1)
+        model.set_fusion(1)
+        # strong scaling: the config's batch as the GLOBAL batch, split over the ranks
+        ms_strong = timed(lambda i: (model.log_loss(xs_d[i % NBUF][:Bs]), model(zs_d[i % NBUF][:Bs], -1)), K, 1)
 
     # ---- dominant kernel: the grouped dilated 3x3 convs of the first full-resolution channel layer (config 2: 28x28x64,
     # gconv_oct_kernel, all dilation branches in one launch; profiles/r02_summary.md), timed ALONE with CUDA events on the
@@ -446,13 +450,13 @@ def run_ours(args):
                        "weights": "trained-like random (SURVEY 8d W-rand; cFlow.randomize_weights, seed 0)",
                        "l2": "no explicit flush: each step streams the model's weights and the s/t-net activations of the "
                              f"full-resolution layers (> 126 MB L2 at this batch) and inputs rotate over {NBUF} distinct batches",
-                       "eval_images_per_s": B * world * K / (ms_eval * 1e-3),
-                       "sample_images_per_s": B * world * K / (ms_samp * 1e-3),
-                       "layer_per_kernel_path_images_per_s": imgs * K / (ms_unfused * 1e-3),
+                       "eval_images_per_s": None if args.quick else B * world * K / (ms_eval * 1e-3),
+                       "sample_images_per_s": None if args.quick else B * world * K / (ms_samp * 1e-3),
+                       "layer_per_kernel_path_images_per_s": None if args.quick else imgs * K / (ms_unfused * 1e-3),
                        "resident_layers": f"{sum(l.resident_kernel_eligible() for l in model.coupling_layers)} of "
                                           f"{len(model.coupling_layers)} coupling layers run as one activation-resident launch",
-                       "strong_scaling": {"global_batch": Bs * world, "batch_per_gpu": Bs,
-                                          "images_per_s": 2 * Bs * world * K / (ms_strong * 1e-3)},
+                       "strong_scaling": None if args.quick else {"global_batch": Bs * world, "batch_per_gpu": Bs,
+                                                                  "images_per_s": 2 * Bs * world * K / (ms_strong * 1e-3)},
                        "coupling_law_kernel": {"shape": [512, 128, 128, 4], "ms": ms_law, "GB/s": law_gbs,
                                                "frac_of_hbm_peak": law_gbs / hbm_peak, "bytes_per_element": 12},
                        "train_step": train,

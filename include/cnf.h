@@ -136,7 +136,8 @@ int cnf_coupling_set_kernel_paths(cnf_coupling* c, int excluded);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* cFlow.call(xy, direction=+1) (M:1743-1772): zy in the ORIGINAL (H,W,D) layout plus the PER-SAMPLE
- * log-det vector [B] (superset of the reference's batch-mean scalar, Q1: scalar = mean of it). */
+ * log-det vector [B] (superset of the reference's batch-mean scalar, Q1: scalar = mean of it).  logdet may also be
+ * [B + 1]: element B then receives that batch mean (fp64 sum in a fixed order), i.e. the scalar call(+1) returns. */
 int cnf_flow_forward(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
                      DLManagedTensor* zy, DLManagedTensor* logdet, DLManagedTensor* workspace,
                      void* stream);

@@ -135,3 +135,19 @@ def test_coupling_function_returns_the_two_networks(dev):
     assert np.abs(model_A(u1c_t).cpu().numpy() - A).max() / np.abs(A).max() < 1e-4
     assert np.abs(model_b(u1c_t).cpu().numpy() - b).max() / np.abs(b).max() < 1e-4
     assert set(model_A.get_weights()) == set(W['A']) and set(model_b.get_weights()) == set(W['b'])
+
+
+@pytest.mark.parametrize("B", [1, 7, 300])
+def test_call_forward_scalar_is_the_batch_mean_of_the_per_sample_logdets(dev, B):
+    """cFlow.call(xy, +1) returns (zy, scalar): the scalar (M:1325-1326, Q1) comes out of the same launch as the per-sample
+    vector (logdet [B + 1] through the C-ABI), not out of an eager reduction."""
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import cFlow
+    m = cFlow(io_shape=[8, 8, 2], x_d=1, squeeze_factor_block_list=[0, 1], ResNeXt_block_list=[1, 1],
+              num_kernels_list=[16, 16], cardinality_list=[2, 2], device=dev)
+    m.randomize_weights(seed=1)
+    xy = torch.randn(B, 8, 8, 2, generator=torch.Generator().manual_seed(B)).to(dev)
+    zy, ld = m(xy, 1)
+    ps = m.last_logdet_per_sample
+    assert ps.shape == (B,) and ld.dim() == 0
+    want = ps.double().mean().item()
+    assert abs(float(ld) - want) <= 1e-6 * max(1.0, abs(want))
