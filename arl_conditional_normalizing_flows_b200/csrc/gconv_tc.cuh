@@ -1,0 +1,257 @@
+// Grouped dilated 3x3 conv for WIDE groups (16 or 32 channels per group) as an implicit GEMM on the 5th-generation tensor
+// cores (tcgen05 / TMEM), sm_100a only.  Reference: grouped_convolution (conv_cINN_base_functions.py F:364-413) inside
+// dilated_residual_block (F:577-590) with add_common_layers (F:330-362) applied to its input.
+//
+// Where it is used: the builder-chosen hyper-parameters of BASELINE configs 4 and 5 give group widths of
+// 16 / 32 channels on the full-resolution layers (nk 64 / cardinality 4 or 2, nk 128 / 256 with cardinality 8).  Those
+// branches are dense enough for the tensor pipe: a 32 x 32 block per tap is 16 x the work per operand byte of the 8-wide
+// groups of config 2, which stay on the FFMA2 octet kernel (gconv_oct.cuh; DESIGN.md section 3 explains the split).
+//
+// One CTA item = (net, sample, group, 16 x 8 output pixels).  The input window (16 + 2 dil) x (8 + 2 dil) pixels x G channels
+// is read once from global memory, LReLU + LayerNorm are applied on the way (gamma / beta per element, zero outside the
+// image: Keras pads the NORMALISED tensor), and every value is split x = hi + lo (hi = TF32 truncation, exactly what
+// kind::tf32 reads) into two channel-planar shared-memory images: [4-channel chunk][window pixel][16 bytes].  In that
+// layout 8 consecutive window pixels of one chunk are one contiguous 128-byte UMMA core matrix (K-major, no swizzle), the
+// next image row is SBO = SW * 16 bytes further and the next channel chunk LBO = one plane further, so the A operand of
+// tap (ky, kx) is the SAME image addressed at start + ((ky dil) SW + kx dil) * 16 bytes: the nine taps are nine descriptor
+// offsets, nothing is gathered or copied.  Per tap and 8-channel K-step one thread issues hi(A) x [hi(W) | lo(W)] (width
+// 2 G) and lo(A) x hi(W) (width G): 3xTF32, fp32-exact to ~1e-6.  The 128 x G accumulator lives in TMEM; the epilogue adds the
+// two halves, the bias, accumulates the LayerNorm statistics of LReLU(out) for the consumer and stores G contiguous floats
+// per pixel.  The group's weights (9 taps, hi and lo) stay in shared memory while the CTA walks over its items.
+#pragma once
+
+namespace cnf {
+
+constexpr int GTC_TH = 16, GTC_TW = 8;     // output pixels of an item: 16 rows x 8 columns = the 128 rows of the UMMA tile
+constexpr int GTC_NT = 256;                // threads per CTA (8 warps: two per TMEM lane quarter in the epilogue)
+
+struct GtcArgs {
+  const float* in;            // [2][B][h][w][Cin]
+  float* out;                 // [2][B][h][w][Cout]
+  long long in_net_stride, out_net_stride;
+  const float* params;
+  long long net_stride, g_off, be_off, w_off, b_off;
+  const double* stats_in;
+  double* stats_out;
+  int B, h, w, Cin, Cout, ln;
+  int dil, groups, out_off;
+  int tiles_y, tiles_x, n_items;   // items per (net, group): B * tiles_y * tiles_x
+  int ctas_per_ng;                 // CTAs that share one (net, group)
+  int SW, NPX, NPXP;               // window width, window pixels, plane stride in pixels (= 1 mod 8: conflict-free chunk stores)
+};
+
+template <int G>
+__global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
+  constexpr int NQ = G / 4;                    // 4-channel chunks of the group
+  constexpr int WT = 2 * G * G;                // floats of one tap's weights: [hi rows | lo rows] x G inputs
+  constexpr uint32_t TMEM_COLS = 2 * G < 32 ? 32 : 2 * G;
+  extern __shared__ __align__(128) float gtc_smem[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float cf_s[2];
+  __shared__ __align__(16) float bias_s[G];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ng = blockIdx.x / a.ctas_per_ng, rank = blockIdx.x - ng * a.ctas_per_ng;
+  const int net = ng / a.groups, grp = ng - net * a.groups;
+  const int plane = a.NPXP * 4;                // floats per chunk plane
+  float* A_hi = gtc_smem;                      // [NQ][NPXP][4]
+  float* A_lo = A_hi + NQ * plane;
+  float* Bw = A_lo + NQ * plane;               // [9][hi | lo][G rows][G] K-major core-matrix layout
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid < G) bias_s[tid] = P[a.b_off + grp * G + tid];
+  // the group's weights W[tap][ci][co] -> B operand rows n = co, columns k = ci: 16-byte unit (n % 8) + 8 (k / 4) + 8 NQ (n / 8)
+  {
+    const float* Wg = P + a.w_off + (long long)grp * 9 * G * G;
+    for (int i = tid; i < 9 * G * G; i += GTC_NT) {
+      const int tap = i / (G * G), r = i - tap * G * G;
+      const int ci = r / G, co = r - ci * G;
+      float hi, lo;
+      tf32_split(Wg[i], hi, lo);
+      const int off = tap * WT + 4 * ((co & 7) + 8 * (ci >> 2) + 8 * NQ * (co >> 3)) + (ci & 3);
+      Bw[off] = hi;
+      Bw[off + G * G] = lo;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  const float* src_n = a.in + (long long)net * a.in_net_stride + grp * G;
+  float* out_n = a.out + (long long)net * a.out_net_stride + a.out_off + grp * G;
+  const float* gam = P + a.g_off + grp * G;
+  const float* bet = P + a.be_off + grp * G;
+  const int d = a.dil, SW = a.SW;
+  const int tiles = a.tiles_y * a.tiles_x;
+  const double n_ln = (double)a.h * (double)a.w * (double)a.Cin;
+  uint32_t phase = 0;
+
+  for (int it = rank; it < a.n_items; it += a.ctas_per_ng) {
+    const int b = it / tiles, t = it - b * tiles;
+    const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+    const int y0 = ty * GTC_TH, x0 = tx * GTC_TW;
+    if (tid == 0) {
+      float mean = 0.f, rstd = 1.f;
+      if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, n_ln, mean, rstd);
+      cf_s[0] = rstd;
+      cf_s[1] = -mean * rstd;
+    }
+    __syncthreads();                       // cf_s visible; the previous item's MMAs and TMEM reads are done (see below)
+    const float sc = cf_s[0], sh = cf_s[1];
+    // ---- window -> LReLU + LayerNorm -> hi / lo planes.  8 consecutive lanes fetch the NQ <= 8 chunks of one pixel
+    const float* src_b = src_n + (long long)b * a.h * a.w * a.Cin;
+    for (int u = tid; u < a.NPX * NQ; u += GTC_NT) {
+      const int q = u / NQ, c4 = u - q * NQ;
+      const int wy = q / SW, wx = q - wy * SW;
+      const int iy = y0 - d + wy, ix = x0 - d + wx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+        const long long e = ((long long)iy * a.w + ix) * a.Cin + 4 * c4;
+        v = ld4(src_b + e);
+        v.x = fmaxf(v.x, CNF_LRELU_SLOPE * v.x); v.y = fmaxf(v.y, CNF_LRELU_SLOPE * v.y);
+        v.z = fmaxf(v.z, CNF_LRELU_SLOPE * v.z); v.w = fmaxf(v.w, CNF_LRELU_SLOPE * v.w);
+        if (a.ln) {
+          const float4 g = ld4(gam + e), be = ld4(bet + e);
+          v.x = fmaf(fmaf(v.x, sc, sh), g.x, be.x);
+          v.y = fmaf(fmaf(v.y, sc, sh), g.y, be.y);
+          v.z = fmaf(fmaf(v.z, sc, sh), g.z, be.z);
+          v.w = fmaf(fmaf(v.w, sc, sh), g.w, be.w);
+        }
+      }
+      float4 hi, lo;
+      tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y);
+      tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
+      st4(A_hi + c4 * plane + q * 4, hi);
+      st4(A_lo + c4 * plane + q * 4, lo);
+    }
+    fence_async_smem();                    // generic-proxy writes -> async proxy (the tensor core reads shared memory)
+    tc_fence_before();
+    __syncthreads();
+    // ---- 9 taps x G / 8 K-steps x 2 MMAs, one thread
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc2 = umma_idesc_tf32(2 * G), idesc1 = umma_idesc_tf32(G);
+      const uint32_t lbo_a = (uint32_t)a.NPXP * 16u, sbo_a = (uint32_t)SW * 16u;
+      const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b0 = smem_u32(Bw);
+      const uint64_t dah0 = umma_desc(a_hi, lbo_a, sbo_a), dal0 = umma_desc(a_lo, lbo_a, sbo_a);
+      const uint64_t db0 = umma_desc(b0, 128u, (uint32_t)NQ * 128u);
+      bool first = true;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const uint32_t shift = (uint32_t)((ky * d) * SW + kx * d);          // window pixels = 16-byte units
+#pragma unroll
+        for (int ks = 0; ks < G / 8; ++ks) {
+          const uint64_t adv_a = (uint64_t)(shift + (uint32_t)(2 * ks) * (uint32_t)a.NPXP);
+          const uint64_t adv_b = (uint64_t)((uint32_t)(tap * WT * 4 + ks * 256) >> 4);
+          umma_tf32(tmem_d, dah0 + adv_a, db0 + adv_b, idesc2, first ? 0u : 1u);
+          umma_tf32(tmem_d, dal0 + adv_a, db0 + adv_b, idesc1, 1u);
+          first = false;
+        }
+      }
+      umma_commit(&bar_mma);
+    }
+    // ---- epilogue: TMEM lane = output pixel (row = lane / 8 of the quarter, column = lane % 8); warps w and w + 4 share
+    // the lane quarter w % 4 and take half of the G channels each
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      constexpr int NH = G / 2;
+      const int quarter = wid & 3, half = wid >> 2;
+      const int c0 = half * NH;
+      const int row = quarter * 4 + (lane >> 3), col = lane & 7;
+      const int oy = y0 + row, ox = x0 + col;
+      float s1 = 0.f, s2 = 0.f;
+      float acc[NH];
+      const uint32_t t0 = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+#pragma unroll
+      for (int cb = 0; cb < NH; cb += 8) {
+        float v0[8], v1[8];
+        tmem_ld<8>(t0 + cb, v0);
+        tmem_ld<8>(t0 + G + cb, v1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[cb + i] = v0[i] + v1[i] + bias_s[c0 + cb + i];
+      }
+      tc_fence_before();
+      if (oy < a.h && ox < a.w) {
+        float* o = out_n + (((long long)b * a.h + oy) * a.w + ox) * a.Cout + c0;
+#pragma unroll
+        for (int j = 0; j < NH; j += 4) {
+          st4(o + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float l = fmaxf(acc[j + i], CNF_LRELU_SLOPE * acc[j + i]);
+            s1 += l;
+            s2 = fmaf(l, l, s2);
+          }
+        }
+      }
+      if (a.stats_out) {
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+          double* so = a.stats_out + 2 * ((long long)net * a.B + b);
+          atomicAdd(so, (double)s1);
+          atomicAdd(so + 1, (double)s2);
+        }
+      }
+    }
+    // the next iteration's first __syncthreads orders these TMEM reads (and the completed MMAs' shared-memory reads) before
+    // the planes are overwritten and the accumulator is restarted
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// One branch with gin == gout in {16, 32}, ksize 3, forward only.  CNF_NOT_ELIGIBLE for anything else.
+static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
+  const GconvBranch& br = g.br[bi];
+  const int G = br.gin;
+  if (g.bwd || g.ks != 3 || br.gin != br.gout || !(G == 16 || G == 32) || br.in_off != 0) return CNF_NOT_ELIGIBLE;
+  if ((g.Cin % 4) || (g.Cout % 4) || (br.out_off % 4) || br.groups * G > g.Cin) return CNF_NOT_ELIGIBLE;
+  if ((((uintptr_t)g.in) & 15) || (((uintptr_t)g.out) & 15) || ((g.in_net_stride * 4) % 16) || ((g.out_net_stride * 4) % 16)) return CNF_NOT_ELIGIBLE;
+  GtcArgs a{};
+  a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
+  a.params = g.params; a.net_stride = g.net_stride; a.g_off = g.g_off; a.be_off = g.be_off;
+  a.w_off = br.w_off; a.b_off = br.b_off;
+  a.stats_in = g.stats_in; a.stats_out = g.stats_out;
+  a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
+  a.dil = br.dil; a.groups = br.groups; a.out_off = br.out_off;
+  a.tiles_y = (g.h + GTC_TH - 1) / GTC_TH;
+  a.tiles_x = (g.w + GTC_TW - 1) / GTC_TW;
+  a.n_items = g.B * a.tiles_y * a.tiles_x;
+  a.SW = GTC_TW + 2 * br.dil;
+  a.NPX = (GTC_TH + 2 * br.dil) * a.SW;
+  a.NPXP = ((a.NPX + 7) & ~7) + 1;
+  // descriptor fields are 14 bits of 16-byte units
+  if ((long long)a.NPXP >= 16384 || a.SW >= 16384) return CNF_NOT_ELIGIBLE;
+  const size_t smem = ((size_t)2 * (G / 4) * a.NPXP * 4 + (size_t)9 * 2 * G * G) * sizeof(float);
+  if (smem > 200 * 1024) return CNF_NOT_ELIGIBLE;
+  int n_sm = 0;
+  CU_TRY((cudaError_t)device_sm_count(&n_sm));
+  const int ngs = 2 * br.groups;
+  a.ctas_per_ng = std::max(1, std::min(a.n_items, (2 * n_sm + ngs - 1) / ngs));   // ~2 CTAs per SM: phases of co-resident CTAs overlap
+  const int grid = ngs * a.ctas_per_ng;
+  if (G == 16) {
+    static SmemAttrCache cache;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)gconv_tc_kernel<16>, smem, cache));
+    gconv_tc_kernel<16><<<grid, GTC_NT, smem, st>>>(a);
+  } else {
+    static SmemAttrCache cache;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)gconv_tc_kernel<32>, smem, cache));
+    gconv_tc_kernel<32><<<grid, GTC_NT, smem, st>>>(a);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace cnf

@@ -1791,6 +1791,7 @@ static int launch_gconv_ffma(GconvArgs a, cudaStream_t st);
 
 }  // namespace cnf
 #include "gconv_oct.cuh"
+#include "gconv_tc.cuh"
 namespace cnf {
 
 static int launch_gconv(GconvArgs a, cudaStream_t st) {
@@ -1802,7 +1803,9 @@ static int launch_gconv(GconvArgs a, cudaStream_t st) {
   GconvArgs rest = a;
   rest.n_br = 0;
   for (int i = 0; i < a.n_br; ++i) {
-    const int rc = (a.paths & CNF_PATH_NO_BRANCH) ? CNF_NOT_ELIGIBLE : launch_gconv3_branch(a, i, st);
+    // groups of 16 / 32 channels: implicit GEMM on the tensor cores (gconv_tc.cuh); narrower groups: FFMA2 per-branch kernel
+    int rc = (a.paths & CNF_PATH_NO_TCGEN05) ? CNF_NOT_ELIGIBLE : launch_gconv_tc_branch(a, i, st);
+    if (rc == CNF_NOT_ELIGIBLE) rc = (a.paths & CNF_PATH_NO_BRANCH) ? CNF_NOT_ELIGIBLE : launch_gconv3_branch(a, i, st);
     if (rc == CNF_NOT_ELIGIBLE) rest.br[rest.n_br++] = a.br[i];
     else if (rc != 0) return rc;
   }

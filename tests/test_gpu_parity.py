@@ -141,6 +141,10 @@ LAYER_CASES = [
     ([16, 16, 8], 1, 2, 4, 32, [1, 2], True),     # (8,8,16) nk 16: c1 = 16, c2 = 16 -> layer-per-kernel path
     ([16, 16, 6], 2, 2, 4, 32, [1, 2, 4], True),  # (16,16,3) nk 32, groups 8/4/2
     ([16, 16, 5], 2, 1, 2, 16, [1, 2], True),     # odd depth through the resident kernel: c1 = 3, c2 = 2
+    # groups of 16 / 32 channels: the tcgen05 implicit-GEMM grouped conv (gconv_tc.cuh), configs 4 / 5 layer shapes
+    ([64, 64, 6], 2, 1, 4, 64, [1, 2, 4, 8], True),   # config-4 (light) channel layer: groups of 16 / 8 / 4 / 2
+    ([32, 32, 4], 2, 2, 2, 64, [1, 2], True),         # groups of 32 (dil 1) and 16 (dil 2): config-5 (light) widths
+    ([20, 12, 4], 2, 1, 2, 32, [1, 2], True),         # ragged 16 x 8 tiles (20 rows, 12 columns), groups of 16
 ]
 
 
