@@ -23,7 +23,8 @@
 namespace cnf {
 
 constexpr int GTC_TH = 16, GTC_TW = 8;     // output pixels of an item: 16 rows x 8 columns = the 128 rows of the UMMA tile
-constexpr int GTC_NT = 256;                // threads per CTA (8 warps: two per TMEM lane quarter in the epilogue)
+constexpr int GTC_WT = 8;                  // worker warps (transform + epilogue: two per TMEM lane quarter)
+constexpr int GTC_NT = (GTC_WT + 1) * 32;  // + one warp whose lane 0 issues the MMAs
 
 struct GtcArgs {
   const float* in;            // [2][B][h][w][Cin]
@@ -40,24 +41,27 @@ struct GtcArgs {
   int SW, NPX, NPXP;               // window width, window pixels, plane stride in pixels (= 1 mod 8: conflict-free chunk stores)
 };
 
+// The item loop is software-pipelined over two plane buffers: while the tensor core works through the 9 x G / 8 x 2 MMAs
+// of item i (asynchronous, issued by lane 0 of the extra warp), the eight worker warps transform the window of item i + 1
+// into the other buffer; they then wait for the MMAs' mbarrier, read the accumulator and store item i.
 template <int G>
 __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
   constexpr int NQ = G / 4;                    // 4-channel chunks of the group
   constexpr int WT = 2 * G * G;                // floats of one tap's weights: [hi rows | lo rows] x G inputs
+  constexpr int NW = GTC_WT * 32;              // worker threads
   constexpr uint32_t TMEM_COLS = 2 * G < 32 ? 32 : 2 * G;
   extern __shared__ __align__(128) float gtc_smem[];
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_slot;
-  __shared__ float cf_s[2];
   __shared__ __align__(16) float bias_s[G];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ng = blockIdx.x / a.ctas_per_ng, rank = blockIdx.x - ng * a.ctas_per_ng;
   const int net = ng / a.groups, grp = ng - net * a.groups;
   const int plane = a.NPXP * 4;                // floats per chunk plane
-  float* A_hi = gtc_smem;                      // [NQ][NPXP][4]
-  float* A_lo = A_hi + NQ * plane;
-  float* Bw = A_lo + NQ * plane;               // [9][hi | lo][G rows][G] K-major core-matrix layout
+  const int bufsz = 2 * NQ * plane;            // floats per buffer: hi planes, lo planes
+  float* Abuf = gtc_smem;                      // [2 buffers][hi | lo][NQ][NPXP][4]
+  float* Bw = Abuf + 2 * bufsz;                // [9][hi | lo][G rows][G] K-major core-matrix layout
 
   const float* P = a.params + (long long)net * a.net_stride;
   if (tid == 0) {
@@ -79,11 +83,6 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
       Bw[off + G * G] = lo;
     }
   }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = tmem_slot;
 
   const float* src_n = a.in + (long long)net * a.in_net_stride + grp * G;
   float* out_n = a.out + (long long)net * a.out_net_stride + a.out_off + grp * G;
@@ -92,79 +91,104 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
   const int d = a.dil, SW = a.SW;
   const int tiles = a.tiles_y * a.tiles_x;
   const double n_ln = (double)a.h * (double)a.w * (double)a.Cin;
-  uint32_t phase = 0;
 
-  for (int it = rank; it < a.n_items; it += a.ctas_per_ng) {
+  // window of item `it` -> LReLU + LayerNorm -> hi / lo planes of buffer `buf`; 8 consecutive lanes fetch the NQ <= 8 chunks
+  // of one pixel (worker threads only)
+  auto transform = [&](int it, int buf) {
     const int b = it / tiles, t = it - b * tiles;
     const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
     const int y0 = ty * GTC_TH, x0 = tx * GTC_TW;
-    if (tid == 0) {
-      float mean = 0.f, rstd = 1.f;
-      if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, n_ln, mean, rstd);
-      cf_s[0] = rstd;
-      cf_s[1] = -mean * rstd;
-    }
-    __syncthreads();                       // cf_s visible; the previous item's MMAs and TMEM reads are done (see below)
-    const float sc = cf_s[0], sh = cf_s[1];
-    // ---- window -> LReLU + LayerNorm -> hi / lo planes.  8 consecutive lanes fetch the NQ <= 8 chunks of one pixel
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln) ln_coeffs(a.stats_in, (long long)net * a.B + b, n_ln, mean, rstd);
+    const float sc = rstd, sh = -mean * rstd;
+    float* A_hi = Abuf + buf * bufsz;
+    float* A_lo = A_hi + NQ * plane;
     const float* src_b = src_n + (long long)b * a.h * a.w * a.Cin;
-    for (int u = tid; u < a.NPX * NQ; u += GTC_NT) {
-      const int q = u / NQ, c4 = u - q * NQ;
-      const int wy = q / SW, wx = q - wy * SW;
-      const int iy = y0 - d + wy, ix = x0 - d + wx;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
-        const long long e = ((long long)iy * a.w + ix) * a.Cin + 4 * c4;
-        v = ld4(src_b + e);
-        v.x = fmaxf(v.x, CNF_LRELU_SLOPE * v.x); v.y = fmaxf(v.y, CNF_LRELU_SLOPE * v.y);
-        v.z = fmaxf(v.z, CNF_LRELU_SLOPE * v.z); v.w = fmaxf(v.w, CNF_LRELU_SLOPE * v.w);
-        if (a.ln) {
-          const float4 g = ld4(gam + e), be = ld4(bet + e);
-          v.x = fmaf(fmaf(v.x, sc, sh), g.x, be.x);
-          v.y = fmaf(fmaf(v.y, sc, sh), g.y, be.y);
-          v.z = fmaf(fmaf(v.z, sc, sh), g.z, be.z);
-          v.w = fmaf(fmaf(v.w, sc, sh), g.w, be.w);
-        }
-      }
-      float4 hi, lo;
-      tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y);
-      tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
-      st4(A_hi + c4 * plane + q * 4, hi);
-      st4(A_lo + c4 * plane + q * 4, lo);
-    }
-    fence_async_smem();                    // generic-proxy writes -> async proxy (the tensor core reads shared memory)
-    tc_fence_before();
-    __syncthreads();
-    // ---- 9 taps x G / 8 K-steps x 2 MMAs, one thread
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idesc2 = umma_idesc_tf32(2 * G), idesc1 = umma_idesc_tf32(G);
-      const uint32_t lbo_a = (uint32_t)a.NPXP * 16u, sbo_a = (uint32_t)SW * 16u;
-      const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b0 = smem_u32(Bw);
-      const uint64_t dah0 = umma_desc(a_hi, lbo_a, sbo_a), dal0 = umma_desc(a_lo, lbo_a, sbo_a);
-      const uint64_t db0 = umma_desc(b0, 128u, (uint32_t)NQ * 128u);
-      bool first = true;
-#pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap - 3 * ky;
-        const uint32_t shift = (uint32_t)((ky * d) * SW + kx * d);          // window pixels = 16-byte units
+    constexpr int UB = 4;                                  // units in flight per thread (12 independent 128-bit loads)
+    const int n_units = a.NPX * NQ;
+    for (int u0 = tid; u0 < n_units; u0 += UB * NW) {
+      float4 v[UB], g[UB], be[UB];
+      int q[UB], c4[UB];
+      bool in[UB];
 #pragma unroll
-        for (int ks = 0; ks < G / 8; ++ks) {
-          const uint64_t adv_a = (uint64_t)(shift + (uint32_t)(2 * ks) * (uint32_t)a.NPXP);
-          const uint64_t adv_b = (uint64_t)((uint32_t)(tap * WT * 4 + ks * 256) >> 4);
-          umma_tf32(tmem_d, dah0 + adv_a, db0 + adv_b, idesc2, first ? 0u : 1u);
-          umma_tf32(tmem_d, dal0 + adv_a, db0 + adv_b, idesc1, 1u);
-          first = false;
-        }
+      for (int k = 0; k < UB; ++k) {
+        const int u = min(u0 + k * NW, n_units - 1);
+        q[k] = u / NQ; c4[k] = u - q[k] * NQ;
+        const int wy = q[k] / SW, wx = q[k] - wy * SW;
+        const int iy = y0 - d + wy, ix = x0 - d + wx;
+        in[k] = iy >= 0 && iy < a.h && ix >= 0 && ix < a.w;
+        const long long e = in[k] ? ((long long)iy * a.w + ix) * a.Cin + 4 * c4[k] : 0;
+        v[k] = ld4(src_b + e);
+        if (a.ln) { g[k] = ld4(gam + e); be[k] = ld4(bet + e); }
       }
-      umma_commit(&bar_mma);
+#pragma unroll
+      for (int k = 0; k < UB; ++k) {
+        if (u0 + k * NW >= n_units) continue;
+        float4 t = v[k];
+        t.x = fmaxf(t.x, CNF_LRELU_SLOPE * t.x); t.y = fmaxf(t.y, CNF_LRELU_SLOPE * t.y);
+        t.z = fmaxf(t.z, CNF_LRELU_SLOPE * t.z); t.w = fmaxf(t.w, CNF_LRELU_SLOPE * t.w);
+        if (a.ln) {
+          t.x = fmaf(fmaf(t.x, sc, sh), g[k].x, be[k].x);
+          t.y = fmaf(fmaf(t.y, sc, sh), g[k].y, be[k].y);
+          t.z = fmaf(fmaf(t.z, sc, sh), g[k].z, be[k].z);
+          t.w = fmaf(fmaf(t.w, sc, sh), g[k].w, be[k].w);
+        }
+        if (!in[k]) t = make_float4(0.f, 0.f, 0.f, 0.f);   // outside the image: Keras pads the NORMALISED tensor with zeros
+        float4 hi, lo;
+        tf32_split(t.x, hi.x, lo.x); tf32_split(t.y, hi.y, lo.y);
+        tf32_split(t.z, hi.z, lo.z); tf32_split(t.w, hi.w, lo.w);
+        st4(A_hi + c4[k] * plane + q[k] * 4, hi);
+        st4(A_lo + c4[k] * plane + q[k] * 4, lo);
+      }
     }
-    // ---- epilogue: TMEM lane = output pixel (row = lane / 8 of the quarter, column = lane % 8); warps w and w + 4 share
-    // the lane quarter w % 4 and take half of the G channels each
-    mbar_wait(&bar_mma, phase);
-    phase ^= 1;
-    tc_fence_after();
-    {
+  };
+
+  int it = rank, buf = 0;
+  if (it < a.n_items && wid < GTC_WT) transform(it, 0);
+  fence_async_smem();                      // generic-proxy writes (planes, weights) -> async proxy (the tensor core reads them)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  uint32_t phase = 0;
+
+  for (; it < a.n_items; it += a.ctas_per_ng, buf ^= 1) {
+    if (wid == GTC_WT) {
+      // ---- 9 taps x G / 8 K-steps x 2 MMAs on buffer `buf`, one thread
+      if (lane == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc2 = umma_idesc_tf32(2 * G), idesc1 = umma_idesc_tf32(G);
+        const uint32_t lbo_a = (uint32_t)a.NPXP * 16u, sbo_a = (uint32_t)SW * 16u;
+        const uint32_t a_hi = smem_u32(Abuf + buf * bufsz), a_lo = a_hi + (uint32_t)(NQ * plane * 4), b0 = smem_u32(Bw);
+        const uint64_t dah0 = umma_desc(a_hi, lbo_a, sbo_a), dal0 = umma_desc(a_lo, lbo_a, sbo_a);
+        const uint64_t db0 = umma_desc(b0, 128u, (uint32_t)NQ * 128u);
+        bool first = true;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          const uint32_t shift = (uint32_t)((ky * d) * SW + kx * d);          // window pixels = 16-byte units
+#pragma unroll
+          for (int ks = 0; ks < G / 8; ++ks) {
+            const uint64_t adv_a = (uint64_t)(shift + (uint32_t)(2 * ks) * (uint32_t)a.NPXP);
+            const uint64_t adv_b = (uint64_t)((uint32_t)(tap * WT * 4 + ks * 256) >> 4);
+            umma_tf32(tmem_d, dah0 + adv_a, db0 + adv_b, idesc2, first ? 0u : 1u);
+            umma_tf32(tmem_d, dal0 + adv_a, db0 + adv_b, idesc1, 1u);
+            first = false;
+          }
+        }
+        umma_commit(&bar_mma);
+      }
+    } else {
+      const int nx = it + a.ctas_per_ng;
+      if (nx < a.n_items) transform(nx, buf ^ 1);       // overlaps the MMAs of `it`
+      fence_async_smem();
+      // ---- epilogue: TMEM lane = output pixel (row = lane / 8 of the quarter, column = lane % 8); warps w and w + 4
+      // share the lane quarter w % 4 and take half of the G channels each
+      mbar_wait(&bar_mma, phase);
+      tc_fence_after();
+      const int b = it / tiles, t = it - b * tiles;
+      const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+      const int y0 = ty * GTC_TH, x0 = tx * GTC_TW;
       constexpr int NH = G / 2;
       const int quarter = wid & 3, half = wid >> 2;
       const int c0 = half * NH;
@@ -181,7 +205,7 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[cb + i] = v0[i] + v1[i] + bias_s[c0 + cb + i];
       }
-      tc_fence_before();
+      tc_fence_before();                   // ordered before the barrier below: the next item's MMAs restart the accumulator
       if (oy < a.h && ox < a.w) {
         float* o = out_n + (((long long)b * a.h + oy) * a.w + ox) * a.Cout + c0;
 #pragma unroll
@@ -205,8 +229,10 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
         }
       }
     }
-    // the next iteration's first __syncthreads orders these TMEM reads (and the completed MMAs' shared-memory reads) before
-    // the planes are overwritten and the accumulator is restarted
+    phase ^= 1;
+    // the MMAs of `it` have completed (every worker waited for their mbarrier), its accumulator has been read, the planes of
+    // the next item are written: the next iteration may issue
+    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
@@ -235,7 +261,7 @@ static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   a.NPXP = ((a.NPX + 7) & ~7) + 1;
   // descriptor fields are 14 bits of 16-byte units
   if ((long long)a.NPXP >= 16384 || a.SW >= 16384) return CNF_NOT_ELIGIBLE;
-  const size_t smem = ((size_t)2 * (G / 4) * a.NPXP * 4 + (size_t)9 * 2 * G * G) * sizeof(float);
+  const size_t smem = ((size_t)2 * 2 * (G / 4) * a.NPXP * 4 + (size_t)9 * 2 * G * G) * sizeof(float);   // two plane buffers + weights
   if (smem > 200 * 1024) return CNF_NOT_ELIGIBLE;
   int n_sm = 0;
   CU_TRY((cudaError_t)device_sm_count(&n_sm));

@@ -1378,7 +1378,9 @@ __global__ void __launch_bounds__(256) stem2_kernel(const GemmArgs a) {
   const float4 bias0 = ld4(b_s + quad * 4), bias1 = ld4(b_s + a.N + quad * 4);
   float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
   const int per_it = PPW * PX;
-  for (int it = wid; it * per_it < a.hw; it += 8) {
+  // small batches of large planes: gridDim.y CTAs share a sample (each stages the whole masked input, which is small, and
+  // takes every gridDim.y-th group of 8 warp tiles), so that the launch still fills the machine
+  for (int it = wid + 8 * blockIdx.y; it * per_it < a.hw; it += 8 * gridDim.y) {
     int pb[PX];
     bool ok[PX];
     float4 acc[2][PX];
@@ -1612,7 +1614,12 @@ static int launch_stem2(const GemmArgs& a, cudaStream_t st) {
   auto kern = stem2_kernel<4>;
   static SmemAttrCache cache;
   CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
-  kern<<<a.B, 256, smem, st>>>(a);
+  // large planes come with small batches (64x64: 64, 128x128: 16 per GPU): one CTA per 1024 pixels.  The split depends on
+  // the plane only, never on the batch, so a sample's statistics are reduced the same way whatever batch it is part of.
+  const int warp_px = (32 / (a.N >> 2)) * 4;                       // pixels of one warp tile
+  const int rounds = (a.hw + 8 * warp_px - 1) / (8 * warp_px);     // groups of 8 warp tiles per sample
+  const int split = std::max(1, std::min(rounds, a.hw / 1024));
+  kern<<<dim3(a.B, split), 256, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -1686,7 +1693,7 @@ static int launch_pw_tc3_t(const GemmArgs& a, cudaStream_t st) {
 // tcgen05 3xTF32 kernel on the smallest UMMA tile (N = 16, 32, 64, 128 columns) that holds the a.N outputs (the extra
 // columns are zero weights and are not stored); CNF_NOT_ELIGIBLE when the shape is outside the tile family
 static int launch_pw_tc3(const GemmArgs& a, cudaStream_t st) {
-  if (a.K % 8 || a.N % 8 || a.N < 8 || a.N > 128) return CNF_NOT_ELIGIBLE;
+  if (a.K % 4 || a.N % 8 || a.N < 8 || a.N > 128) return CNF_NOT_ELIGIBLE;   // K % 8 == 4: the last K-step is zero-padded
   if (a.N <= 16) return a.N == 16 ? launch_pw_tc3_t<16>(a, st) : CNF_NOT_ELIGIBLE;   // N = 8: no 8-column epilogue split
   if (a.N <= 32) return launch_pw_tc3_t<32>(a, st);
   if (a.N <= 64) return launch_pw_tc3_t<64>(a, st);

@@ -343,6 +343,14 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
             st4(As_hi + 4 * unit, make_float4(h[0], h[1], h[2], h[3]));
             st4(As_lo + 4 * unit, make_float4(l[0], l[1], l[2], l[3]));
           }
+        } else if (akq * 4 < ((kc + 7) & ~7)) {
+          // K % 8 == 4: the second half of the last 8-wide K-step does not exist; it is fed as zeros (its weights are zero too)
+#pragma unroll
+          for (int j = 0; j < SPT; ++j) {
+            const int unit = ar + 8 * akq + 64 * (((sh0 + j) * PT + ap) >> 3);
+            st4(As_hi + 4 * unit, make_float4(0.f, 0.f, 0.f, 0.f));
+            st4(As_lo + 4 * unit, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
         }
         if (tid == 0) TC3_STAMP(0, gi, 5);
         fence_async_smem();          // my generic-proxy writes -> async proxy ...
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           // the descriptors of a K-step differ from those of step 0 only in the start-address field (16-byte units;
           // shared-memory addresses stay below 2^18, so the 14-bit field never carries): one 64-bit add each
           const uint64_t dah0 = umma_desc(a_hi, LBO, SBO), dal0 = umma_desc(a_lo, LBO, SBO), dbh0 = umma_desc(b_hi, LBO, SBO);
-          for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : kc / 8); ++ks) {
+          for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : (kc + 7) / 8); ++ks) {
             const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);
             umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, (c | ks) != 0);
             umma_tf32(d_addr, dal0 + adv, dbh0 + adv, idesc1, 1);
