@@ -22,6 +22,7 @@
 
 #include "cnf_internal.h"
 #include "device_utils.cuh"
+#include "wgrad_tc.cuh"
 
 namespace cnf {
 
@@ -507,6 +508,42 @@ __global__ void __launch_bounds__(256) wgrad_pw_kernel(const WgradPwArgs a) {
       if (n < nt_len) atomicAdd(gB + n0 + n, bacc[j]);
     }
   }
+}
+
+// tensor-core version (wgrad_tc.cuh): K <= 128 input channels, N <= 64 output channels; CNF_NOT_ELIGIBLE otherwise
+static int launch_wgrad_pw_tc(const WgradPwArgs& w, float* partial, cudaStream_t st) {
+  if (w.K % 4 || w.K > 128 || w.K < 4 || w.N % 4 || w.N > 64 || w.N < 4 || !partial) return CNF_NOT_ELIGIBLE;
+  if ((((uintptr_t)w.x) & 15) || (((uintptr_t)w.dy) & 15) || ((w.x_net_stride * 4) % 16) || ((w.dy_net_stride * 4) % 16)) return CNF_NOT_ELIGIBLE;
+  WgtArgs a{};
+  a.x = w.x; a.dy = w.dy; a.x_net_stride = w.x_net_stride; a.dy_net_stride = w.dy_net_stride;
+  a.params = w.params; a.net_stride = w.net_stride; a.g_off = w.g_off; a.be_off = w.be_off; a.stats = w.stats;
+  a.partial = partial;
+  a.B = w.B; a.hw = w.hw; a.K = w.K; a.N = w.N; a.ln = w.ln;
+  a.sps = (w.hw + WGT_PX - 1) / WGT_PX;
+  a.n_stages = w.B * a.sps;
+  int n_sm = 0;
+  CU_TRY((cudaError_t)device_sm_count(&n_sm));
+  a.nc = std::max(1, std::min(std::min(a.n_stages, n_sm), WGT_MAX_NC));   // two CTAs per SM, half of them per net
+  const int NB = w.N <= 16 ? 16 : w.N <= 32 ? 32 : 64;
+  const size_t smem = (size_t)2 * (2 * 128 * WGT_PX + 2 * NB * WGT_PX) * sizeof(float);
+  dim3 grid(a.nc, 2);
+  if (NB == 16) {
+    static SmemAttrCache cache;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)wgrad_tc_kernel<16>, smem, cache));
+    wgrad_tc_kernel<16><<<grid, WGT_NT, smem, st>>>(a);
+  } else if (NB == 32) {
+    static SmemAttrCache cache;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)wgrad_tc_kernel<32>, smem, cache));
+    wgrad_tc_kernel<32><<<grid, WGT_NT, smem, st>>>(a);
+  } else {
+    static SmemAttrCache cache;
+    CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)wgrad_tc_kernel<64>, smem, cache));
+    wgrad_tc_kernel<64><<<grid, WGT_NT, smem, st>>>(a);
+  }
+  CU_TRY(cudaGetLastError());
+  const int total = w.K * w.N + w.N;
+  wgrad_tc_reduce_kernel<<<dim3((total + 255) / 256, 2), 256, 0, st>>>(partial, a.nc, w.K * w.N, w.N, w.grads, w.net_stride, w.w_off, w.b_off);
+  return (int)cudaGetLastError();
 }
 
 static int launch_wgrad_pw(WgradPwArgs a, cudaStream_t st) {
@@ -1023,8 +1060,11 @@ struct WgradGcArgs {
   int TH, TW, tiles_y, tiles_x, SB, teams;
 };
 
+// threads per CTA: a thread of the 32-wide variant holds 3 x 32 accumulators and needs the larger register budget
+__host__ __device__ constexpr int wgrad_gc_max_nt(int G, int KYS) { return KYS == 3 ? 256 : (G >= 32 ? 384 : 768); }
+
 template <int G, int KYS>   // KYS = 3: a thread owns all 9 taps of its channel; KYS = 1: one kernel row (wide groups)
-__global__ void __launch_bounds__(KYS == 3 ? 256 : 768) wgrad_gconv_kernel(const WgradGcArgs a) {
+__global__ void __launch_bounds__(wgrad_gc_max_nt(G, KYS)) wgrad_gconv_kernel(const WgradGcArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, NT = blockDim.x;
   const int net = blockIdx.z;
@@ -1180,7 +1220,7 @@ template <int G, int KYS>
 static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   const int Cb = a.groups * G, d = a.dil;
   const int tpt = (3 / KYS) * Cb;
-  const int max_nt = KYS == 3 ? 256 : 768;
+  const int max_nt = wgrad_gc_max_nt(G, KYS);
   if (tpt > max_nt) return CNF_NOT_ELIGIBLE;
   a.TW = std::min(a.w, 32);
   a.TH = std::min(a.h, 32);
@@ -1190,7 +1230,7 @@ static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   a.tiles_y = (a.h + a.TH - 1) / a.TH;
   a.tiles_x = (a.w + a.TW - 1) / a.TW;
   const int tiles = a.tiles_y * a.tiles_x;
-  a.teams = std::max(1, std::min(a.TH * a.TW, (KYS == 3 ? 256 : 384) / tpt));
+  a.teams = std::max(1, std::min(a.TH * a.TW, std::min(max_nt, KYS == 3 ? 256 : 384) / tpt));
   const int NT = std::max(64, ((tpt * a.teams + 31) / 32) * 32);
   const int want = std::max(1, 148 * 6 / (2 * tiles));
   a.SB = std::max(1, (a.B + want - 1) / want);
@@ -1206,7 +1246,7 @@ static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
 
 template <int G>
 static int launch_wgrad_gconv_g(const WgradGcArgs& a, cudaStream_t st) {
-  if (G <= 8) {
+  if constexpr (G <= 8) {
     const int rc = launch_wgrad_gconv_t<G, 3>(a, st);
     if (rc != CNF_NOT_ELIGIBLE) return rc;
   }
@@ -1221,6 +1261,7 @@ static int launch_wgrad_gconv(const WgradGcArgs& a, int G, cudaStream_t st) {
     case 4: return launch_wgrad_gconv_g<4>(a, st);
     case 8: return launch_wgrad_gconv_g<8>(a, st);
     case 16: return launch_wgrad_gconv_g<16>(a, st);
+    case 32: return launch_wgrad_gconv_g<32>(a, st);      // config 5 (light): nk 64 / cardinality 2
     default: return (int)cudaErrorInvalidConfiguration;
   }
 }
@@ -1347,7 +1388,8 @@ int64_t coupling_bwd_scratch_bytes(const cnf_coupling* c, int64_t B) {
   auto al = [](int64_t x) { return (x + 255) & ~int64_t(255); };
   const int64_t hw = c->hw();
   const int64_t wide = std::max(c->nk, c->cat);
-  return al(2 * B * hw * c->c2 * 4) + al(2 * B * hw * c->nk * 4) + 2 * al(2 * B * hw * wide * 4) + al(4 * B * 8);
+  return al(2 * B * hw * c->c2 * 4) + al(2 * B * hw * c->nk * 4) + 2 * al(2 * B * hw * wide * 4) + al(4 * B * 8) +
+         al(wgrad_tc_scratch_bytes(c->nk, c->cat, B, (int)hw));
 }
 
 int run_coupling_backward(const cnf_coupling* c, const float* params, float* grads, const CouplingSaved& sv,
@@ -1362,7 +1404,16 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
   float* GX = (float*)sp; sp += al(2LL * B * hw * nk * 4);
   float* GA = (float*)sp; sp += al(2LL * B * hw * wide * 4);
   float* GY = (float*)sp; sp += al(2LL * B * hw * wide * 4);
-  double* bst = (double*)sp;
+  double* bst = (double*)sp; sp += al(4LL * B * 8);
+  float* WP = wgrad_tc_scratch_bytes(nk, cat, B, hw) ? (float*)sp : nullptr;   // per-CTA partials of the tensor-core weight gradients
+  // 1x1 weight gradients: tcgen05 kernel + ordered reduction where the shape fits, else the FFMA kernel with fp32 atomics
+  auto wgrad_pw = [&](const WgradPwArgs& a) -> int {
+    if (!(c->paths & CNF_PATH_NO_TCGEN05)) {
+      const int rc = launch_wgrad_pw_tc(a, WP, st);
+      if (rc != CNF_NOT_ELIGIBLE) return rc;
+    }
+    return launch_wgrad_pw(a, st);
+  };
   const long long slot = 2LL * B * 2;
   auto stats = [&](int i) -> const double* { return c->n_ln() ? sv.stats + slot * i : nullptr; };
   const long long ns = c->net_stride;
@@ -1421,7 +1472,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
       a.params = params; a.grads = grads; a.net_stride = ns; a.w_off = L.pw2_w; a.b_off = L.pw2_b;
       a.g_off = L.ln3_g; a.be_off = L.ln3_b; a.stats = stats(3 * r + 2);
       a.B = B; a.hw = hw; a.K = cat; a.N = nk; a.ln = c->ln;
-      CU_TRY(launch_wgrad_pw(a, st));
+      CU_TRY(wgrad_pw(a));
       CU_TRY(dgrad_pw(params, ns, L.pw2_w, GX, GA, B, hw, cat, nk, st, c->paths));
       CU_TRY(ln_backward(GA, sv.Y2[r], GY, params, grads, ns, L.ln3_g, L.ln3_b, stats(3 * r + 2), bst, B,
                          (long long)hw * cat, c->ln, 0, st));
@@ -1453,7 +1504,7 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
       a.params = params; a.grads = grads; a.net_stride = ns; a.w_off = L.pw1_w; a.b_off = L.pw1_b;
       a.g_off = L.ln1_g; a.be_off = L.ln1_b; a.stats = stats(3 * r);
       a.B = B; a.hw = hw; a.K = nk; a.N = nk; a.ln = c->ln;
-      CU_TRY(launch_wgrad_pw(a, st));
+      CU_TRY(wgrad_pw(a));
       CU_TRY(dgrad_pw(params, ns, L.pw1_w, GY, GA, B, hw, nk, nk, st, c->paths));
       CU_TRY(ln_backward(GA, sv.X[r], GX, params, grads, ns, L.ln1_g, L.ln1_b, stats(3 * r), bst, B, (long long)hw * nk,
                          c->ln, 1, st));

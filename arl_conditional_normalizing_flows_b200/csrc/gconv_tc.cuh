@@ -39,6 +39,7 @@ struct GtcArgs {
   int tiles_y, tiles_x, n_items;   // items per (net, group): B * tiles_y * tiles_x
   int ctas_per_ng;                 // CTAs that share one (net, group)
   int SW, NPX, NPXP;               // window width, window pixels, plane stride in pixels (= 1 mod 8: conflict-free chunk stores)
+  int vec4;                        // 1: 128-bit output stores (Cout % 4 == 0), 0: 64-bit (Cout % 4 == 2, e.g. cat = 62)
 };
 
 // The item loop is software-pipelined over two plane buffers: while the tensor core works through the 9 x G / 8 x 2 MMAs
@@ -210,7 +211,12 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
         float* o = out_n + (((long long)b * a.h + oy) * a.w + ox) * a.Cout + c0;
 #pragma unroll
         for (int j = 0; j < NH; j += 4) {
-          st4(o + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+          if (a.vec4) {
+            st4(o + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+          } else {
+            *reinterpret_cast<float2*>(o + j) = make_float2(acc[j], acc[j + 1]);
+            *reinterpret_cast<float2*>(o + j + 2) = make_float2(acc[j + 2], acc[j + 3]);
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float l = fmaxf(acc[j + i], CNF_LRELU_SLOPE * acc[j + i]);
@@ -244,7 +250,7 @@ static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   const GconvBranch& br = g.br[bi];
   const int G = br.gin;
   if (g.bwd || g.ks != 3 || br.gin != br.gout || !(G == 16 || G == 32) || br.in_off != 0) return CNF_NOT_ELIGIBLE;
-  if ((g.Cin % 4) || (g.Cout % 4) || (br.out_off % 4) || br.groups * G > g.Cin) return CNF_NOT_ELIGIBLE;
+  if ((g.Cin % 4) || (g.Cout % 2) || (br.out_off % 4) || br.groups * G > g.Cin) return CNF_NOT_ELIGIBLE;
   if ((((uintptr_t)g.in) & 15) || (((uintptr_t)g.out) & 15) || ((g.in_net_stride * 4) % 16) || ((g.out_net_stride * 4) % 16)) return CNF_NOT_ELIGIBLE;
   GtcArgs a{};
   a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
@@ -259,6 +265,7 @@ static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   a.SW = GTC_TW + 2 * br.dil;
   a.NPX = (GTC_TH + 2 * br.dil) * a.SW;
   a.NPXP = ((a.NPX + 7) & ~7) + 1;
+  a.vec4 = (g.Cout % 4) == 0 ? 1 : 0;
   // descriptor fields are 14 bits of 16-byte units
   if ((long long)a.NPXP >= 16384 || a.SW >= 16384) return CNF_NOT_ELIGIBLE;
   const size_t smem = ((size_t)2 * 2 * (G / 4) * a.NPXP * 4 + (size_t)9 * 2 * G * G) * sizeof(float);   // two plane buffers + weights

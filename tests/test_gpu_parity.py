@@ -145,6 +145,7 @@ LAYER_CASES = [
     ([64, 64, 6], 2, 1, 4, 64, [1, 2, 4, 8], True),   # config-4 (light) channel layer: groups of 16 / 8 / 4 / 2
     ([32, 32, 4], 2, 2, 2, 64, [1, 2], True),         # groups of 32 (dil 1) and 16 (dil 2): config-5 (light) widths
     ([20, 12, 4], 2, 1, 2, 32, [1, 2], True),         # ragged 16 x 8 tiles (20 rows, 12 columns), groups of 16
+    ([64, 64, 2], 0, 1, 2, 64, [1, 2, 4, 8, 16], True),   # config-5 (light) checkerboard layer: (32,32,4), cat = 62 (64-bit stores)
 ]
 
 

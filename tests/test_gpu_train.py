@@ -21,6 +21,10 @@ SMALL = dict(io_shape=[8, 8, 3], x_d=2, squeeze_factor_block_list=[1, 0], ResNeX
              num_kernels_list=[16, 8], cardinality_list=[2, 2])
 MID = dict(io_shape=[16, 16, 4], x_d=3, squeeze_factor_block_list=[0, 1, 1], ResNeXt_block_list=[1, 2, 1],
            num_kernels_list=[32, 32, 16], cardinality_list=[4, 2, 2])
+# groups of 32 / 16 channels (the widths of BASELINE config 5 light: nk 64, cardinality 2): tensor-core grouped conv in the
+# forward pass, 32-wide weight-gradient kernel and the generic grouped data gradient in the backward pass
+WIDE = dict(io_shape=[16, 16, 2], x_d=1, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
+            num_kernels_list=[64], cardinality_list=[2])
 CFG2_R1 = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[1] * 4,
                num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
 
@@ -94,7 +98,8 @@ def compare_grads_kink_tolerant(model, want, tol=GTOL, frac=0.9, hard=1e-1):
     return worst
 
 
-@pytest.mark.parametrize("cfg,B,shape", [(TINY, 5, 'noise:4x4x2'), (SMALL, 6, 'noise:8x8x3'), (MID, 4, 'noise:16x16x4')])
+@pytest.mark.parametrize("cfg,B,shape", [(TINY, 5, 'noise:4x4x2'), (SMALL, 6, 'noise:8x8x3'), (MID, 4, 'noise:16x16x4'),
+                                         (WIDE, 3, 'noise:16x16x2')])
 def test_gradients_match_autograd_oracle(dev, cfg, B, shape):
     m, o, _ = mk(cfg)
     xy = synth_inputs(shape, B, seed=3)
