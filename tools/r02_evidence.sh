@@ -13,9 +13,15 @@ done
 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train --quick > $O/r02n_step_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r02n_launches_bench_step.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train --quick > $O/r02n_step_ncu.log 2>&1
 python tools/profile_layer.py 256 1 > $O/r02n_layer_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -s 11 -c 11 -f -o $O/r02n_layer_full python tools/profile_layer.py 256 1 > $O/r02n_layer_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -s 11 -c 11 -f -o /tmp/r02n_layer_full python tools/profile_layer.py 256 1 > $O/r02n_layer_ncu.log 2>&1
+python tools/ncu_export.py /tmp/r02n_layer_full.ncu-rep $O/r02n_layer28x28x64_ncu_full gconv_oct pw_tc3
 python tools/profile_layer.py 256 2 2 small > $O/r02n_small_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fused_coupling -s 2 -c 1 -f -o $O/r02n_small_full python tools/profile_layer.py 256 2 2 small > $O/r02n_small_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fused_coupling -s 2 -c 1 -f -o /tmp/r02n_small_full python tools/profile_layer.py 256 2 2 small > $O/r02n_small_ncu.log 2>&1
+python tools/ncu_export.py /tmp/r02n_small_full.ncu-rep $O/r02n_fused_coupling_14x14x32_ncu_full fused_coupling
 python tools/profile_layer.py 16 2 2 cfg5 > $O/r02n_cfg5layer_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:gconv_tc -s 4 -c 2 -f -o $O/r02n_gconv_tc_full python tools/profile_layer.py 16 2 2 cfg5 > $O/r02n_cfg5layer_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gconv_tc -s 4 -c 2 -f -o /tmp/r02n_gconv_tc_full python tools/profile_layer.py 16 2 2 cfg5 > $O/r02n_cfg5layer_ncu.log 2>&1
+python tools/ncu_export.py /tmp/r02n_gconv_tc_full.ncu-rep $O/r02n_gconv_tc_128x128x64_ncu_full gconv_tc
+python tools/profile_train.py 256 1 once > $O/r02n_train_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 4 -c 2 -f -o /tmp/r02n_wgrad_tc_full python tools/profile_train.py 256 1 once > $O/r02n_train_ncu.log 2>&1
+python tools/ncu_export.py /tmp/r02n_wgrad_tc_full.ncu-rep $O/r02n_wgrad_tc_ncu_full wgrad_tc_kernel
 grep -h "layer fwd" $O/r02n_layer_plain.log $O/r02n_small_plain.log $O/r02n_cfg5layer_plain.log

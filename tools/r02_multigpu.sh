@@ -11,6 +11,7 @@ run() {   # run <nproc> <outfile> <bench args...>
   echo "$out rc=$? $(python -c "import json,sys; d=json.load(open('$O/$out')); t=d['config'].get('train_step') or {}; print(round(d['value']), 'img/s', round(d['ms_per_step'],2), 'ms; train', t.get('images_per_s'), t.get('ms_per_step'))" 2>&1 | tail -1)"
   P=$((P+1))
 }
+python -m pytest tests/test_gpu_multi_device.py -q -m gpu 2>&1 | tail -2 > $O/r02o_two_device_test.log; cat $O/r02o_two_device_test.log
 if [ "$1" = "8" ]; then
   run 8 r02o_bench_line_cfg2_n8.json --steps 20 --warmup 3 --quick
   run 8 r02o_bench_line_cfg3_n8.json --config 3 --steps 10 --warmup 3 --quick
