@@ -69,12 +69,15 @@ __global__ void __launch_bounds__(WGT_NT, 2) wgrad_tc_kernel(const WgtArgs a) {
   auto unit = [](int m, int kq) { return (m & 7) + 8 * kq + 8 * KQ8 * (m >> 3); };
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of db (its dY block has a fixed channel quad)
 
+  // One A^T block (channel quad c4, pixel quad rq) and at most one dY^T block per thread (K <= 128, N <= 64: at most 256 / 128
+  // blocks per stage), so ALL global loads of a stage -- 4 x, 4 gamma, 4 beta, 4 dY, the sample's two LayerNorm sums -- are issued
+  // before the first use; a thread's dY channel quad is the same in every stage (its share of db stays in registers).
+  const bool has_a = tid < KQ * KQ8, has_d = tid < NQ * KQ8;
+  const int c4 = has_a ? tid % KQ : 0, rq = has_a ? tid / KQ : 0;
+  const int n4 = has_d ? tid % NQ : 0, rqd = has_d ? tid / NQ : 0;
   auto transform = [&](int st, int buf) {
     const int b = st / a.sps, p0 = (st - b * a.sps) * WGT_PX;
     const int np = min(WGT_PX, a.hw - p0);
-    float mean = 0.f, rstd = 1.f;
-    if (a.ln) ln_coeffs(a.stats, (long long)net * a.B + b, n_ln, mean, rstd);
-    const float sc = rstd, sh = -mean * rstd;
     float* A_hi = wgt_smem + buf * BUF;
     float* A_lo = A_hi + A_ST;
     float* B_hi = A_lo + A_ST;
@@ -83,10 +86,8 @@ __global__ void __launch_bounds__(WGT_NT, 2) wgrad_tc_kernel(const WgtArgs a) {
     const float* ds = dy_n + ((long long)b * a.hw + p0) * a.N;
     const float* gs = gam + (long long)p0 * a.K;
     const float* bs = bet + (long long)p0 * a.K;
-    // ---- A^T: blocks (channel quad c4, pixel quad rq)
-    for (int blk = tid; blk < KQ * KQ8; blk += WGT_WT * 32) {
-      const int c4 = blk % KQ, rq = blk / KQ;
-      float4 v[4], g[4], be[4];
+    float4 v[4], g[4], be[4], dv[4];
+    if (has_a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int p = min(rq * 4 + j, np - 1);
@@ -94,6 +95,15 @@ __global__ void __launch_bounds__(WGT_NT, 2) wgrad_tc_kernel(const WgtArgs a) {
         v[j] = ld4(xs + e);
         if (a.ln) { g[j] = ld4(gs + e); be[j] = ld4(bs + e); }
       }
+    }
+    if (has_d) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dv[j] = ld4(ds + (long long)min(rqd * 4 + j, np - 1) * a.N + 4 * n4);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln) ln_coeffs(a.stats, (long long)net * a.B + b, n_ln, mean, rstd);
+    const float sc = rstd, sh = -mean * rstd;
+    if (has_a) {
       float t[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -119,25 +129,20 @@ __global__ void __launch_bounds__(WGT_NT, 2) wgrad_tc_kernel(const WgtArgs a) {
         st4(A_lo + 4 * u, lo);
       }
     }
-    // ---- dY^T (no transform); one block per thread, so a thread's channel quad is the same in every stage
-    if (tid < NQ * KQ8) {
-      const int n4 = tid % NQ, rq = tid / NQ;
-      float4 v[4];
+    if (has_d) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int p = min(rq * 4 + j, np - 1);
-        v[j] = ld4(ds + (long long)p * a.N + 4 * n4);
-        if (rq * 4 + j >= np) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bsum.x += v[j].x; bsum.y += v[j].y; bsum.z += v[j].z; bsum.w += v[j].w;
+        if (rqd * 4 + j >= np) dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bsum.x += dv[j].x; bsum.y += dv[j].y; bsum.z += dv[j].z; bsum.w += dv[j].w;
       }
-      const float t[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
-                             {v[2].x, v[2].y, v[2].z, v[2].w}, {v[3].x, v[3].y, v[3].z, v[3].w}};
+      const float t[4][4] = {{dv[0].x, dv[0].y, dv[0].z, dv[0].w}, {dv[1].x, dv[1].y, dv[1].z, dv[1].w},
+                             {dv[2].x, dv[2].y, dv[2].z, dv[2].w}, {dv[3].x, dv[3].y, dv[3].z, dv[3].w}};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 hi, lo;
         tf32_split(t[0][i], hi.x, lo.x); tf32_split(t[1][i], hi.y, lo.y);
         tf32_split(t[2][i], hi.z, lo.z); tf32_split(t[3][i], hi.w, lo.w);
-        const int u = unit(4 * n4 + i, rq);
+        const int u = unit(4 * n4 + i, rqd);
         st4(B_hi + 4 * u, hi);
         st4(B_lo + 4 * u, lo);
       }
@@ -214,8 +219,7 @@ __global__ void __launch_bounds__(WGT_NT, 2) wgrad_tc_kernel(const WgtArgs a) {
     tc_fence_before();
     // db: the eight pixel-quad threads of a channel quad add up in shared memory (fixed set of addends; fp32 atomics on 8
     // values: order-dependent in the last bit only within this CTA's partial, the cross-CTA sum is ordered)
-    if (tid < NQ * KQ8) {
-      const int n4 = tid % NQ;
+    if (has_d) {
       atomicAdd(&bias_s[4 * n4], bsum.x); atomicAdd(&bias_s[4 * n4 + 1], bsum.y);
       atomicAdd(&bias_s[4 * n4 + 2], bsum.z); atomicAdd(&bias_s[4 * n4 + 3], bsum.w);
     }
