@@ -1277,6 +1277,7 @@ struct GcDgradArgs {
   const float* params;
   long long net_stride;
   int B, h, w, nk, cat, ks, n_br;
+  unsigned mask;     // bit i = add branch i; the result is ADDED to da (the other branches were written by the specialised kernels)
   GcDgradBranch br[CNF_MAX_BRANCHES];
 };
 
@@ -1295,6 +1296,7 @@ __global__ void __launch_bounds__(256) gconv_dgrad_naive_kernel(const GcDgradArg
   float acc = 0.f;
   for (int i = 0; i < a.n_br; ++i) {
     const GcDgradBranch& br = a.br[i];
+    if (!((a.mask >> i) & 1u)) continue;
     if (c >= br.groups * br.gin) continue;            // this branch reads only the first nk//d channels (F:579-586)
     const int g = c / br.gin, ci = c % br.gin;
     const float* W = P + br.w_off + (long long)g * a.ks * a.ks * br.gin * br.gout;
@@ -1310,15 +1312,16 @@ __global__ void __launch_bounds__(256) gconv_dgrad_naive_kernel(const GcDgradArg
       }
     }
   }
-  a.da[idx] = acc;
+  a.da[idx] += acc;
 }
 
 static int dgrad_gconv_naive(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B,
-                             cudaStream_t st) {
+                             unsigned mask, cudaStream_t st) {
   const ResBlockLayout& L = c->rb[r];
   GcDgradArgs a = {};
   a.dy = dY; a.da = dA; a.params = params; a.net_stride = c->net_stride;
   a.B = B; a.h = c->h; a.w = c->w; a.nk = c->nk; a.cat = c->cat; a.ks = c->ks; a.n_br = (int)L.br.size();
+  a.mask = mask;
   for (int i = 0; i < a.n_br; ++i) {
     const Branch& s = L.br[i];
     a.br[i].dil = s.dil; a.br[i].groups = s.groups; a.br[i].gin = s.gin; a.br[i].gout = s.gout;
@@ -1490,9 +1493,9 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
         CU_TRY(launch_wgrad_gconv(a, s.gin, st));
       }
       {
-        const int rc = dgrad_gconv(c, r, params, GY, GA, B, st);
-        if (rc == (int)cudaErrorInvalidConfiguration) CU_TRY(dgrad_gconv_naive(c, r, params, GY, GA, B, st));
-        else CU_TRY(rc);
+        unsigned leftover = 0;
+        CU_TRY(dgrad_gconv(c, r, params, GY, GA, B, st, &leftover));
+        if (leftover) CU_TRY(dgrad_gconv_naive(c, r, params, GY, GA, B, leftover, st));
       }
       CU_TRY(ln_backward(GA, sv.Y1[r], GY, params, grads, ns, L.ln2_g, L.ln2_b, stats(3 * r + 1), bst, B,
                          (long long)hw * nk, c->ln, 0, st));

@@ -145,7 +145,8 @@ int run_coupling_backward(const cnf_coupling* c, const float* params, float* gra
                           FlowView g_view, FlowView s_view, int B, float inv_batch, void* scratch, void* stream);
 int dgrad_pw(const float* params, long long net_stride, long long w_off, const float* dY, float* dA, int B, int hw,
              int K, int N, void* stream, int paths = 0);
-int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B, void* stream);
+int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B, void* stream,
+                unsigned* leftover);
 int launch_loss_grad(const float* zy, const float* xy, float* G, int64_t n, int D, int x_d, float lambda_y,
                      float inv_batch, void* stream);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,

@@ -40,6 +40,10 @@ struct GtcArgs {
   int ctas_per_ng;                 // CTAs that share one (net, group)
   int SW, NPX, NPXP;               // window width, window pixels, plane stride in pixels (= 1 mod 8: conflict-free chunk stores)
   int vec4;                        // 1: 128-bit output stores (Cout % 4 == 0), 0: 64-bit (Cout % 4 == 2, e.g. cat = 62)
+  // data-gradient mode (training): the input is the raw gradient slice of the branch (no LReLU / LayerNorm, channel offset
+  // in_off), the weights are read flipped and transposed (dx[p] = sum_tap dy[p - off(tap)] W[tap]^T), the result is ADDED to
+  // `out` (the branches of a block are separate launches on one stream), no bias, no statistics
+  int bwd, in_off;
 };
 
 // The item loop is software-pipelined over two plane buffers: while the tensor core works through the 9 x G / 8 x 2 MMAs
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (wid == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid < G) bias_s[tid] = P[a.b_off + grp * G + tid];
+  if (tid < G) bias_s[tid] = a.bwd ? 0.f : P[a.b_off + grp * G + tid];
   // the group's weights W[tap][ci][co] -> B operand rows n = co, columns k = ci: 16-byte unit (n % 8) + 8 (k / 4) + 8 NQ (n / 8)
   {
     const float* Wg = P + a.w_off + (long long)grp * 9 * G * G;
@@ -79,13 +83,15 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
       const int ci = r / G, co = r - ci * G;
       float hi, lo;
       tf32_split(Wg[i], hi, lo);
-      const int off = tap * WT + 4 * ((co & 7) + 8 * (ci >> 2) + 8 * NQ * (co >> 3)) + (ci & 3);
+      // forward: rows n = co, columns k = ci of tap; data gradient: rows n = ci, columns k = co of the mirrored tap
+      const int n = a.bwd ? ci : co, k = a.bwd ? co : ci, tp = a.bwd ? 8 - tap : tap;
+      const int off = tp * WT + 4 * ((n & 7) + 8 * (k >> 2) + 8 * NQ * (n >> 3)) + (k & 3);
       Bw[off] = hi;
       Bw[off + G * G] = lo;
     }
   }
 
-  const float* src_n = a.in + (long long)net * a.in_net_stride + grp * G;
+  const float* src_n = a.in + (long long)net * a.in_net_stride + a.in_off + grp * G;
   float* out_n = a.out + (long long)net * a.out_net_stride + a.out_off + grp * G;
   const float* gam = P + a.g_off + grp * G;
   const float* bet = P + a.be_off + grp * G;
@@ -126,8 +132,10 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
       for (int k = 0; k < UB; ++k) {
         if (u0 + k * NW >= n_units) continue;
         float4 t = v[k];
-        t.x = fmaxf(t.x, CNF_LRELU_SLOPE * t.x); t.y = fmaxf(t.y, CNF_LRELU_SLOPE * t.y);
-        t.z = fmaxf(t.z, CNF_LRELU_SLOPE * t.z); t.w = fmaxf(t.w, CNF_LRELU_SLOPE * t.w);
+        if (!a.bwd) {
+          t.x = fmaxf(t.x, CNF_LRELU_SLOPE * t.x); t.y = fmaxf(t.y, CNF_LRELU_SLOPE * t.y);
+          t.z = fmaxf(t.z, CNF_LRELU_SLOPE * t.z); t.w = fmaxf(t.w, CNF_LRELU_SLOPE * t.w);
+        }
         if (a.ln) {
           t.x = fmaf(fmaf(t.x, sc, sh), g[k].x, be[k].x);
           t.y = fmaf(fmaf(t.y, sc, sh), g[k].y, be[k].y);
@@ -211,6 +219,10 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
         float* o = out_n + (((long long)b * a.h + oy) * a.w + ox) * a.Cout + c0;
 #pragma unroll
         for (int j = 0; j < NH; j += 4) {
+          if (a.bwd) {   // accumulate onto the other branches' contributions (vec4 layout: Cout = nk, a multiple of 4)
+            const float4 old = ld4(o + j);
+            acc[j] += old.x; acc[j + 1] += old.y; acc[j + 2] += old.z; acc[j + 3] += old.w;
+          }
           if (a.vec4) {
             st4(o + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
           } else {
@@ -245,12 +257,14 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
   if (wid == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-// One branch with gin == gout in {16, 32}, ksize 3, forward only.  CNF_NOT_ELIGIBLE for anything else.
+// One branch with gin == gout in {16, 32}, ksize 3; forward, or (g.bwd) its data gradient.  CNF_NOT_ELIGIBLE for anything else.
 static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   const GconvBranch& br = g.br[bi];
   const int G = br.gin;
-  if (g.bwd || g.ks != 3 || br.gin != br.gout || !(G == 16 || G == 32) || br.in_off != 0) return CNF_NOT_ELIGIBLE;
-  if ((g.Cin % 4) || (g.Cout % 2) || (br.out_off % 4) || br.groups * G > g.Cin) return CNF_NOT_ELIGIBLE;
+  if (g.ks != 3 || br.gin != br.gout || !(G == 16 || G == 32) || (br.in_off % 4)) return CNF_NOT_ELIGIBLE;
+  if (!g.bwd && br.in_off != 0) return CNF_NOT_ELIGIBLE;
+  if ((g.Cin % 4) || (g.Cout % 2) || (br.out_off % 4) || br.in_off + br.groups * G > g.Cin) return CNF_NOT_ELIGIBLE;
+  if (g.bwd && ((g.Cout % 4) || g.ln)) return CNF_NOT_ELIGIBLE;
   if ((((uintptr_t)g.in) & 15) || (((uintptr_t)g.out) & 15) || ((g.in_net_stride * 4) % 16) || ((g.out_net_stride * 4) % 16)) return CNF_NOT_ELIGIBLE;
   GtcArgs a{};
   a.in = g.in; a.out = g.out; a.in_net_stride = g.in_net_stride; a.out_net_stride = g.out_net_stride;
@@ -259,6 +273,8 @@ static int launch_gconv_tc_branch(const GconvArgs& g, int bi, cudaStream_t st) {
   a.stats_in = g.stats_in; a.stats_out = g.stats_out;
   a.B = g.B; a.h = g.h; a.w = g.w; a.Cin = g.Cin; a.Cout = g.Cout; a.ln = g.ln;
   a.dil = br.dil; a.groups = br.groups; a.out_off = br.out_off;
+  a.bwd = g.bwd ? 1 : 0; a.in_off = br.in_off;
+  if (g.bwd) a.stats_out = nullptr;
   a.tiles_y = (g.h + GTC_TH - 1) / GTC_TH;
   a.tiles_x = (g.w + GTC_TW - 1) / GTC_TW;
   a.n_items = g.B * a.tiles_y * a.tiles_x;

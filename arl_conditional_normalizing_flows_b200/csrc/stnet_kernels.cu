@@ -2130,12 +2130,15 @@ int dgrad_pw(const float* params, long long net_stride, long long w_off, const f
   return launch_gemm<false>(a, (cudaStream_t)stream);
 }
 
-// grouped dilated convs: dA[2][B][hw][nk] = sum over branches of conv^T(dY[2][B][hw][cat]); returns
-// cudaErrorInvalidConfiguration for group shapes gconv3 does not cover
-int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B, void* stream) {
+// grouped dilated convs: dA[2][B][hw][nk] = sum over branches of conv^T(dY[2][B][hw][cat]).  Branches are handled by the
+// tensor-core kernel (groups of 16 / 32), else by gconv3 (groups of 1 / 2 / 4 / 8); bit i of *leftover is set for a branch
+// neither covers (the caller adds it with the generic kernel).
+int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* dY, float* dA, int B, void* stream,
+                unsigned* leftover) {
   cudaStream_t st = (cudaStream_t)stream;
   const ResBlockLayout& L = c->rb[r];
   const int hw = c->hw(), nk = c->nk, cat = c->cat;
+  *leftover = 0;
   CU_TRY(cudaMemsetAsync(dA, 0, sizeof(float) * 2 * (size_t)B * hw * nk, st));
   GconvArgs a = {};
   a.in = dY; a.in_net_stride = (long long)B * hw * cat; a.Cin = cat;
@@ -2149,9 +2152,10 @@ int dgrad_gconv(const cnf_coupling* c, int r, const float* params, const float* 
     a.br[i].in_off = s.out_off; a.br[i].out_off = 0; a.br[i].w_off = s.w_off; a.br[i].b_off = s.b_off;
   }
   for (int i = 0; i < a.n_br; ++i) {
-    const int rc = launch_gconv3_branch(a, i, st);
-    if (rc == CNF_NOT_ELIGIBLE) return (int)cudaErrorInvalidConfiguration;
-    if (rc) return rc;
+    int rc = (c->paths & CNF_PATH_NO_TCGEN05) ? CNF_NOT_ELIGIBLE : launch_gconv_tc_branch(a, i, st);
+    if (rc == CNF_NOT_ELIGIBLE) rc = launch_gconv3_branch(a, i, st);
+    if (rc == CNF_NOT_ELIGIBLE) *leftover |= 1u << i;
+    else if (rc) return rc;
   }
   return 0;
 }
