@@ -121,7 +121,10 @@ int cnf_coupling_set_fusion(cnf_coupling* c, int enable);
  * A/B-timed (bench.py).  0 (default) = the fastest eligible kernel everywhere.  All combinations give the same results to
  * fp32 rounding.  Host-side flag, not thread-safe against concurrent calls on the same descriptor. */
 #define CNF_PATH_NO_RESIDENT 1  /* no activation-resident launch (fused_kernels.cu): layer-per-kernel path          */
-#define CNF_PATH_NO_TCGEN05 2   /* 1x1 convs: no tcgen05 3xTF32 kernel (pw_tc3_kernel) -> fp32 FFMA pw_kernel          */
+#define CNF_PATH_NO_TCGEN05 2   /* no tcgen05 3xTF32 kernels: 1x1 convs and their data gradients (pw_tc3_kernel) -> FFMA
+                                 * pw_kernel / gemm_kernel; 16 / 32-wide grouped convs and their data gradients
+                                 * (gconv_tc_kernel) -> gconv_kernel / generic gradient; 1x1 weight gradients
+                                 * (wgrad_tc_kernel) -> wgrad_pw_kernel                                          */
 #define CNF_PATH_NO_PW_FFMA 4   /* 1x1 convs: no multi-sample FFMA kernel either -> generic gemm_kernel                */
 #define CNF_PATH_NO_OCTET 8     /* grouped convs: no all-branch octet kernel (gconv_oct_kernel) -> one launch per branch */
 #define CNF_PATH_NO_BRANCH 16   /* grouped convs: no per-branch gconv3_kernel -> gconv2_kernel / gconv_kernel          */

@@ -288,3 +288,21 @@ def test_states_recovered_by_the_inverse_pass(dev, cfg, B, shape, kind, tol):
     from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import Adam
     m.compile(optimizer=Adam(3e-4))
     assert np.isfinite(m.train_step(x)['loss'])
+
+
+@pytest.mark.parametrize("cfg,B,shape", [(MID, 4, 'noise:16x16x4'), (WIDE, 3, 'noise:16x16x2'), (CFG2_R1, 3, 'cfg2')])
+def test_gradients_do_not_depend_on_the_kernel_family(dev, cfg, B, shape):
+    """The tcgen05 kernels of the training step (1x1 data and weight gradients, grouped convs of wide groups and their data
+    gradients) and the FFMA kernels they replace (CNF_PATH_NO_TCGEN05) compute the same loss and gradients: 3xTF32 is
+    fp32-exact to ~1e-6, the rest is summation order (stated: 1e-4 of the largest gradient entry, 1e-5 on the loss)."""
+    from arl_conditional_normalizing_flows_b200 import _lib
+    m, _, _ = mk(cfg, 'rand', seed=2)
+    x = torch.from_numpy(synth_inputs(shape, B, seed=9)).to(dev)
+    four_a, g_a = m.loss_and_grad(x)
+    four_a, g_a = [float(t) for t in four_a], g_a.clone()
+    m.set_kernel_paths(_lib.CNF_PATH_NO_TCGEN05)
+    four_b, g_b = m.loss_and_grad(x)
+    m.set_kernel_paths(0)
+    np.testing.assert_allclose([float(t) for t in four_b], four_a, rtol=1e-5)
+    scale = float(g_a.abs().max())
+    assert float((g_b - g_a).abs().max()) <= 1e-4 * scale
