@@ -1655,12 +1655,13 @@ static int launch_pw_t(GemmArgs a, cudaStream_t st) {
 }
 
 // warp-specialised persistent tcgen05 1x1 conv; CNF_NOT_ELIGIBLE when the resident-W image does not fit
-template <int N, int TW, int NST, bool PADN>
+template <int N, int TW, int NST, bool PADN, bool ATM>
 static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   const int nchunks = (a.K + 31) / 32;
-  const size_t smem = ((size_t)NST * 2 * 128 * 32 + 3 * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
+  const size_t ops = ATM ? 0 : (size_t)NST * 2 * 128 * 32;           // operand stages: shared memory, or tensor memory (ATM)
+  const size_t smem = (ops + (size_t)(ATM ? 5 : 3) * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
   if (smem > 225 * 1024) return CNF_NOT_ELIGIBLE;
-  auto kern = pw_tc3_kernel<N, TW, NST, PADN>;
+  auto kern = pw_tc3_kernel<N, TW, NST, PADN, ATM>;
   static SmemAttrCache cache;
   CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   int n_sm = 0;
@@ -1673,15 +1674,24 @@ static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-// more operand stages decouple the transform warps from the MMA round trip; use as many as shared memory allows
+// N <= 64: the A operand stages live in tensor memory (3 stages of 64 columns beside the two accumulators) and the raw ring is
+// 5 deep.  N = 128 (zero-padded data gradients): operand stages in shared memory, as many as fit beside the resident weights.
 template <int N, bool PADN>
 static int launch_pw_tc3_p(const GemmArgs& a, cudaStream_t st) {
+  if constexpr (N <= 64) {
+    static int atm = -1;
+    if (atm < 0) atm = knob_int("PW_ATM", 1);
+    if (atm) {
+      const int rc = launch_pw_tc3_tw<N, 8, 3, PADN, true>(a, st);
+      if (rc != CNF_NOT_ELIGIBLE) return rc;
+    }
+  }
   static int nst = -1;
   if (nst < 0) nst = knob_int("PW_NST", 4);
   int rc = CNF_NOT_ELIGIBLE;
-  if (nst >= 4) rc = launch_pw_tc3_tw<N, 8, 4, PADN>(a, st);
-  if (rc == CNF_NOT_ELIGIBLE && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3, PADN>(a, st);
-  if (rc == CNF_NOT_ELIGIBLE) rc = launch_pw_tc3_tw<N, 8, 2, PADN>(a, st);
+  if (nst >= 4) rc = launch_pw_tc3_tw<N, 8, 4, PADN, false>(a, st);
+  if (rc == CNF_NOT_ELIGIBLE && nst >= 3) rc = launch_pw_tc3_tw<N, 8, 3, PADN, false>(a, st);
+  if (rc == CNF_NOT_ELIGIBLE) rc = launch_pw_tc3_tw<N, 8, 2, PADN, false>(a, st);
   return rc;
 }
 

@@ -67,7 +67,11 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {   // 256-bit loa
 // a.N < N outputs (the other columns of the UMMA tile are zero weights and are not stored).
 // Measured and dropped (profiles/r02_summary.md): two transform groups on alternate K-chunks (16 + 1 + 4 + 2 warps): the four
 // epilogue warps then hold a TMEM buffer across their first store pass and the tile period grows from 6.0 k to 7.5 k cycles.
-template <int N, int TW, int NST, bool PADN = false>
+// ATM: the transformed A operand (hi and lo, 32 + 32 columns per stage) is written straight into TENSOR MEMORY with tcgen05.st
+// and the MMAs read it from there (tcgen05.mma with a TMEM A operand): no operand stages in shared memory, no proxy fence,
+// the shared-memory port only carries the raw ring and the resident weights, and the ring is 5 deep.  Needs 4 N + 64 NST <= 512
+// columns, i.e. N <= 64.
+template <int N, int TW, int NST, bool PADN = false, bool ATM = false>
 __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
   constexpr int NTT = 256;                     // 16-byte units per sample and K-chunk (32 rows x 8 quads)
   constexpr int NTH = TW * 32;                 // transform threads
@@ -75,15 +79,18 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
   static_assert(SPT == 4, "8 transform warps");
   constexpr int S = 4, PT = 32, M = 128;
   constexpr int KC = 32;
-  constexpr int DEPTH = 3;
+  constexpr int DEPTH = ATM ? 5 : 3;
   constexpr int A_ST = M * KC, B_ST = N * KC;
   constexpr int RAW = 6 * NTT * 4;
   // one accumulator buffer = 2 N columns: [0, N) hi*hi + lo*hi, [N, 2N) hi*lo (the epilogue adds the halves); two buffers
-  constexpr uint32_t TMEM_COLS = 4 * N < 32 ? 32 : 4 * N;
+  constexpr uint32_t TMEM_NEED = 4 * N + (ATM ? 64 * NST : 0);
+  static_assert(TMEM_NEED <= 512, "tensor memory");
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  constexpr uint32_t A_TM = 4 * N;             // first column of the A stages (ATM): [stage][hi 32 | lo 32]
   extern __shared__ __align__(128) float tc3_smem[];
   const int nchunks = (a.K + KC - 1) / KC;
   float* opsA = tc3_smem;                      // [NST stages][hi, lo][A_ST]
-  float* raw = opsA + NST * 2 * A_ST;                // [DEPTH][6][NTT] float4
+  float* raw = opsA + (ATM ? 0 : NST * 2 * A_ST);    // [DEPTH][6][NTT] float4
   float* Bres = raw + DEPTH * RAW;             // [nchunks][hi, lo][B_ST]
   constexpr int PWARPS = 4, NPT = PWARPS * 32;  // producer (copy) warps / threads
   constexpr int EWARPS = 8;                     // epilogue warps: two per TMEM lane quarter, half of the columns each
@@ -142,6 +149,67 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
 
   if (wid < TW) {
     // =============================== transform warps ===============================
+    if constexpr (ATM) {
+      // warp w: TMEM lane quarter w & 3 = sample of the tile, lane = pixel; warps w and w + 4 take 16 of the chunk's 32
+      // channels each.  A thread reads its row's quads from the swizzled raw slot (8 lanes = 8 rows -> 8 distinct 16-byte
+      // bank slots), applies LReLU + LayerNorm, splits hi / lo and writes 2 x 8 + 2 x 8 columns of its own TMEM lane.
+      const int quarter = wid & 3, khalf = wid >> 2;
+      const float slope = a.raw_in ? 1.f : CNF_LRELU_SLOPE;
+      const uint32_t lane_addr = tmem_d + ((uint32_t)(quarter * 32) << 16);
+      int gi = 0, slot = 0;
+      const int dq = ncta / tiles_p, dp = ncta - dq * tiles_p;
+      int tq = cta / tiles_p, tp = cta - tq * tiles_p;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int s0 = tq * S, p0 = tp * PT;
+        const int ns = min(S, a.B - s0);
+        tq += dq; tp += dp;
+        if (tp >= tiles_p) { tp -= tiles_p; ++tq; }
+        const bool ok = (p0 + lane) < a.hw && quarter < ns;
+        const bool use_ln = ok && a.ln;
+        float sc = 1.f, sh = 0.f;
+        for (int c = 0; c < nchunks; ++c, ++gi) {
+          const int stage = gi % NST;
+          const int kc = min(KC, a.K - c * KC);
+          mbar_wait(&raw_full[slot], (gi / DEPTH) & 1);   // the producer warps' copies of chunk gi have landed
+          if (c == 0) { const float2 cf = cf_s[slot][quarter]; sc = cf.x; sh = cf.y; }
+          if (gi >= NST) mbar_wait(&bar_free[stage], ((gi / NST) - 1) & 1);   // the MMAs that read this A stage are done
+          tc_fence_after();
+          const float* src = raw + slot * RAW;
+          const uint32_t a_hi = lane_addr + A_TM + stage * 64 + 16 * khalf, a_lo = a_hi + 32;
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int q0 = 4 * khalf + 2 * h2;            // first of the two channel quads of this pass
+            float hi[8], lo[8];
+#pragma unroll
+            for (int jq = 0; jq < 2; ++jq) {
+              const int unit = lane * 8 + ((q0 + jq) ^ (lane & 7));
+              const float4 xv = ld4(src + (quarter * NTT + unit) * 4);
+              float4 g = ld4(src + (4 * NTT + unit) * 4), be = ld4(src + (5 * NTT + unit) * 4);
+              g.x = use_ln ? g.x : 1.f; g.y = use_ln ? g.y : 1.f; g.z = use_ln ? g.z : 1.f; g.w = use_ln ? g.w : 1.f;
+              be.x = use_ln ? be.x : 0.f; be.y = use_ln ? be.y : 0.f; be.z = use_ln ? be.z : 0.f; be.w = use_ln ? be.w : 0.f;
+              float v[4];
+              v[0] = fmaf(fmaf(fmaxf(xv.x, slope * xv.x), sc, sh), g.x, be.x);
+              v[1] = fmaf(fmaf(fmaxf(xv.y, slope * xv.y), sc, sh), g.y, be.y);
+              v[2] = fmaf(fmaf(fmaxf(xv.z, slope * xv.z), sc, sh), g.z, be.z);
+              v[3] = fmaf(fmaf(fmaxf(xv.w, slope * xv.w), sc, sh), g.w, be.w);
+              const bool valid = ok && (q0 + jq) * 4 < kc && !(a.dbg & 8);   // rows / channels beyond the tensor feed zeros
+#pragma unroll
+              for (int i = 0; i < 4; ++i) tf32_split(valid ? v[i] : 0.f, hi[4 * jq + i], lo[4 * jq + i]);
+            }
+            tmem_st8(a_hi + 8 * h2, hi);
+            tmem_st8(a_lo + 8 * h2, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&raw_free[slot]);              // the ring slot may be refilled
+            mbar_arrive(&bar_full[stage]);
+          }
+          slot = slot + 1 == DEPTH ? 0 : slot + 1;
+        }
+      }
+    } else {
     const int wl = wid & 7, sh0 = 0;           // transform warp index; first sample this thread handles
     const int ar = lane & 7, akq = (lane >> 3) + 4 * (wl >> 2);
     const int ap = 8 * (wl & 3) + ar;
@@ -235,6 +303,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
         if (tid == 0) TC3_STAMP(0, gi, 7);
       }
     }
+    }
   } else if (wid >= TW + 1 + EWARPS) {
     // =============================== producer (copy) warps ===============================
     // 8 consecutive lanes fetch the 8 16-byte pieces of ONE 128-byte row segment (one L2 line -> one shared-memory
@@ -326,8 +395,14 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           const uint64_t dah0 = umma_desc(a_hi, LBO, SBO), dal0 = umma_desc(a_lo, LBO, SBO), dbh0 = umma_desc(b_hi, LBO, SBO);
           for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : (kc + 7) / 8); ++ks) {
             const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);
-            umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, (c | ks) != 0);
-            umma_tf32(d_addr, dal0 + adv, dbh0 + adv, idesc1, 1);
+            if constexpr (ATM) {
+              const uint32_t at = tmem_d + A_TM + stage * 64 + 8 * ks;     // hi columns of this K-step; lo 32 further
+              umma_tf32_ts(d_addr, at, dbh0 + adv, idesc2, (c | ks) != 0);
+              umma_tf32_ts(d_addr, at + 32, dbh0 + adv, idesc1, 1);
+            } else {
+              umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, (c | ks) != 0);
+              umma_tf32(d_addr, dal0 + adv, dbh0 + adv, idesc1, 1);
+            }
           }
           TC3_STAMP(1, gi, 2);
           umma_commit(&bar_free[stage]);
