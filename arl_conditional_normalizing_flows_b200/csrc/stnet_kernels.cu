@@ -1655,13 +1655,14 @@ static int launch_pw_t(GemmArgs a, cudaStream_t st) {
 }
 
 // warp-specialised persistent tcgen05 1x1 conv; CNF_NOT_ELIGIBLE when the resident-W image does not fit
-template <int N, int TW, int NST, bool PADN, bool ATM>
+template <int N, int TW, int NST, bool PADN, bool ATM, int KCH = 32>
 static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
-  const int nchunks = (a.K + 31) / 32;
+  const int nchunks = (a.K + KCH - 1) / KCH;
   const size_t ops = ATM ? 0 : (size_t)NST * 2 * 128 * 32;           // operand stages: shared memory, or tensor memory (ATM)
-  const size_t smem = (ops + (size_t)(ATM ? 5 : 3) * 6 * 256 * 4 + (size_t)nchunks * 2 * N * 32) * sizeof(float);
+  const size_t depth = (ATM && KCH == 32) ? 5 : 3;
+  const size_t smem = (ops + depth * 6 * (32 * KCH / 4) * 4 + (size_t)nchunks * 2 * N * KCH) * sizeof(float);
   if (smem > 225 * 1024) return CNF_NOT_ELIGIBLE;
-  auto kern = pw_tc3_kernel<N, TW, NST, PADN, ATM>;
+  auto kern = pw_tc3_kernel<N, TW, NST, PADN, ATM, KCH>;
   static SmemAttrCache cache;
   CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   int n_sm = 0;
@@ -1682,6 +1683,8 @@ static int launch_pw_tc3_p(const GemmArgs& a, cudaStream_t st) {
     static int atm = -1;
     if (atm < 0) atm = knob_int("PW_ATM", 1);
     if (atm) {
+      // 32-channel chunks, 3 TMEM stages of 64 columns.  (64-channel chunks with 2 stages of 128 columns, KCH = 64, measured
+      // slower: 77.7 / 133.0 us against 70.8 / 112.7 us, profiles/r02_summary.md)
       const int rc = launch_pw_tc3_tw<N, 8, 3, PADN, true>(a, st);
       if (rc != CNF_NOT_ELIGIBLE) return rc;
     }

@@ -71,22 +71,26 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {   // 256-bit loa
 // and the MMAs read it from there (tcgen05.mma with a TMEM A operand): no operand stages in shared memory, no proxy fence,
 // the shared-memory port only carries the raw ring and the resident weights, and the ring is 5 deep.  Needs 4 N + 64 NST <= 512
 // columns, i.e. N <= 64.
-template <int N, int TW, int NST, bool PADN = false, bool ATM = false>
+// KCH: channels per K-chunk (32, or 64 with ATM: the MMA issuer and the transform warps pay their per-chunk hand-off costs half
+// as often; clock stamps put those at ~1000 of ~2300 cycles per 32-channel chunk).
+template <int N, int TW, int NST, bool PADN = false, bool ATM = false, int KCH = 32>
 __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
-  constexpr int NTT = 256;                     // 16-byte units per sample and K-chunk (32 rows x 8 quads)
+  static_assert(KCH == 32 || (KCH == 64 && ATM), "64-channel chunks need the TMEM operand path");
+  constexpr int QPR = KCH / 4;                 // 16-byte quads per row of a chunk
+  constexpr int NTT = 32 * QPR;                // 16-byte units per sample and K-chunk (32 rows x QPR quads)
   constexpr int NTH = TW * 32;                 // transform threads
   constexpr int SPT = 4 * 256 / NTH;           // samples per transform thread
   static_assert(SPT == 4, "8 transform warps");
   constexpr int S = 4, PT = 32, M = 128;
-  constexpr int KC = 32;
-  constexpr int DEPTH = ATM ? 5 : 3;
+  constexpr int KC = KCH;
+  constexpr int DEPTH = (ATM && KCH == 32) ? 5 : 3;
   constexpr int A_ST = M * KC, B_ST = N * KC;
   constexpr int RAW = 6 * NTT * 4;
   // one accumulator buffer = 2 N columns: [0, N) hi*hi + lo*hi, [N, 2N) hi*lo (the epilogue adds the halves); two buffers
-  constexpr uint32_t TMEM_NEED = 4 * N + (ATM ? 64 * NST : 0);
+  constexpr uint32_t TMEM_NEED = 4 * N + (ATM ? 2 * KC * NST : 0);
   static_assert(TMEM_NEED <= 512, "tensor memory");
   constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
-  constexpr uint32_t A_TM = 4 * N;             // first column of the A stages (ATM): [stage][hi 32 | lo 32]
+  constexpr uint32_t A_TM = 4 * N;             // first column of the A stages (ATM): [stage][hi KC | lo KC]
   extern __shared__ __align__(128) float tc3_smem[];
   const int nchunks = (a.K + KC - 1) / KC;
   float* opsA = tc3_smem;                      // [NST stages][hi, lo][A_ST]
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
   if (wid < TW) {
     // =============================== transform warps ===============================
     if constexpr (ATM) {
-      // warp w: TMEM lane quarter w & 3 = sample of the tile, lane = pixel; warps w and w + 4 take 16 of the chunk's 32
+      // warp w: TMEM lane quarter w & 3 = sample of the tile, lane = pixel; warps w and w + 4 take half of the chunk's
       // channels each.  A thread reads its row's quads from the swizzled raw slot (8 lanes = 8 rows -> 8 distinct 16-byte
       // bank slots), applies LReLU + LayerNorm, splits hi / lo and writes 2 x 8 + 2 x 8 columns of its own TMEM lane.
       const int quarter = wid & 3, khalf = wid >> 2;
@@ -175,14 +179,14 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           if (gi >= NST) mbar_wait(&bar_free[stage], ((gi / NST) - 1) & 1);   // the MMAs that read this A stage are done
           tc_fence_after();
           const float* src = raw + slot * RAW;
-          const uint32_t a_hi = lane_addr + A_TM + stage * 64 + 16 * khalf, a_lo = a_hi + 32;
+          const uint32_t a_hi = lane_addr + A_TM + stage * 2 * KC + (KC / 2) * khalf, a_lo = a_hi + KC;
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int q0 = 4 * khalf + 2 * h2;            // first of the two channel quads of this pass
+          for (int h2 = 0; h2 < QPR / 4; ++h2) {
+            const int q0 = (QPR / 2) * khalf + 2 * h2;    // first of the two channel quads of this pass
             float hi[8], lo[8];
 #pragma unroll
             for (int jq = 0; jq < 2; ++jq) {
-              const int unit = lane * 8 + ((q0 + jq) ^ (lane & 7));
+              const int unit = lane * QPR + ((q0 + jq) ^ (lane & 7));
               const float4 xv = ld4(src + (quarter * NTT + unit) * 4);
               float4 g = ld4(src + (4 * NTT + unit) * 4), be = ld4(src + (5 * NTT + unit) * 4);
               g.x = use_ln ? g.x : 1.f; g.y = use_ln ? g.y : 1.f; g.z = use_ln ? g.z : 1.f; g.w = use_ln ? g.w : 1.f;
@@ -347,10 +351,10 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
 #pragma unroll
         for (int h = 0; h < NTT / NPT; ++h) {
           const int u = pt + h * NPT;
-          const int cq = u & 7, crow = u >> 3;
+          const int cq = u % QPR, crow = u / QPR;
           const int gp = p0 + crow;
           if (cq * 4 < kc && gp < a.hw && !(a.dbg & 2)) {
-            const int cunit = crow * 8 + (cq ^ (crow & 7));
+            const int cunit = crow * QPR + (cq ^ (crow & 7));
             const long long e = (long long)gp * a.K + k0 + cq * 4;
 #pragma unroll
             for (int s = 0; s < S; ++s)
@@ -396,9 +400,9 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : (kc + 7) / 8); ++ks) {
             const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);
             if constexpr (ATM) {
-              const uint32_t at = tmem_d + A_TM + stage * 64 + 8 * ks;     // hi columns of this K-step; lo 32 further
+              const uint32_t at = tmem_d + A_TM + stage * 2 * KC + 8 * ks;   // hi columns of this K-step; lo KC further
               umma_tf32_ts(d_addr, at, dbh0 + adv, idesc2, (c | ks) != 0);
-              umma_tf32_ts(d_addr, at + 32, dbh0 + adv, idesc1, 1);
+              umma_tf32_ts(d_addr, at + KC, dbh0 + adv, idesc1, 1);
             } else {
               umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, (c | ks) != 0);
               umma_tf32(d_addr, dal0 + adv, dbh0 + adv, idesc1, 1);
