@@ -380,6 +380,8 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
       constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;
       const uint32_t a_base = smem_u32(opsA), b_base = smem_u32(Bres);
       int gi = 0;
+      const int n_total = my_tiles * nchunks;
+      bool ready = false;                      // the next chunk's operands were already seen complete (early poll below)
       for (int tl = 0; tl < my_tiles; ++tl) {
         const int buf = tl & 1;
         if (tl >= 2) mbar_wait(&bar_tempty[buf], ((tl >> 1) - 1) & 1);   // epilogue drained this accumulator
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           const int stage = gi % NST;
           const int kc = min(KC, a.K - c * KC);
           TC3_STAMP(1, gi, 0);
-          mbar_wait(&bar_full[stage], (gi / NST) & 1);
+          if (!ready) mbar_wait(&bar_full[stage], (gi / NST) & 1);
           TC3_STAMP(1, gi, 1);
           tc_fence_after();
           const uint32_t a_hi = a_base + stage * 2 * A_ST * 4, a_lo = a_hi + A_ST * 4;
@@ -409,6 +411,9 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
             }
           }
           TC3_STAMP(1, gi, 2);
+          // poll the NEXT chunk's barrier before the commits: the ~250-cycle latency of the try_wait overlaps them (this
+          // thread's chain -- wait, 8 MMAs, commits -- paces the kernel, clock stamps in profiles/r02t_*)
+          ready = gi + 1 < n_total && mbar_try_wait(&bar_full[(gi + 1) % NST], ((gi + 1) / NST) & 1);
           umma_commit(&bar_free[stage]);
           if (c == nchunks - 1) umma_commit(&bar_tfull[buf]);
           TC3_STAMP(1, gi, 3);
