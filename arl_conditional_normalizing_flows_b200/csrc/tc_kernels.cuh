@@ -2,17 +2,20 @@
 //
 // out[m, n] = sum_k LN(LReLU(x))[m, k] * W[k, n] + bias[n] (+ res[m, n]) on the 5th-generation tensor
 // cores with fp32-level accuracy: every fp32 operand is split x = hi + lo with hi = x truncated to TF32
-// (low 13 mantissa bits cleared, exactly what kind::tf32 reads) and lo = x - hi (exact in fp32), and three
-// MMAs hi*hi + lo*hi + hi*lo accumulate into one fp32 TMEM tile (the dropped lo*lo term is ~2^-20 relative).
+// (low 13 mantissa bits cleared, exactly what kind::tf32 reads) and lo = x - hi (exact in fp32); per 8-wide K-step
+// hi(A) x [hi(W) | lo(W)] (ONE tcgen05.mma of width 2 N) and lo(A) x hi(W) (width N) accumulate into a 2 N-column fp32
+// TMEM tile whose halves the epilogue adds (3xTF32; the dropped lo*lo term is ~2^-20 relative).
 //
-// A CTA owns 128 rows = 4 samples x 32 pixels (gamma/beta of a pixel slot are loaded once and shared by
-// the 4 samples).  K is consumed in chunks of 32 through a 2-stage shared-memory ring: all 8 warps apply
-// LReLU + LayerNorm + the hi/lo split in registers and store the operands in the canonical K-major
-// no-swizzle UMMA layout (core matrix = 8 rows x 16 B; LBO = 128 B between K chunks, SBO = 1 KB between
-// 8-row groups); one thread then issues 12 tcgen05.mma (4 K-steps x 3 terms) and a tcgen05.commit that
-// releases the stage, so the next chunk's loads overlap the tensor-core work.  The epilogue reads the
-// accumulators back with tcgen05.ld (32 lanes x 32b x N/2 columns per thread), adds bias/residual, stores
-// and accumulates the LayerNorm statistics of LReLU(out) for the consumer.
+// A CTA owns 128 rows = 4 samples x 32 pixels (gamma/beta of a pixel are fetched once per tile for the 4 samples) and is
+// persistent over tiles.  K is consumed in chunks of 32 channels: producer warps cp.async the raw rows (+ gamma, beta) into a
+// swizzled shared-memory ring; transform warps apply LReLU + LayerNorm + the hi/lo split and hand the A operand to the tensor
+// core -- for N <= 64 by writing it straight into TENSOR MEMORY (tcgen05.st; the MMA takes A from TMEM), for N = 128 through
+// K-major no-swizzle operand stages in shared memory (core matrix = 8 rows x 16 B; LBO = 128 B between K chunks, SBO = 1 KB
+// between 8-row groups); W (hi and lo) stays resident in shared memory in that same layout; one thread issues the MMAs and a
+// tcgen05.commit per chunk that releases the stage.  The epilogue reads the accumulator with tcgen05.ld, adds the halves onto
+// the prefetched residual, the bias, stores and accumulates the LayerNorm statistics of LReLU(out) for the consumer.
+// The same kernel computes the 1x1 DATA gradients (a.raw_in: operand taken as it is; a.w_trans: W read transposed; zero-padded
+// UMMA tile when the output width is not 16 / 32 / 64 / 128).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -26,11 +29,12 @@ namespace cnf {
 
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised persistent variant (the one the flow uses):
-//   warps 0-7   transform: cp.async ring -> LReLU + LayerNorm + hi/lo split -> UMMA operand stages
-//   warp  8     MMA issuer (one lane): waits full[stage], issues 3 tcgen05.mma per K-step, commits free[stage]
-//   warps 9-12  epilogue: wait tmem_full[buf], tcgen05.ld, + bias (+ residual), store, LN statistics,
+//   warps 0-7   transform: cp.async ring -> LReLU + LayerNorm + hi/lo split -> A operand stages (tensor memory, or shared)
+//   warp  8     MMA issuer (one lane): waits full[stage], issues 2 tcgen05.mma per K-step, commits free[stage]
+//   warps 9-16  epilogue: wait tmem_full[buf], tcgen05.ld, + bias (+ residual), store, LN statistics,
 //               arrive tmem_empty[buf]   (epilogue warp w owns TMEM lanes 32*(w%4).. = sample w%4)
-// The accumulator is double-buffered in TMEM (2 x N columns), so the epilogue of tile t overlaps the
+//   warps 17-20 producers: cp.async of the raw rows, gamma, beta; LayerNorm coefficients of the tile's samples
+// The accumulator is double-buffered in TMEM (2 x 2 N columns), so the epilogue of tile t overlaps the
 // transform + MMA of tile t+1, and nothing but the ring depth bounds the loads in flight.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
