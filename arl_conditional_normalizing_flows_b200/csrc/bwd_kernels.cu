@@ -1058,6 +1058,7 @@ struct WgradGcArgs {
   int B, h, w, nk, cat, ln;
   int dil, groups, out_off;
   int TH, TW, tiles_y, tiles_x, SB, teams;
+  int gchunk;   // groups per CTA (blockIdx.y selects the chunk): wide branches whose channels exceed the thread budget are split
 };
 
 // threads per CTA: a thread of the 32-wide variant holds 3 x 32 accumulators and needs the larger register budget
@@ -1068,7 +1069,9 @@ __global__ void __launch_bounds__(wgrad_gc_max_nt(G, KYS)) wgrad_gconv_kernel(co
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, NT = blockDim.x;
   const int net = blockIdx.z;
-  const int Cb = a.groups * G;
+  const int g0 = blockIdx.y * a.gchunk;                // first group of this CTA's chunk
+  const int Cb = min(a.gchunk, a.groups - g0) * G;     // channels of the chunk
+  const int cbase = g0 * G;
   const int tiles = a.tiles_y * a.tiles_x;
   const int tile = blockIdx.x % tiles, sb = blockIdx.x / tiles;
   const int y0 = (tile / a.tiles_x) * a.TH, x0 = (tile % a.tiles_x) * a.TW;
@@ -1078,8 +1081,8 @@ __global__ void __launch_bounds__(wgrad_gc_max_nt(G, KYS)) wgrad_gconv_kernel(co
   float* a_s = smem;                                   // [SH][SW][Cb]
   float* d_s = smem + ((SH * SW * Cb + 3) & ~3);       // [TH][TW][Cb]
   const float* P = a.params + (long long)net * a.net_stride;
-  const float* gam = P + a.g_off;
-  const float* bet = P + a.be_off;
+  const float* gam = P + a.g_off + cbase;
+  const float* bet = P + a.be_off + cbase;
   const int tpt = (3 / KYS) * Cb;
   const int team = tid / tpt, t = tid % tpt;
   const bool worker = team < a.teams;
@@ -1101,8 +1104,8 @@ __global__ void __launch_bounds__(wgrad_gc_max_nt(G, KYS)) wgrad_gconv_kernel(co
   for (int b = b0; b < b1; ++b) {
     float mean = 0.f, rstd = 1.f;
     if (a.ln) ln_coeffs(a.stats, (long long)net * a.B + b, (double)a.h * a.w * (double)a.nk, mean, rstd);
-    const float* xs = a.x + (long long)net * a.x_net_stride + (long long)b * a.h * a.w * a.nk;
-    const float* ds = a.dy + (long long)net * a.dy_net_stride + (long long)b * a.h * a.w * a.cat + a.out_off;
+    const float* xs = a.x + (long long)net * a.x_net_stride + (long long)b * a.h * a.w * a.nk + cbase;
+    const float* ds = a.dy + (long long)net * a.dy_net_stride + (long long)b * a.h * a.w * a.cat + a.out_off + cbase;
     __syncthreads();
     if (vec) {
       const int q = Cb >> 2;
@@ -1210,18 +1213,23 @@ __global__ void __launch_bounds__(wgrad_gc_max_nt(G, KYS)) wgrad_gconv_kernel(co
     }
   }
   __syncthreads();
-  float* gW = a.grads + (long long)net * a.net_stride + a.w_off;
-  float* gB = a.grads + (long long)net * a.net_stride + a.b_off;
+  float* gW = a.grads + (long long)net * a.net_stride + a.w_off + (long long)g0 * 9 * G * G;
+  float* gB = a.grads + (long long)net * a.net_stride + a.b_off + cbase;
   for (int i = tid; i < n_out; i += NT) atomicAdd(gW + i, red_w[i]);
   for (int i = tid; i < Cb; i += NT) atomicAdd(gB + i, red_b[i]);
 }
 
 template <int G, int KYS>
 static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
-  const int Cb = a.groups * G, d = a.dil;
-  const int tpt = (3 / KYS) * Cb;
+  const int d = a.dil;
   const int max_nt = wgrad_gc_max_nt(G, KYS);
-  if (tpt > max_nt) return CNF_NOT_ELIGIBLE;
+  // all groups of the branch in one CTA when its channels fit the thread budget, else chunks of whole groups (16-byte aligned)
+  a.gchunk = std::min(a.groups, max_nt / ((3 / KYS) * G));
+  if (a.gchunk < 1) return CNF_NOT_ELIGIBLE;
+  if (a.gchunk < a.groups && (a.gchunk * G) % 4) return CNF_NOT_ELIGIBLE;
+  const int n_chunks = (a.groups + a.gchunk - 1) / a.gchunk;
+  const int Cb = a.gchunk * G;
+  const int tpt = (3 / KYS) * Cb;
   a.TW = std::min(a.w, 32);
   a.TH = std::min(a.h, 32);
   auto bytes = [&](int th) { return (size_t)((((th + 2 * d) * (a.TW + 2 * d) * Cb + 3) & ~3) + th * a.TW * Cb) * sizeof(float); };
@@ -1239,7 +1247,7 @@ static int launch_wgrad_gconv_t(WgradGcArgs a, cudaStream_t st) {
   auto kern = wgrad_gconv_kernel<G, KYS>;
   static SmemAttrCache cache;
   CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
-  dim3 grid(tiles * sbs, 1, 2);
+  dim3 grid(tiles * sbs, n_chunks, 2);
   kern<<<grid, NT, smem, st>>>(a);
   return (int)cudaGetLastError();
 }

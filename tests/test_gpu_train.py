@@ -25,6 +25,10 @@ MID = dict(io_shape=[16, 16, 4], x_d=3, squeeze_factor_block_list=[0, 1, 1], Res
 # forward pass, 32-wide weight-gradient kernel and the generic grouped data gradient in the backward pass
 WIDE = dict(io_shape=[16, 16, 2], x_d=1, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
             num_kernels_list=[64], cardinality_list=[2])
+# config-5-heavy widths (256 kernels, cardinality 8: eight groups of 32 channels): the grouped weight gradient splits the branch
+# into chunks of four groups per CTA; 1x1 convs with 256 / 128 kernels run on the FFMA kernels
+HEAVY = dict(io_shape=[8, 8, 2], x_d=1, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
+             num_kernels_list=[256], cardinality_list=[8])
 CFG2_R1 = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[1] * 4,
                num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
 
@@ -99,7 +103,7 @@ def compare_grads_kink_tolerant(model, want, tol=GTOL, frac=0.9, hard=1e-1):
 
 
 @pytest.mark.parametrize("cfg,B,shape", [(TINY, 5, 'noise:4x4x2'), (SMALL, 6, 'noise:8x8x3'), (MID, 4, 'noise:16x16x4'),
-                                         (WIDE, 3, 'noise:16x16x2')])
+                                         (WIDE, 3, 'noise:16x16x2'), (HEAVY, 2, 'noise:8x8x2')])
 def test_gradients_match_autograd_oracle(dev, cfg, B, shape):
     m, o, _ = mk(cfg)
     xy = synth_inputs(shape, B, seed=3)
