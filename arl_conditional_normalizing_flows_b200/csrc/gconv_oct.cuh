@@ -53,6 +53,7 @@ struct OctArgs {
   int tma;                                      // 1: the tiles (zero halo included) arrive by TMA (cp.async.bulk.tensor.4d, 32-byte swizzle)
   int vec8;                                     // 256-bit stores: out 32-byte aligned, Cout % 8 == 0
   int nbuf;                                     // 2: cp.async double buffering inside the CTA; 1: single buffer, two CTAs per SM overlap
+  int ws;                                       // 1: warp-specialised body (TMA tiles, two buffers): OCT_PROD extra producer threads
   int dbg;                                      // CNF_OCT_DBG (timing experiments, wrong results): 1 skip branches, 2 transform, 4 copies, 8 epilogue, 16 coeffs, 32 weight loads (G = 8), 128 clock stamps
   OctBranch br[CNF_MAX_BRANCHES];
   unsigned short cta_first[OCT_MAX + 1];        // CTAs [cta_first[o], cta_first[o+1]) of a net own octet o
@@ -499,11 +500,258 @@ __device__ __forceinline__ void gconv_oct_body(const OctArgs& a, const CUtensorM
   cp_async_wait<0>();
 }
 
+// Warp-specialised variant (TMA tiles, two buffers): the LAST two warps of the CTA are producers.  They wait for the TMA tile
+// of item i + 1, turn the per-sample LayerNorm sums into coefficients, apply LReLU + LayerNorm in place and hand the buffer to
+// the consumer warps through an mbarrier, all while the consumers convolve item i; as soon as the consumers release a buffer
+// the producers re-arm its TMA.  The transform (2.6 k cycles per item on the whole CTA, clock stamps of round 1) and the
+// wait for the copies (0.8 k) no longer sit in front of the branches.  Consumer threads keep the thread -> column-segment
+// map and the fixed-order statistics of the single-role body, so results are bit-identical to it.
+constexpr int OCT_PROD = 64;   // producer threads (2 warps: 200 registers per thread stay available to the consumers)
+
+__device__ __forceinline__ void gconv_oct_body_ws(const OctArgs& a, const CUtensorMap* tmap) {
+  extern __shared__ __align__(1024) float oct_smem[];
+  __shared__ __align__(8) uint64_t tma_bar[2], xf_full[2], x_free[2];
+  const int tid = threadIdx.x, NT = blockDim.x - OCT_PROD, lane = tid & 31;   // NT = consumer threads
+  const int net = blockIdx.y;
+  const int hw = a.h * a.w;
+  int o = 0;
+  while (o + 1 < a.n_oct && (int)blockIdx.x >= (int)a.cta_first[o + 1]) ++o;
+  const int rank = blockIdx.x - a.cta_first[o], nshare = a.cta_first[o + 1] - a.cta_first[o];
+
+  const int xsz = a.S * a.SHW * 8;                          // floats per x buffer
+  float* xbuf = oct_smem;                                   // [2][S][SHW][8]
+  float* gb = xbuf + 2 * xsz;                               // [2][hw][8] gamma, beta of the octet
+  float* w_s = gb + (a.ln ? 2 * hw * 8 : 0);                // per branch [9][2][4G+4]
+  int wtot = 0;
+  for (int b = 0; b < a.n_br; ++b) wtot += oct_w_floats(a.br[b].G);
+  float* b_s = w_s + wtot;                                  // [n_br][8]
+  float* mr = b_s + a.n_br * 8;                             // [2][S][2]  (rstd, -mean rstd) per buffer parity
+  float* red = mr + 4 * a.S;                                // [2 parities][OCT_MAXT][2] partial sums
+  unsigned* segtab = reinterpret_cast<unsigned*>(red + 4 * OCT_MAXT);              // [n_br][OCT_MAXT]
+  unsigned short* pt = reinterpret_cast<unsigned short*>(segtab + a.n_br * OCT_MAXT);   // [hw] pixel offset inside a sample tile
+
+  const float* P = a.params + (long long)net * a.net_stride;
+  float* out_n = a.out + (long long)net * a.out_net_stride + o * 8;
+  const int NTA = blockDim.x;
+
+  // ---- one-time setup (all threads): barriers, tables, weights, gamma/beta ----
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tma_bar[i], 1);
+      mbar_init(&xf_full[i], OCT_PROD / 32);       // one arrival per producer warp
+      mbar_init(&x_free[i], NT / 32);              // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int p = tid; p < hw; p += NTA) {
+    const int y = p / a.w, x = p - y * a.w;
+    pt[p] = (unsigned short)((y + a.halo) * a.SW + x + a.halo);
+  }
+  for (int b = 0; b < a.n_br; ++b) {
+    const OctBranch& br = a.br[b];
+    if (o >= br.noct) continue;
+    const int G = br.G, HS = 4 * G + 4;
+    float* wd = w_s + br.w_smem;
+    const float* wsrc = P + br.w_off + (long long)o * (8 / G) * 9 * G * G;
+    for (int i = tid; i < 9 * 8 * G; i += NTA) {
+      const int co = i % G, ci = (i / G) % 8, tap = i / (8 * G);
+      const int grp = ci / G, cig = ci - grp * G;
+      wd[tap * 2 * HS + (ci >> 2) * HS + oct_w_pos(G, ci, co)] = wsrc[((grp * 9 + tap) * G + cig) * G + co];
+    }
+    if (tid < 8) b_s[b * 8 + tid] = P[br.b_off + o * 8 + tid];
+  }
+  if (a.ln) {
+    const float* gam = P + a.g_off + o * 8;
+    const float* bet = P + a.be_off + o * 8;
+    for (int i0 = tid; i0 < hw * 2; i0 += 4 * NTA) {
+      float4 gv[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(i0 + u * NTA, hw * 2 - 1);
+        gv[u] = ld4(gam + (long long)(i >> 1) * a.Cin + (i & 1) * 4);
+        bv[u] = ld4(bet + (long long)(i >> 1) * a.Cin + (i & 1) * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NTA;
+        if (i < hw * 2) {
+          st4(gb + (i >> 1) * 8 + (i & 1) * 4, gv[u]);
+          st4(gb + hw * 8 + (i >> 1) * 8 + (i & 1) * 4, bv[u]);
+        }
+      }
+    }
+  }
+  const int q = tid / a.tps, sl = tid - q * a.tps;
+  const bool tactive = tid < NT && q < a.S && sl < a.nsps;
+  const int seg_t = sl / a.w, seg_x = sl - seg_t * a.w;
+  if (tid < NT) {
+    for (int b = 0; b < a.n_br; ++b) {
+      const OctBranch& br = a.br[b];
+      const int d = br.dil;
+      const int r = seg_t / br.nsr, k = seg_t - r * br.nsr;
+      const int y0 = r + OCT_PX * k * d;
+      unsigned e = 0;
+      if (tactive && o < br.noct && r < d && y0 < a.h) {
+        int vmask = 0;
+#pragma unroll
+        for (int j = 0; j < OCT_PX; ++j) vmask |= (y0 + j * d < a.h) ? (1 << j) : 0;
+        e = 0x80000000u | ((unsigned)vmask << 8) | (unsigned)y0;
+      }
+      segtab[b * OCT_MAXT + tid] = e;
+    }
+  }
+  __syncthreads();
+
+  if (tid >= NT) {
+    // =============================== producers ===============================
+    const int ptid = tid - NT;
+    const double inv_n = 1.0 / ((double)hw * (double)a.Cin);   // mean and centred variance in fp64 (see ln_coeffs)
+    auto issue = [&](int item, int par) {
+      if (ptid == 0) {
+        const int b0 = item * a.S, ns = min(a.S, a.B - b0);
+        float* xb = xbuf + par * xsz;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the consumers' generic reads of this buffer come first
+        const uint32_t bar = smem_u32(&tma_bar[par]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(ns * a.SHW * 32)) : "memory");
+        for (int s = 0; s < ns; ++s) {
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+              ::"r"(smem_u32(xb + s * a.SHW * 8)), "l"((unsigned long long)tmap), "r"(o * 8), "r"(-a.halo), "r"(-a.halo),
+              "r"(net * a.B + b0 + s), "r"(bar)
+              : "memory");
+        }
+      }
+    };
+    int item = rank;
+    if (item < a.n_items) issue(item, 0);
+    for (int it = 0; item < a.n_items; ++it, item += nshare) {
+      const int par = it & 1;
+      const int b0 = item * a.S, ns = min(a.S, a.B - b0);
+      // LayerNorm coefficients of this item's samples (the loads fly while the tile lands)
+      if (ptid < a.S) {
+        float sc = 1.f, sh = 0.f;
+        const int s = b0 + ptid;
+        if (a.ln && s < a.B) {
+          const double* sp = a.stats_in + 2 * ((long long)net * a.B + s);
+          const double md = sp[0] * inv_n;
+          const float m = (float)md;
+          const float var = fmaxf((float)(sp[1] * inv_n - md * md), 0.f);
+          sc = 1.0f / sqrtf(var + (float)CNF_LN_EPS);
+          sh = -m * sc;
+        }
+        mr[(par * a.S + ptid) * 2] = sc;
+        mr[(par * a.S + ptid) * 2 + 1] = sh;
+      }
+      named_bar_sync(2, OCT_PROD);                 // coefficients visible to both producer warps
+      mbar_wait(&tma_bar[par], (it >> 1) & 1);     // the tile(s) of `item` have landed (async proxy -> visible)
+      float* xb = xbuf + par * xsz;
+      for (int s = 0; s < ns; ++s) {
+        const float sc = mr[(par * a.S + s) * 2], sh = mr[(par * a.S + s) * 2 + 1];
+        for (int i0 = ptid; i0 < hw * 2; i0 += 8 * OCT_PROD) {   // 8 units in flight per thread
+          float4 v[8], g[8], be[8];
+          float* px[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = min(i0 + u * OCT_PROD, hw * 2 - 1);
+            const int p = i >> 1, qd = (i & 1) * 4;
+            px[u] = xb + oct_xoff(s * a.SHW + pt[p], i & 1);
+            v[u] = ld4(px[u]);
+            if (a.ln) {
+              g[u] = ld4(gb + p * 8 + qd);
+              be[u] = ld4(gb + hw * 8 + p * 8 + qd);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 t = v[u];
+            t.x = lrelu(t.x); t.y = lrelu(t.y); t.z = lrelu(t.z); t.w = lrelu(t.w);
+            if (a.ln) {
+              t.x = fmaf(fmaf(t.x, sc, sh), g[u].x, be[u].x);
+              t.y = fmaf(fmaf(t.y, sc, sh), g[u].y, be[u].y);
+              t.z = fmaf(fmaf(t.z, sc, sh), g[u].z, be[u].z);
+              t.w = fmaf(fmaf(t.w, sc, sh), g[u].w, be[u].w);
+            }
+            if (i0 + u * OCT_PROD < hw * 2) st4(px[u], t);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xf_full[par]);   // transformed buffer -> consumers (release)
+      // re-arm the other buffer for the item after next as soon as the consumers have released it
+      const int next = item + nshare;
+      if (next < a.n_items) {
+        if (it >= 1) mbar_wait(&x_free[par ^ 1], ((it - 1) >> 1) & 1);   // consumers are done with item it - 1
+        issue(next, par ^ 1);
+      }
+    }
+    return;
+  }
+
+  // =============================== consumers ===============================
+  int item = rank;
+  for (int it = 0; item < a.n_items; ++it, item += nshare) {
+    const int par = it & 1;
+    const int b0 = item * a.S, ns = min(a.S, a.B - b0);
+    float* xb = xbuf + par * xsz;
+    mbar_wait(&xf_full[par], (it >> 1) & 1);       // LReLU + LayerNorm applied to the whole buffer (acquire)
+    const bool live = tactive && q < ns;
+    float2 s1p = make_float2(0.f, 0.f), s2p = make_float2(0.f, 0.f);
+    if (live) {
+      const int Pmax = (q + 1) * a.SHW - 1;
+      for (int b = 0; b < a.n_br; ++b) {
+        const unsigned e = segtab[b * OCT_MAXT + tid];
+        if (!(e >> 31)) continue;
+        const OctBranch& br = a.br[b];
+        const int d = br.dil, x = seg_x;
+        const int y0 = (int)(e & 255u), vmask = (int)((e >> 8) & 127u);
+        const int P0 = q * a.SHW + (y0 - d + a.halo) * a.SW + x - d + a.halo;
+        const float* wb = w_s + br.w_smem;
+        float* dptr = out_n + ((long long)(b0 + q) * hw + (long long)y0 * a.w + x) * a.Cout + br.out_off;
+        const long long jstride = (long long)d * a.w * a.Cout;
+        const bool vec8 = a.vec8 && !(br.out_off & 7);
+        switch (br.G) {
+          case 8: oct_branch<8>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
+          case 4: oct_branch<4>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
+          case 2: oct_branch<2>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
+          default: oct_branch<1>(xb, wb, b_s + b * 8, P0, Pmax, d * a.SW, d, dptr, jstride, vmask, vec8, s1p, s2p); break;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&x_free[par]);      // this warp no longer reads the buffer (release)
+    const float s1 = s1p.x + s1p.y, s2 = s2p.x + s2p.y;
+    // statistics of LReLU(out): fixed-order reduction (bit-reproducible run to run), fp64 across CTAs
+    if (a.stats_out) {
+      float* rd = red + par * 2 * OCT_MAXT;        // two parities: the flush of item i and the writes of item i + 1 never meet
+      if (a.nsps >= 32) {
+        const float a1 = warp_sum(s1), a2 = warp_sum(s2);       // the warp belongs to one sample
+        if (lane == 0) {
+          rd[2 * (tid >> 5)] = a1;
+          rd[2 * (tid >> 5) + 1] = a2;
+        }
+      } else {
+        rd[2 * tid] = s1;
+        rd[2 * tid + 1] = s2;
+      }
+      named_bar_sync(1, NT);
+      const int ft = NT >= 64 ? tid - 32 : tid;   // flushed by warp 1
+      if (ft >= 0 && ft < 2 * a.S && (ft >> 1) < ns) {
+        const int s = ft >> 1, which = ft & 1;
+        double t = 0.0;
+        const int cnt = a.nsps >= 32 ? (a.tps >> 5) : a.nsps;      // partial sums of sample s: per warp or per thread
+        for (int k = 0; k < cnt; ++k) t += (double)rd[2 * (s * cnt + k) + which];
+        atomicAdd(a.stats_out + 2 * ((long long)net * a.B + b0 + s) + which, t);
+      }
+    }
+  }
+}
+
 // 8 warps (2 per scheduler, each scheduler owns 16 K registers): up to 255 registers per thread.  The shared-memory carve-out
 // leaves almost no L1, so a spilled value costs an L2 round trip -- the kernel must not spill (ptxas -v: 0 bytes).
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) gconv_oct_kernel(const OctArgs a, const __grid_constant__ CUtensorMap tmap) {
-  gconv_oct_body(a, &tmap);
+__global__ void __launch_bounds__(MAXT + OCT_PROD, 1) gconv_oct_kernel(const OctArgs a, const __grid_constant__ CUtensorMap tmap) {
+  if (a.ws) gconv_oct_body_ws(a, &tmap);
+  else gconv_oct_body(a, &tmap);
 }
 
 // 4-D tensor map over the input [2 nets * B][h][w][Cin] with box [1][h + 2 halo][w + 2 halo][8] and the 32-byte swizzle (16-byte
@@ -573,7 +821,7 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (!nbuf_env) nbuf_env = knob_int("OCT_NBUF", 2) == 1 ? 1 : 2;
   a.nbuf = nbuf_env;
   auto smem_for = [&](int S) {
-    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 2 * OCT_MAXT +
+    size_t f = (size_t)a.nbuf * S * a.SHW * 8 + (g.ln ? (size_t)2 * hw * 8 : 0) + wtot + (size_t)g.n_br * 8 + 4 * S + 4 * OCT_MAXT +
                (size_t)g.n_br * OCT_MAXT;
     return f * sizeof(float) + (((size_t)hw * 2 + 15) & ~(size_t)15);
   };
@@ -657,7 +905,10 @@ static int launch_gconv_oct(const GconvArgs& g, cudaStream_t st) {
   if (tma_env && a.nbuf == 2 && g.in_net_stride == (long long)g.B * hw * g.Cin && (((uintptr_t)g.in) & 15) == 0 && SH <= 256 &&
       a.SW <= 256 && (a.SHW % 4) == 0 && ((S * a.SHW) % 8) == 0)
     a.tma = oct_make_tmap(&tm, g.in, 2 * g.B, g.h, g.w, g.Cin, SH, a.SW) ? 1 : 0;
-  gconv_oct_kernel<OCT_MAXT><<<dim3(tot, 2), NT, smem, st>>>(a, tm);
+  static int ws_env = -1;
+  if (ws_env < 0) ws_env = knob_int("OCT_WS", 1) ? 1 : 0;
+  a.ws = (a.tma && a.nbuf == 2 && ws_env && NT == OCT_MAXT) ? 1 : 0;   // producer warps: TMA tiles, one full-size CTA per SM
+  gconv_oct_kernel<OCT_MAXT><<<dim3(tot, 2), NT + (a.ws ? OCT_PROD : 0), smem, st>>>(a, tm);
   return (int)cudaGetLastError();
 }
 
