@@ -9,7 +9,9 @@
 // shared memory for the whole launch, and the next item's raw tile (zero halo included) arrives by TMA
 // (cp.async.bulk.tensor.4d with the 32-byte swizzle, completion on an mbarrier; 16-byte cp.async pieces where the shape does
 // not allow a tensor map) while the current item is transformed (LReLU + LayerNorm, in place) and convolved.  Octets that feed more branches get proportionally more CTAs
-// (host-side split, launch_gconv_oct).
+// (host-side split, launch_gconv_oct).  With TMA tiles and a full-size CTA the kernel is warp-specialised (gconv_oct_body_ws): two
+// producer warps do the waiting, the LayerNorm coefficients and the in-place transform of item i + 1 while eight consumer warps
+// convolve item i (mbarrier hand-offs both ways).
 //
 // Compute: a thread owns a COLUMN SEGMENT of OCT_PX = 7 output pixels spaced `dil` rows apart x the full octet (8 in, 8 out).
 // For each kx it loads the 9 input rows the segment's 3 ky taps touch ONCE (9 x 128-bit shared loads per channel quad) and
