@@ -60,6 +60,10 @@ class BlockInfo(Structure):
                 ("n_channelwise", c_int), ("channelwise", c_int * CNF_MAX_BRANCHES)]
 
 
+# cnf_layer_grads_ready_fn (include/cnf.h): void (*)(void* user, int layer, int64_t param_offset, int64_t param_count)
+LAYER_GRADS_READY_FN = ctypes.CFUNCTYPE(None, c_void_p, c_int, c_int64, c_int64)
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -101,6 +105,7 @@ def _load():
         "cnf_flow_loss_and_grad_recompute": (I, [P, P, P, P, P, P, P, P, P, P, V]),
         "cnf_plan_train_workspace_bytes_invert": (I64, [P, I64]),
         "cnf_flow_loss_and_grad_invert": (I, [P, P, P, P, P, P, P, P, P, P, V]),
+        "cnf_flow_loss_and_grad_hooked": (I, [P, P, P, P, P, P, P, P, P, P, V, I, LAYER_GRADS_READY_FN, V]),
         "cnf_adam_step": (I, [P, P, P, P, I64, D, D, D, D, D, V]),
         "cnf_coupling_forward": (I, [P, P, P, P, P, P, V]),
         "cnf_coupling_backward": (I, [P, P, P, P, P, V]),

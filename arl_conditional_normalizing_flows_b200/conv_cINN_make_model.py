@@ -15,9 +15,10 @@ from ctypes import byref, c_int, c_void_p
 
 import numpy as np
 import torch
+import torch.distributed
 
 from . import _lib, initializers
-from ._lib import lib, check, Borrowed, stream_ptr, require_cuda, int_array
+from ._lib import lib, check, Borrowed, stream_ptr, require_cuda, int_array, LAYER_GRADS_READY_FN
 from .conv_cINN_base_functions import dilated_residual_block  # noqa: F401  (reference import, M:24)
 
 
@@ -730,9 +731,17 @@ class cFlow:
             self._train_ws = ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
         return ws
 
-    def loss_and_grad(self, xy):
+    def _grad_buffer(self):
+        if getattr(self, '_grads', None) is None or self._grads.device != self.params.device:
+            self._grads = torch.empty_like(self.params)
+        return self._grads
+
+    def loss_and_grad(self, xy, on_layer_grads=None):
         """log_loss(xy) plus dloss/dparams as ONE flat tensor with the layout of self.params (hand-written
-        backward kernels).  Returns ((loss, z_loss, y_loss, detJ_loss), grads)."""
+        backward kernels).  Returns ((loss, z_loss, y_loss, detJ_loss), grads).
+        on_layer_grads(layer, offset, count), if given, is called on the host in backward order as soon as the kernels
+        that complete grads[offset: offset + count] of coupling layer `layer` are enqueued on the current stream
+        (cnf_flow_loss_and_grad_hooked): the hook of the overlapped gradient all-reduce, sharding.BucketedGradAllReduce."""
         xy = self._check_io(xy, "xy")
         B = xy.shape[0]
         dev = xy.device
@@ -741,15 +750,21 @@ class cFlow:
         pers = torch.empty((3, Bp), dtype=torch.float32, device=dev)
         loss4 = torch.empty(4, dtype=torch.float32, device=dev)
         ll_z, ll_y, ld = pers[0, :B], pers[1, :B], pers[2, :B]
-        if getattr(self, '_grads', None) is None or self._grads.device != self.params.device:
-            self._grads = torch.empty_like(self.params)
+        grads = self._grad_buffer()
         br = Borrowed()
-        fn = self._train_fns()[1]
-        check(fn(self._plan, br(xy), br(self.params), br(self._grads), br(zy), br(ll_z), br(ll_y), br(ld), br(loss4),
-                 br(self._train_workspace(B)), stream_ptr()))
+        if on_layer_grads is None:
+            fn = self._train_fns()[1]
+            check(fn(self._plan, br(xy), br(self.params), br(grads), br(zy), br(ll_z), br(ll_y), br(ld), br(loss4),
+                     br(self._train_workspace(B)), stream_ptr()))
+        else:
+            mode = 2 if self.recover_states_by_inverse else 1 if self.recompute_activations else 0
+            cb = LAYER_GRADS_READY_FN(lambda _user, layer, off, count: on_layer_grads(layer, off, count))
+            check(lib.cnf_flow_loss_and_grad_hooked(self._plan, br(xy), br(self.params), br(grads), br(zy), br(ll_z), br(ll_y),
+                                                    br(ld), br(loss4), br(self._train_workspace(B)), stream_ptr(), mode,
+                                                    cb, None))
         self.last_logdet_per_sample = ld
         self.last_per_sample = {'ll_z': ll_z, 'll_y': ll_y, 'logdet': ld, 'zy': zy}
-        return (loss4[0], loss4[1], loss4[2], loss4[3]), self._grads
+        return (loss4[0], loss4[1], loss4[2], loss4[3]), grads
 
     def grad_views(self, grads=None):
         """the flat gradient buffer as the same named views get_weights() uses: [{'A': {...}, 'b': {...}}, ...]"""
@@ -760,19 +775,32 @@ class cFlow:
             out.append(layer.weight_views(grads[off: off + layer.params.numel()]))
         return out
 
+    # data-parallel train_step: gradient buckets of at least this many bytes are all-reduced while the backward pass is
+    # still running (sharding.BucketedGradAllReduce); 0 / None: one flat all-reduce after the backward pass
+    grad_bucket_bytes = 8 << 20
+
     def train_step(self, xy):
         """cFlow.train_step (M:1850-1880): gradients of log_loss, optimizer.apply_gradients, metric trackers.
-        Data-parallel (torch.distributed initialised): one sum all-reduce of the flat gradient buffer over
-        NCCL (sharding.allreduce_mean_gradients); the reported metrics are this rank's shard's."""
+        Data-parallel (torch.distributed initialised): the flat gradient buffer is sum all-reduced over NCCL in buckets of
+        coupling layers, each issued as soon as the backward pass has completed it (sharding.BucketedGradAllReduce,
+        SURVEY 8e; grad_bucket_bytes = 0: one all-reduce after the backward pass, sharding.allreduce_mean_gradients);
+        the reported metrics are this rank's shard's."""
         if self.optimizer is None:
             raise RuntimeError("train_step: call model.compile(optimizer=Adam(...)) first")   # keras raises too
-        from .sharding import allreduce_mean_gradients, sync_replicas
+        from .sharding import BucketedGradAllReduce, allreduce_mean_gradients, sync_replicas
         if not getattr(self, '_replicas_synced', False):
             # data-parallel replicas must start from the same weights / optimizer state (rank 0's); single process: no-op
             sync_replicas(self)
             self._replicas_synced = True
-        four, grads = self.loss_and_grad(xy)
-        allreduce_mean_gradients(grads, xy.shape[0])
+        parallel = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        if parallel and self.grad_bucket_bytes:
+            red = BucketedGradAllReduce(self._grad_buffer(), xy.shape[0], self.grad_bucket_bytes)
+            four, grads = self.loss_and_grad(xy, on_layer_grads=red.layer_ready)
+            red.finish()
+        else:
+            four, grads = self.loss_and_grad(xy)
+            allreduce_mean_gradients(grads, xy.shape[0])
         self.optimizer.apply_gradients(self.params, grads)
         return self._update_trackers(four)
 

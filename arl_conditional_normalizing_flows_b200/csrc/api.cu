@@ -256,7 +256,8 @@ int64_t cnf_plan_train_workspace_bytes_invert(const cnf_plan* p, int64_t batch) 
 static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
                               DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
                               DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream,
-                              int mode) {
+                              int mode, cnf_layer_grads_ready_fn ready = nullptr, void* user = nullptr) {
+  if (mode < 0 || mode > 2) return fail(CNF_ERR_ARG, "training mode must be 0 (saved), 1 (recompute) or 2 (invert)");
   const bool recompute = mode != 0, invert = mode == 2;
   if (!p) return fail(CNF_ERR_ARG, "null plan");
   Ten X, P, Gd, Z, A, Bt, L, F, W;
@@ -349,8 +350,18 @@ static int flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, cons
     FlowView sview = make_view(saved[li].state, p->H, p->W, p->D, p->level[li]);
     TRY(cuda_rc(run_coupling_backward(c, P.p + p->param_off[li], Gd.p + p->param_off[li], saved[li], gv, sview, (int)B,
                                       invB, scratch, stream), "coupling layer backward"));
+    // everything that writes grads[param_off[li], + param_count) is enqueued: the caller may queue this slice's collective
+    // behind the stream's current position while the layers below are still being differentiated
+    if (ready) ready(user, li, p->param_off[li], 2 * c->net_stride);
   }
   return CNF_OK;
+}
+
+int cnf_flow_loss_and_grad_hooked(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                                  DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z, DLManagedTensor* ll_y,
+                                  DLManagedTensor* logdet, DLManagedTensor* loss4, DLManagedTensor* workspace, void* stream,
+                                  int mode, cnf_layer_grads_ready_fn ready, void* user) {
+  return flow_loss_and_grad(p, xy, params, grads, zy, ll_z, ll_y, logdet, loss4, workspace, stream, mode, ready, user);
 }
 
 int cnf_flow_loss_and_grad(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,

@@ -4,7 +4,9 @@ F:350-360), so the data path has NO collective; the only cross-sample quantities
 of cFlow.log_loss (M:1325, M:1840), recovered exactly from per-shard sums with one tiny all-reduce.
 Training (cFlow.train_step, M:1850-1880) is data-parallel: every rank differentiates the mean loss of its own
 shard and ONE sum all-reduce of the flat gradient buffer (NCCL over NVLink on the GPUs, gloo in the CPU tests)
-gives the gradient of the global-batch loss; every rank then applies the identical Adam update.
+gives the gradient of the global-batch loss; every rank then applies the identical Adam update.  With
+`BucketedGradAllReduce` that all-reduce is issued per bucket of coupling layers, in the order the backward pass completes
+them, so the transfer of the upper layers' gradients overlaps the differentiation of the lower ones.
 """
 import torch
 import torch.distributed as dist
@@ -85,3 +87,82 @@ def allreduce_mean_gradients(grads, n_local, group=None):
     grads.mul_((n / total).to(grads.dtype))
     dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)
     return grads
+
+
+class BucketedGradAllReduce:
+    """The gradient all-reduce of a data-parallel train_step, overlapped with the backward pass.
+
+    libcnf's backward pass walks the coupling layers from the last to the first and reports, through the
+    `cnf_layer_grads_ready_fn` hook of `cnf_flow_loss_and_grad_hooked`, every layer whose slice of the flat gradient
+    buffer is complete on the compute stream.  `layer_ready` merges consecutive slices into buckets of at least
+    `bucket_bytes` (sized for launch latency, not link count: NVSwitch gives every pair full bandwidth) and issues one
+    asynchronous sum all-reduce per bucket; NCCL orders it behind the compute stream's position at that moment and runs it
+    on its own stream while the layers below are still being differentiated.  `finish` reduces whatever the hook did not
+    cover and makes the compute stream wait for every bucket.  The result equals `allreduce_mean_gradients` (the slices
+    are scaled by n_local / N before the sum, so uneven shards are weighted correctly); a single process does nothing.
+    """
+
+    def __init__(self, grads, n_local, bucket_bytes=8 << 20, group=None):
+        self.grads = grads
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.bucket_elems = max(1, int(bucket_bytes) // grads.element_size())
+        self.works = []
+        self.buckets = []            # (lo, hi) element ranges already handed to the collective, in issue order
+        self._lo = self._hi = None   # pending contiguous range
+        self.error = None            # an exception raised inside the ctypes callback (ctypes would only print it)
+        if self.active:
+            n = torch.tensor([float(n_local)], dtype=torch.float64, device=grads.device)
+            total = n.clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)      # 8 bytes, queued before the backward pass
+            self.scale = (n / total).to(grads.dtype)
+
+    def layer_ready(self, layer, offset, count):
+        """grads[offset, offset + count) of coupling layer `layer` is complete on the current stream."""
+        if not self.active or self.error is not None:
+            return
+        try:
+            lo, hi = int(offset), int(offset) + int(count)
+            if self._lo is None:
+                self._lo, self._hi = lo, hi
+            elif hi == self._lo:            # the backward pass moves down the buffer
+                self._lo = lo
+            elif lo == self._hi:
+                self._hi = hi
+            else:
+                self._flush()
+                self._lo, self._hi = lo, hi
+            if self._hi - self._lo >= self.bucket_elems:
+                self._flush()
+        except Exception as e:      # noqa: BLE001 -- re-raised by finish()
+            self.error = e
+
+    def _reduce(self, lo, hi):
+        if hi <= lo:
+            return
+        sl = self.grads[lo:hi]
+        sl.mul_(self.scale)
+        self.works.append(dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.buckets.append((lo, hi))
+
+    def _flush(self):
+        if self._lo is not None:
+            self._reduce(self._lo, self._hi)
+            self._lo = self._hi = None
+
+    def finish(self):
+        """Reduce what the hook did not report (nothing, for a cFlow plan) and wait for every bucket."""
+        if self.error is not None:
+            raise self.error
+        if not self.active:
+            return self.grads
+        self._flush()
+        pos = 0
+        for lo, hi in sorted(self.buckets):
+            self._reduce(pos, lo)
+            pos = max(pos, hi)
+        self._reduce(pos, self.grads.numel())
+        for w in self.works:
+            w.wait()          # NCCL: the current stream waits for the collective's stream; gloo: blocks the host
+        self.works = []
+        return self.grads

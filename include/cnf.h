@@ -189,6 +189,20 @@ int cnf_flow_loss_and_grad_invert(const cnf_plan* p, const DLManagedTensor* xy, 
                                   DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
                                   DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
                                   DLManagedTensor* workspace, void* stream);
+/* The same three training modes (mode 0 = saved activations, 1 = recompute, 2 = invert) with a host-side hook for the
+ * data-parallel gradient all-reduce of cFlow.train_step (M:1850-1880 run under a distribution strategy): the
+ * backward pass walks the coupling layers from the last to the first, and `ready(user, layer, param_offset, param_count)`
+ * is called ON THE HOST, in that order, as soon as every kernel that writes grads[param_offset, param_offset + param_count)
+ * has been enqueued on `stream`.  Work the callback queues behind the stream's current position (an event + a collective
+ * on another stream) therefore overlaps the backward pass of the layers below.  The callback must not touch the other
+ * arguments of the call; ready = NULL gives the plain entry points above.  Replaces nothing in the reference (keras
+ * hides the bucketing inside its strategy). */
+typedef void (*cnf_layer_grads_ready_fn)(void* user, int layer, int64_t param_offset, int64_t param_count);
+int cnf_flow_loss_and_grad_hooked(const cnf_plan* p, const DLManagedTensor* xy, const DLManagedTensor* params,
+                                  DLManagedTensor* grads, DLManagedTensor* zy, DLManagedTensor* ll_z,
+                                  DLManagedTensor* ll_y, DLManagedTensor* logdet, DLManagedTensor* loss4,
+                                  DLManagedTensor* workspace, void* stream, int mode, cnf_layer_grads_ready_fn ready,
+                                  void* user);
 /* optimizer.apply_gradients with keras Adam (M:1874; C:567 / P:130: lr 3e-4, beta 0.9/0.999, eps 1e-7):
  * one fused update of the flat parameter buffer; `step` counts from 1; grads are multiplied by
  * grad_scale first (1/world_size after a data-parallel sum all-reduce). */

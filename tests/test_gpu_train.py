@@ -315,3 +315,40 @@ def test_gradients_do_not_depend_on_the_kernel_family(dev, cfg, B, shape):
     diff = (g_b - g_a).abs()
     assert float(torch.quantile(diff[::max(1, diff.numel() // 4_000_000)].float(), 0.999)) <= 1e-4 * scale
     assert float(diff.norm()) <= 1e-3 * float(g_a.norm())
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_layer_hook_reports_every_layer_in_backward_order(dev, mode):
+    """cnf_flow_loss_and_grad_hooked: the hook of the overlapped gradient all-reduce is called once per coupling
+    layer, from the last layer to the first, with slices that tile the flat gradient buffer; the gradients are those of
+    the plain entry point (up to the arrival order of the fp32 atomics, as in the recompute test), in every training mode."""
+    m, _, _ = mk(SMALL, 'init' if mode == 2 else 'rand', seed=4)
+    m.recompute_activations = mode == 1
+    m.recover_states_by_inverse = mode == 2
+    x = torch.from_numpy(synth_inputs('noise:8x8x3', 6, seed=5)).to(dev)
+    four_a, g_a = m.loss_and_grad(x)
+    four_a = [float(t) for t in four_a]
+    g_a = g_a.clone()
+    seen = []
+    four_b, g_b = m.loss_and_grad(x, on_layer_grads=lambda layer, off, count: seen.append((layer, off, count)))
+    n = len(m.coupling_layers)
+    assert [s[0] for s in seen] == list(range(n - 1, -1, -1))
+    pos = m.params.numel()
+    for layer, off, count in seen:                      # contiguous, moving down the buffer, ending at 0
+        assert off + count == pos and count == m.coupling_layers[layer].params.numel()
+        pos = off
+    assert pos == 0
+    np.testing.assert_allclose([float(t) for t in four_b], four_a, rtol=1e-6)
+    assert float((g_b - g_a).abs().max()) <= 2e-5 * float(g_a.abs().max())
+
+
+def test_layer_hook_errors_surface(dev):
+    """an exception inside the hook must not be swallowed by ctypes: BucketedGradAllReduce keeps it and finish() re-raises"""
+    from arl_conditional_normalizing_flows_b200.sharding import BucketedGradAllReduce
+    m, _, _ = mk(TINY, 'rand', seed=4)
+    x = torch.from_numpy(synth_inputs('noise:4x4x2', 3, seed=5)).to(dev)
+    red = BucketedGradAllReduce(m._grad_buffer(), 3)
+    red.active = True                                   # no process group here: the collective call fails inside the hook
+    m.loss_and_grad(x, on_layer_grads=red.layer_ready)
+    with pytest.raises(Exception):
+        red.finish()

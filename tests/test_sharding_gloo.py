@@ -162,3 +162,69 @@ def test_two_rank_replicas_are_synchronised_before_training():
         assert before is False and did is True and after is True
         assert it == 7 and m0 == 0.25 and v0 == 0.5
     np.testing.assert_array_equal(res[0][4], res[1][4])
+
+
+# ---- the overlapped, bucketed form of the gradient all-reduce (sharding.BucketedGradAllReduce) ----------------------
+def _bucket_worker(rank, world, port, n_local, bucket_bytes, q):
+    from arl_conditional_normalizing_flows_b200.sharding import BucketedGradAllReduce
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(10 + rank)
+    local = torch.randn(1000, generator=g, dtype=torch.float32)
+    flat = local.clone()
+    allreduce_mean_gradients(flat, n_local[rank])
+    # the backward pass reports the coupling layers from the last to the first; [0, 40) and [900, 1000) are never
+    # reported (finish() must still reduce them), the layer slices are uneven
+    layers = [(40, 150), (200, 100), (300, 350), (650, 250)]        # (offset, count); [190, 200) is a hole as well
+    buf = local.clone()
+    red = BucketedGradAllReduce(buf, n_local[rank], bucket_bytes=bucket_bytes)
+    for li in reversed(range(len(layers))):
+        red.layer_ready(li, *layers[li])
+    red.finish()
+    q.put((rank, flat.numpy(), buf.numpy(), list(red.buckets)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_local,bucket_bytes", [((3, 3), 1200), ((4, 1), 1), ((2, 5), 1 << 20)])
+def test_two_rank_bucketed_allreduce_equals_flat_allreduce(n_local, bucket_bytes):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, n_local, bucket_bytes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, flat, bucketed, buckets in res:
+        np.testing.assert_allclose(bucketed, flat, rtol=1e-6, atol=1e-7)
+        # every element went through exactly one collective
+        cover = np.zeros(1000, np.int32)
+        for lo, hi in buckets:
+            cover[lo:hi] += 1
+        assert (cover == 1).all()
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    first = res[0][3]
+    if bucket_bytes == 1:           # one bucket per layer, issued in backward order, then the unreported ranges
+        assert first[:4] == [(650, 900), (300, 650), (200, 300), (40, 190)]
+    if bucket_bytes == 1 << 20:     # everything reported merges into as few buckets as contiguity allows
+        assert first[0] == (200, 900)
+
+
+def test_bucketed_allreduce_single_process_is_a_no_op_and_reraises_hook_errors():
+    from arl_conditional_normalizing_flows_b200.sharding import BucketedGradAllReduce
+    g = torch.arange(10, dtype=torch.float32)
+    red = BucketedGradAllReduce(g, 4)
+    red.layer_ready(0, 0, 10)
+    assert red.finish() is g and torch.equal(g, torch.arange(10, dtype=torch.float32))
+    red = BucketedGradAllReduce(g, 4)
+    red.active = True                       # force the bucket path without a process group: the error must surface
+    red.layer_ready(0, 0, 10)
+    with pytest.raises(Exception):
+        red.finish()
