@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(GTC_NT, 1) gconv_tc_kernel(const GtcArgs a) {
 
   for (; it < a.n_items; it += a.ctas_per_ng, buf ^= 1) {
     if (wid == GTC_WT) {
-      // ---- 9 taps x G / 8 K-steps x 2 MMAs on buffer `buf`, one thread
-      if (lane == 0) {
+      // ---- 9 taps x G / 8 K-steps x 2 MMAs on buffer `buf`, one (elected) thread
+      if (elect_one()) {
         tc_fence_after();
         constexpr uint32_t idesc2 = umma_idesc_tf32(2 * G), idesc1 = umma_idesc_tf32(G);
         const uint32_t lbo_a = (uint32_t)a.NPXP * 16u, sbo_a = (uint32_t)SW * 16u;

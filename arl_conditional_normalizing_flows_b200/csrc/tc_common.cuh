@@ -36,6 +36,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One thread of a CONVERGED warp (every lane must reach this call).  Unlike `lane == 0`, the compiler knows that exactly one
+// thread runs the guarded region, so tcgen05.mma / tcgen05.commit -- whose operands live in uniform registers -- become single
+// UTCHMMA / UTCBAR instructions instead of an ELECT / BRA.U.ANY loop over the "possibly several" active lanes (10 instructions
+// per MMA less in the issuer thread, whose instruction stream paces the 1x1 kernel: tools/microbench/umma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t leader;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+  return leader != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (wid == TW) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       // B = [hi rows | lo rows] is one K-major operand of 2 N rows (the two blocks are adjacent and share the layout), so
       // hi(A) * [hi(B) | lo(B)] is ONE instruction of width 2 N and the A operand is read twice per K-step instead of
       // three times; lo(A) * hi(B) accumulates into the first N columns
@@ -403,16 +403,28 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           // the descriptors of a K-step differ from those of step 0 only in the start-address field (16-byte units;
           // shared-memory addresses stay below 2^18, so the 14-bit field never carries): one 64-bit add each
           const uint64_t dah0 = umma_desc(a_hi, LBO, SBO), dal0 = umma_desc(a_lo, LBO, SBO), dbh0 = umma_desc(b_hi, LBO, SBO);
-          for (int ks = 0; ks < ((a.dbg & 4) ? (c == 0 ? 1 : 0) : (kc + 7) / 8); ++ks) {
+          // one K-step: hi(A) [hi(B) | lo(B)] (width 2 N) then lo(A) hi(B) (width N)
+          auto kstep = [&](const int ks, const uint32_t acc) {
             const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);
             if constexpr (ATM) {
               const uint32_t at = tmem_d + A_TM + stage * 2 * KC + 8 * ks;   // hi columns of this K-step; lo KC further
-              umma_tf32_ts(d_addr, at, dbh0 + adv, idesc2, (c | ks) != 0);
+              umma_tf32_ts(d_addr, at, dbh0 + adv, idesc2, acc);
               umma_tf32_ts(d_addr, at + KC, dbh0 + adv, idesc1, 1);
             } else {
-              umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, (c | ks) != 0);
+              umma_tf32(d_addr, dah0 + adv, dbh0 + adv, idesc2, acc);
               umma_tf32(d_addr, dal0 + adv, dbh0 + adv, idesc1, 1);
             }
+          };
+#ifdef CNF_DEBUG
+          const int nks = (a.dbg & 4) ? (c == 0 ? 1 : 0) : (kc + 7) / 8;
+#else
+          const int nks = (kc + 7) / 8;
+#endif
+          if (nks == KC / 8) {                    // full chunk: straight-line code, every offset an immediate
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) kstep(ks, ks ? 1u : (uint32_t)(c != 0));
+          } else {
+            for (int ks = 0; ks < nks; ++ks) kstep(ks, (uint32_t)((c | ks) != 0));
           }
           TC3_STAMP(1, gi, 2);
           // poll the NEXT chunk's barrier before the commits: the ~250-cycle latency of the try_wait overlaps them (this

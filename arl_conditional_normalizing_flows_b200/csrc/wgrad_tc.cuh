@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(WGT_NT, 2) wgrad_tc_kernel(const WgtArgs a) {
 
   for (; st < a.n_stages; st += a.nc, buf ^= 1) {
     if (wid == WGT_WT) {
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         constexpr uint32_t idesc2 = umma_idesc_tf32(2 * NB), idesc1 = umma_idesc_tf32(NB);
         constexpr uint32_t LBO = 128, SBO = KQ8 * 128;
