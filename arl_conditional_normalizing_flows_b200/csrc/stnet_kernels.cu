@@ -1654,15 +1654,66 @@ static int launch_pw_t(GemmArgs a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-// warp-specialised persistent tcgen05 1x1 conv; CNF_NOT_ELIGIBLE when the resident-W image does not fit
-template <int N, int TW, int NST, bool PADN, bool ATM, int KCH = 32>
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link); nullptr if unavailable
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      return (tmap_encode_fn)ptr;
+    return (tmap_encode_fn) nullptr;
+  }();
+  return fn;
+}
+
+// Tensor maps of the TMA producer of pw_tc3_kernel (tc_kernels.cuh, Tc3Maps): false when a pointer / stride does not meet
+// the 16-byte rules of a tensor map (the caller then uses the cp.async producer).
+static bool tc3_make_maps(const GemmArgs& a, Tc3Maps* m) {
+  tmap_encode_fn fn = tmap_encoder();
+  if (!fn) return false;
+  auto ok16 = [](long long bytes) { return bytes > 0 && (bytes % 16) == 0; };
+  const long long row = (long long)a.K * 4, img = (long long)a.hw * a.K * 4;
+  if (!ok16(row) || ((uintptr_t)a.in & 15) || !ok16(a.in_net_stride * 4)) return false;
+  const cuuint32_t one[4] = {1, 1, 1, 1};
+  {
+    const cuuint64_t gdim[4] = {(cuuint64_t)a.K, (cuuint64_t)a.hw, (cuuint64_t)a.B, 2};
+    const cuuint64_t gstr[3] = {(cuuint64_t)row, (cuuint64_t)img, (cuuint64_t)a.in_net_stride * 4};
+    const cuuint32_t box[4] = {32, 32, 4, 1};
+    if (fn(&m->x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.in, gdim, gstr, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  if (a.ln) {
+    const float* g = a.params + a.g_off;
+    const float* b = a.params + a.be_off;
+    if (((uintptr_t)g & 15) || ((uintptr_t)b & 15) || !ok16(a.net_stride * 4)) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.K, (cuuint64_t)a.hw, 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)row, (cuuint64_t)a.net_stride * 4};
+    const cuuint32_t box[3] = {32, 32, 1};
+    for (int i = 0; i < 2; ++i)
+      if (fn(i ? &m->b : &m->g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(i ? b : g), gdim, gstr, box, one,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+  }
+  return true;
+}
+
+// warp-specialised persistent tcgen05 1x1 conv; CNF_NOT_ELIGIBLE when the resident-W image does not fit (or, TMA, when the
+// tensors do not meet the tensor-map alignment rules)
+template <int N, int TW, int NST, bool PADN, bool ATM, int KCH = 32, bool TMA = false>
 static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   const int nchunks = (a.K + KCH - 1) / KCH;
   const size_t ops = ATM ? 0 : (size_t)NST * 2 * 128 * 32;           // operand stages: shared memory, or tensor memory (ATM)
   const size_t depth = (ATM && KCH == 32) ? 5 : 3;
   const size_t smem = (ops + depth * 6 * (32 * KCH / 4) * 4 + (size_t)nchunks * 2 * N * KCH) * sizeof(float);
   if (smem > 225 * 1024) return CNF_NOT_ELIGIBLE;
-  auto kern = pw_tc3_kernel<N, TW, NST, PADN, ATM, KCH>;
+  Tc3Maps maps{};
+  if (TMA && !tc3_make_maps(a, &maps)) return CNF_NOT_ELIGIBLE;
+  auto kern = pw_tc3_kernel<N, TW, NST, PADN, ATM, KCH, TMA>;
   static SmemAttrCache cache;
   CU_TRY((cudaError_t)ensure_dynamic_smem((const void*)kern, smem, cache));
   int n_sm = 0;
@@ -1671,7 +1722,7 @@ static int launch_pw_tc3_tw(const GemmArgs& a, cudaStream_t st) {
   const int grid = std::min(2 * tiles_p * tiles_s, n_sm & ~1);
   GemmArgs b = a;
   { static int dbg = -1; if (dbg < 0) dbg = knob_int("PW_DBG", 0); b.dbg = dbg; }
-  kern<<<grid, (TW + 1 + 8 + 4) * 32, smem, st>>>(b, tiles_p, tiles_s);
+  kern<<<grid, (TW + 1 + 8 + (TMA ? 1 : 4)) * 32, smem, st>>>(b, tiles_p, tiles_s, maps);
   return (int)cudaGetLastError();
 }
 
@@ -1685,6 +1736,12 @@ static int launch_pw_tc3_p(const GemmArgs& a, cudaStream_t st) {
     if (atm) {
       // 32-channel chunks, 3 TMEM stages of 64 columns.  (64-channel chunks with 2 stages of 128 columns, KCH = 64, measured
       // slower: 77.7 / 133.0 us against 70.8 / 112.7 us, profiles/r02_summary.md)
+      static int tma = -1;
+      if (tma < 0) tma = knob_int("PW_TMA", 1);
+      if (tma) {     // raw ring filled by bulk tensor copies (one producer thread)
+        const int rc = launch_pw_tc3_tw<N, 8, 3, PADN, true, 32, true>(a, st);
+        if (rc != CNF_NOT_ELIGIBLE) return rc;
+      }
       const int rc = launch_pw_tc3_tw<N, 8, 3, PADN, true>(a, st);
       if (rc != CNF_NOT_ELIGIBLE) return rc;
     }

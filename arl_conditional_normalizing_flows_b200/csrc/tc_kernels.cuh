@@ -18,6 +18,7 @@
 // UMMA tile when the output width is not 16 / 32 / 64 / 128).
 #pragma once
 
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -40,6 +41,26 @@ namespace cnf {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// TMA variant of the producer role: tensor maps over the input [K, hw, B, 2 nets] (box 32 channels x 32 pixels x 4 samples) and
+// over gamma / beta [K, hw, 2 nets] (box 32 x 32), all with the 128-byte swizzle -- exactly the raw-ring layout the transform
+// warps read (16-byte unit q of row r at r * 8 + (q ^ (r & 7))); rows / channels / samples beyond the tensor arrive as zeros.
+struct Tc3Maps {
+  CUtensorMap x, g, b;
+};
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(smem_u32(dst)), "l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -71,15 +92,30 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {   // 256-bit loa
 // a.N < N outputs (the other columns of the UMMA tile are zero weights and are not stored).
 // Measured and dropped (profiles/r02_summary.md): two transform groups on alternate K-chunks (16 + 1 + 4 + 2 warps): the four
 // epilogue warps then hold a TMEM buffer across their first store pass and the tile period grows from 6.0 k to 7.5 k cycles.
+// Also measured and dropped, after the MMA issuer became an elected thread with straight-line UTCHMMAs (its chain fell from ~1750
+// to ~900 cycles per chunk, profiles/r02x_clocks_*): the eight transform warps as two groups of four on ALTERNATE chunks (each
+// thread transforms its row's whole chunk; LayerNorm coefficients in a ring indexed by tile): 73.0 / 116.0 us against 69.9 /
+// 109.1 us -- the transform role is paced by shared-memory / MIO throughput under the producers' cp.async traffic, not by the
+// latency of its hand-off chain, so running two chains in parallel buys nothing.  Likewise sixteen transform warps (one pass of
+// two quads per thread and chunk, 72 registers): 70.5 / 116.5 us, and 64-channel chunks again: 77.9 / 127.2 us.  Clock stamps of
+// every variant show the same ~2000 cycles per 16 KB chunk in the transform role: ~200 + ~280 for the two (non-blocking)
+// mbarrier waits, 500-900 for 12 shared loads, the math and 4 tcgen05.st, ~100-200 for tcgen05.wait::st + fence + __syncwarp and
+// ~250 for the two arrives (profiles/r02x_clocks_*).
 // ATM: the transformed A operand (hi and lo, 32 + 32 columns per stage) is written straight into TENSOR MEMORY with tcgen05.st
 // and the MMAs read it from there (tcgen05.mma with a TMEM A operand): no operand stages in shared memory, no proxy fence,
 // the shared-memory port only carries the raw ring and the resident weights, and the ring is 5 deep.  Needs 4 N + 64 NST <= 512
 // columns, i.e. N <= 64.
 // KCH: channels per K-chunk (32, or 64 with ATM: the MMA issuer and the transform warps pay their per-chunk hand-off costs half
 // as often; clock stamps put those at ~1000 of ~2300 cycles per 32-channel chunk).
-template <int N, int TW, int NST, bool PADN = false, bool ATM = false, int KCH = 32>
-__global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s) {
+// TMA: the raw ring is filled by ONE producer thread with three bulk tensor copies per chunk (input box of 4 samples, gamma,
+// beta; completion by transaction bytes on raw_full) instead of 128 threads x 12 cp.async of 16 bytes: the per-thread copies
+// kept the load/store (MIO) queue of every scheduler busy ~70 % of the time (clock stamps: 700-3300 cycles to issue one
+// chunk), and every shared load and mbarrier operation of the transform warps queued behind them.
+template <int N, int TW, int NST, bool PADN = false, bool ATM = false, int KCH = 32, bool TMA = false>
+__global__ void __launch_bounds__((TW + 1 + 8 + (TMA ? 1 : 4)) * 32, 1)
+    pw_tc3_kernel(const GemmArgs a, const int tiles_p, const int tiles_s, const __grid_constant__ Tc3Maps maps) {
   static_assert(KCH == 32 || (KCH == 64 && ATM), "64-channel chunks need the TMEM operand path");
+  static_assert(!TMA || (ATM && KCH == 32), "the tensor maps describe 32-channel chunks at the start of the dynamic shared memory");
   constexpr int QPR = KCH / 4;                 // 16-byte quads per row of a chunk
   constexpr int NTT = 32 * QPR;                // 16-byte units per sample and K-chunk (32 rows x QPR quads)
   constexpr int NTH = TW * 32;                 // transform threads
@@ -95,12 +131,12 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
   static_assert(TMEM_NEED <= 512, "tensor memory");
   constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   constexpr uint32_t A_TM = 4 * N;             // first column of the A stages (ATM): [stage][hi KC | lo KC]
-  extern __shared__ __align__(128) float tc3_smem[];
+  extern __shared__ __align__(1024) float tc3_smem[];   // 1024: the 128-byte swizzle of the TMA variant is address based
   const int nchunks = (a.K + KC - 1) / KC;
   float* opsA = tc3_smem;                      // [NST stages][hi, lo][A_ST]
   float* raw = opsA + (ATM ? 0 : NST * 2 * A_ST);    // [DEPTH][6][NTT] float4
   float* Bres = raw + DEPTH * RAW;             // [nchunks][hi, lo][B_ST]
-  constexpr int PWARPS = 4, NPT = PWARPS * 32;  // producer (copy) warps / threads
+  constexpr int PWARPS = TMA ? 1 : 4, NPT = PWARPS * 32;  // producer (copy) warps / threads
   constexpr int EWARPS = 8;                     // epilogue warps: two per TMEM lane quarter, half of the columns each
   __shared__ __align__(8) uint64_t bar_full[NST], bar_free[NST], bar_tfull[2], bar_tempty[2], raw_full[DEPTH], raw_free[DEPTH];
   __shared__ uint32_t tmem_slot;
@@ -121,7 +157,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
       mbar_init(&bar_free[i], 1);
     }
     for (int i = 0; i < DEPTH; ++i) {
-      mbar_init(&raw_full[i], NPT);            // every producer thread's copies of the chunk have landed
+      mbar_init(&raw_full[i], TMA ? 1 : NPT);  // every producer thread's copies of the chunk have landed (TMA: one arrival + bytes)
       mbar_init(&raw_free[i], TW);             // every transform warp has read the slot
     }
     for (int i = 0; i < 2; ++i) {
@@ -178,10 +214,13 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
         for (int c = 0; c < nchunks; ++c, ++gi) {
           const int stage = gi % NST;
           const int kc = min(KC, a.K - c * KC);
+          if (tid == 0) TC3_STAMP(0, gi, 0);
           mbar_wait(&raw_full[slot], (gi / DEPTH) & 1);   // the producer warps' copies of chunk gi have landed
+          if (tid == 0) TC3_STAMP(0, gi, 3);
           if (c == 0) { const float2 cf = cf_s[slot][quarter]; sc = cf.x; sh = cf.y; }
           if (gi >= NST) mbar_wait(&bar_free[stage], ((gi / NST) - 1) & 1);   // the MMAs that read this A stage are done
           tc_fence_after();
+          if (tid == 0) TC3_STAMP(0, gi, 4);
           const float* src = raw + slot * RAW;
           const uint32_t a_hi = lane_addr + A_TM + stage * 2 * KC + (KC / 2) * khalf, a_lo = a_hi + KC;
 #pragma unroll
@@ -207,13 +246,16 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
             tmem_st8(a_hi + 8 * h2, hi);
             tmem_st8(a_lo + 8 * h2, lo);
           }
+          if (tid == 0) TC3_STAMP(0, gi, 5);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
+          if (tid == 0) TC3_STAMP(0, gi, 6);
           if (lane == 0) {
             mbar_arrive(&raw_free[slot]);              // the ring slot may be refilled
             mbar_arrive(&bar_full[stage]);
           }
+          if (tid == 0) TC3_STAMP(0, gi, 7);
           slot = slot + 1 == DEPTH ? 0 : slot + 1;
         }
       }
@@ -322,58 +364,114 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
     const float* bet = P + a.be_off;
     const int pt = tid - (TW + 1 + EWARPS) * 32;
     int idx = 0, pslot = 0, r = cta;
-    // threads 0-3: (sum, sumsq) of sample pt of the NEXT tile, loaded one tile ahead
-    const double inv_n = 1.0 / ((double)a.hw * (double)a.K);   // mean and centred variance in fp64 (see ln_coeffs)
-    double st_s = 0.0, st_q = 1.0;
-    auto load_stats = [&](int rt) {
-      st_s = 0.0; st_q = 1.0;
-      const int sn = (rt / tiles_p) * S + pt;
-      if (a.ln && pt < S && rt < ntiles && sn < a.B) {
-        const double* sp = a.stats_in + 2 * ((long long)net * a.B + sn);
-        st_s = sp[0];
-        st_q = sp[1];
-      }
-    };
-    load_stats(r);
-    for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
-      const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
-      const int ns = min(S, a.B - s0);
-      for (int c = 0; c < nchunks; ++c, ++idx) {
-        if (idx >= DEPTH) mbar_wait(&raw_free[pslot], ((idx / DEPTH) - 1) & 1);
-        if (c == 0 && pt < S) {
-          // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence; the difference is ~1e-7 relative
-          const double md = st_s * inv_n;
-          const float m_ = (float)md;
-          const float var = fmaxf((float)(st_q * inv_n - md * md), 0.f);
-          const float sc = rsqrtf(var + (float)CNF_LN_EPS);
-          cf_s[pslot][pt] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
-          load_stats(r + ncta);
-          __threadfence_block();   // ordered before this thread's arrival on raw_full[pslot] below
-        }
-        const int k0 = c * KC, kc = min(KC, a.K - k0);
-        float* dst = raw + pslot * RAW;
+    if constexpr (TMA) {
+      // one thread: waits for the slot, turns the tile's LayerNorm sums into coefficients (the four samples' sums are loaded
+      // one tile ahead), then three bulk tensor copies complete the slot's barrier by transaction bytes
+      if (pt == 0) {
+        const double inv_n = 1.0 / ((double)a.hw * (double)a.K);   // mean and centred variance in fp64 (see ln_coeffs)
+        double st[S][2];
+        auto load_stats = [&](int rt) {
 #pragma unroll
-        for (int h = 0; h < NTT / NPT; ++h) {
-          const int u = pt + h * NPT;
-          const int cq = u % QPR, crow = u / QPR;
-          const int gp = p0 + crow;
-          if (cq * 4 < kc && gp < a.hw && !(a.dbg & 2)) {
-            const int cunit = crow * QPR + (cq ^ (crow & 7));
-            const long long e = (long long)gp * a.K + k0 + cq * 4;
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-              if (s < ns) cp_async16_cg(dst + (s * NTT + cunit) * 4, src_n + ((long long)(s0 + s) * a.hw) * a.K + e);
-            if (a.ln) {
-              cp_async16_ca(dst + (4 * NTT + cunit) * 4, gam + e);
-              cp_async16_ca(dst + (5 * NTT + cunit) * 4, bet + e);
+          for (int s = 0; s < S; ++s) {
+            st[s][0] = 0.0; st[s][1] = 1.0;
+            const int sn = (rt / tiles_p) * S + s;
+            if (a.ln && rt < ntiles && sn < a.B) {
+              const double* sp = a.stats_in + 2 * ((long long)net * a.B + sn);
+              st[s][0] = sp[0];
+              st[s][1] = sp[1];
             }
           }
+        };
+        const uint32_t chunk_bytes = (uint32_t)((a.ln ? 6 : 4) * NTT * 16);
+        load_stats(r);
+        for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
+          const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+          for (int c = 0; c < nchunks; ++c, ++idx) {
+            if (pt == 0) TC3_STAMP(3, idx, 0);
+            if (idx >= DEPTH) mbar_wait(&raw_free[pslot], ((idx / DEPTH) - 1) & 1);
+            if (pt == 0) TC3_STAMP(3, idx, 1);
+            if (c == 0) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence; the difference is ~1e-7 relative
+                const double md = st[s][0] * inv_n;
+                const float m_ = (float)md;
+                const float var = fmaxf((float)(st[s][1] * inv_n - md * md), 0.f);
+                const float sc = rsqrtf(var + (float)CNF_LN_EPS);
+                cf_s[pslot][s] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
+              }
+              load_stats(r + ncta);
+            }
+            float* dst = raw + pslot * RAW;
+            fence_async_smem();   // the transform warps' generic reads of this slot (ordered by raw_free) before the async writes
+            mbar_arrive_expect_tx(&raw_full[pslot], chunk_bytes);   // release: the coefficients above are visible with the phase
+            tma_load_4d(dst, &maps.x, c * KC, p0, s0, net, &raw_full[pslot]);
+            if (a.ln) {
+              tma_load_3d(dst + 4 * NTT * 4, &maps.g, c * KC, p0, net, &raw_full[pslot]);
+              tma_load_3d(dst + 5 * NTT * 4, &maps.b, c * KC, p0, net, &raw_full[pslot]);
+            }
+            if (pt == 0) TC3_STAMP(3, idx, 2);
+            pslot = pslot + 1 == DEPTH ? 0 : pslot + 1;
+          }
         }
-        cp_async_mbar_arrive_noinc(&raw_full[pslot]);
-        pslot = pslot + 1 == DEPTH ? 0 : pslot + 1;
       }
+    } else {
+      // threads 0-3: (sum, sumsq) of sample pt of the NEXT tile, loaded one tile ahead
+      const double inv_n = 1.0 / ((double)a.hw * (double)a.K);   // mean and centred variance in fp64 (see ln_coeffs)
+      double st_s = 0.0, st_q = 1.0;
+      auto load_stats = [&](int rt) {
+        st_s = 0.0; st_q = 1.0;
+        const int sn = (rt / tiles_p) * S + pt;
+        if (a.ln && pt < S && rt < ntiles && sn < a.B) {
+          const double* sp = a.stats_in + 2 * ((long long)net * a.B + sn);
+          st_s = sp[0];
+          st_q = sp[1];
+        }
+      };
+      load_stats(r);
+      for (int tl = 0; tl < my_tiles; ++tl, r += ncta) {
+        const int s0 = (r / tiles_p) * S, p0 = (r % tiles_p) * PT;
+        const int ns = min(S, a.B - s0);
+        for (int c = 0; c < nchunks; ++c, ++idx) {
+          if (pt == 0) TC3_STAMP(3, idx, 0);
+          if (idx >= DEPTH) mbar_wait(&raw_free[pslot], ((idx / DEPTH) - 1) & 1);
+          if (pt == 0) TC3_STAMP(3, idx, 1);
+          if (c == 0 && pt < S) {
+            // rsqrtf (2 ulp) instead of the IEEE 1/sqrt sequence; the difference is ~1e-7 relative
+            const double md = st_s * inv_n;
+            const float m_ = (float)md;
+            const float var = fmaxf((float)(st_q * inv_n - md * md), 0.f);
+            const float sc = rsqrtf(var + (float)CNF_LN_EPS);
+            cf_s[pslot][pt] = a.ln ? make_float2(sc, -m_ * sc) : make_float2(1.f, 0.f);
+            load_stats(r + ncta);
+            __threadfence_block();   // ordered before this thread's arrival on raw_full[pslot] below
+          }
+          const int k0 = c * KC, kc = min(KC, a.K - k0);
+          float* dst = raw + pslot * RAW;
+  #pragma unroll
+          for (int h = 0; h < NTT / NPT; ++h) {
+            const int u = pt + h * NPT;
+            const int cq = u % QPR, crow = u / QPR;
+            const int gp = p0 + crow;
+            if (cq * 4 < kc && gp < a.hw && !(a.dbg & 2)) {
+              const int cunit = crow * QPR + (cq ^ (crow & 7));
+              const long long e = (long long)gp * a.K + k0 + cq * 4;
+  #pragma unroll
+              for (int s = 0; s < S; ++s)
+                if (s < ns) cp_async16_cg(dst + (s * NTT + cunit) * 4, src_n + ((long long)(s0 + s) * a.hw) * a.K + e);
+              if (a.ln) {
+                cp_async16_ca(dst + (4 * NTT + cunit) * 4, gam + e);
+                cp_async16_ca(dst + (5 * NTT + cunit) * 4, bet + e);
+              }
+            }
+          }
+          cp_async_mbar_arrive_noinc(&raw_full[pslot]);
+          if (pt == 0) TC3_STAMP(3, idx, 2);
+          pslot = pslot + 1 == DEPTH ? 0 : pslot + 1;
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (wid == TW) {
     // =============================== MMA issuer ===============================
     if (elect_one()) {
@@ -526,6 +624,7 @@ __global__ void __launch_bounds__((TW + 1 + 8 + 4) * 32, 1) pw_tc3_kernel(const 
           atomicAdd(so + 1, (double)s2);
         }
       }
+      if (wid == TW + 1 && lane == 0) TC3_STAMP(2, tl, 3);
     }
   }
   tc_fence_before();

@@ -34,7 +34,11 @@ print("MMA role: chunk, loop top (abs), bar_full wait, MMA issue, commits; perio
 for gi in range(4, 28):
     r = c[1, gi]
     print(gi, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], "| period", c[1, gi + 1, 0] - r[0])
-print("epilogue role (warp TW+1): tile, before tfull wait (abs), tfull wait, ld+release; period")
+print("epilogue role (warp TW+1): tile, before tfull wait (abs), tfull wait, ld+release, bias/stats/stores; period")
 for tl in range(2, 12):
     r = c[2, tl]
-    print(tl, r[0] - t0, r[1] - r[0], r[2] - r[1], "| period", c[2, tl + 1, 0] - r[0])
+    print(tl, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], "| period", c[2, tl + 1, 0] - r[0])
+print("producer role (thread 0): chunk, loop top (abs), raw_free wait, copies issued; period")
+for gi in range(4, 28):
+    r = c[3, gi]
+    print(gi, r[0] - t0, r[1] - r[0], r[2] - r[1], "| period", c[3, gi + 1, 0] - r[0])
