@@ -72,9 +72,11 @@ def _nccl_worker(rank, world, port, q):
             m.randomize_weights(seed=3)
             m.grad_bucket_bytes = bucket
             m.compile(optimizer=Adam(3e-4))
-            losses = [float(m.train_step(x)['loss']) for _ in range(3)]      # successive steps reuse the gradient buffer
+            losses = [float(m.train_step(x)['loss'])]
+            g1 = m._grads.clone()                                            # the reduced gradient of the FIRST step (same weights)
+            losses += [float(m.train_step(x)['loss']) for _ in range(2)]     # successive steps reuse the gradient buffer
             torch.cuda.synchronize(dev)
-            out[name] = (losses, m._grads.clone(), m.params.clone(), replicas_checksum_equal(m))
+            out[name] = (losses, g1, m.params.clone(), replicas_checksum_equal(m))
         ref = out["flat"]
         res = {}
         for name in ("bucketed", "one_bucket"):
@@ -111,9 +113,10 @@ def test_two_gpus_bucketed_allreduce_matches_flat_allreduce():
     for rank, flat_losses, flat_equal, by_name in res:
         assert flat_equal
         for name, (g_err, p_err, losses, equal) in by_name.items():
-            # same gradients as the flat all-reduce up to the arrival order of the fp32 atomics of the weight gradients
-            # (three Adam steps amplify that slightly in the parameters)
-            assert g_err <= 1e-4, (rank, name, g_err)
-            assert p_err <= 1e-4, (rank, name, p_err)
+            # first step: the flat all-reduce's gradient up to the arrival order of the fp32 atomics of the weight gradients
+            # (two runs of the same mode differ by ~2e-5 of the largest entry, tests/test_gpu_train.py); three Adam steps
+            # amplify that in the parameters (a missing or mis-ordered bucket would be an O(1) error)
+            assert g_err <= 5e-5, (rank, name, g_err)
+            assert p_err <= 1e-3, (rank, name, p_err)
             assert losses == pytest.approx(flat_losses, rel=1e-4)
             assert equal, f"replicas diverged with {name}"
