@@ -638,10 +638,16 @@ class cFlow:
         self.set_weights(weights)
 
     def _workspace(self, B):
+        """s/t-net workspace of the CURRENT stream: calls issued on different streams (log_loss_and_sample) may run
+        concurrently on the device, so each stream owns its buffer."""
         need = int(lib.cnf_plan_workspace_bytes(self._plan, B))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != self.params.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
-        return self._ws
+        if self._ws is None:
+            self._ws = {}
+        key = torch.cuda.current_stream().cuda_stream if self.params.is_cuda else 0
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need or ws.device != self.params.device:
+            self._ws[key] = ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
+        return ws
 
     def _check_io(self, t, name):
         t = require_cuda(t, name)
@@ -674,6 +680,25 @@ class cFlow:
         return None
 
     __call__ = call
+
+    def log_loss_and_sample(self, xy, zy):
+        """log_loss(xy) and call(zy, -1) -- the two halves of a likelihood-evaluation + sampling step, which do not depend
+        on each other -- issued on TWO CUDA streams.  Every s/t-net kernel is a persistent grid of one CTA per SM whose
+        CTAs finish at different times (20 to 22 tiles each) and start with a prologue (resident weights, gamma / beta, tensor
+        memory); with a second, independent kernel queue the SMs that one pass leaves idle at every kernel boundary run
+        the other pass's CTAs.  Same kernels, same results as the two calls in sequence (each stream has its own workspace).
+        Returns ((loss, z_loss, y_loss, detJ_loss), samples); both are ready on the current stream."""
+        main = torch.cuda.current_stream()
+        side = getattr(self, '_side_stream', None)
+        if side is None or side.device != self.params.device:
+            self._side_stream = side = torch.cuda.Stream(device=self.params.device)
+        side.wait_stream(main)                       # zy (and the weights) were produced on the current stream
+        with torch.cuda.stream(side):
+            samples = self.call(zy, -1)
+        four = self.log_loss(xy)
+        main.wait_stream(side)
+        samples.record_stream(main)                  # allocated under the side stream, used by the caller on this one
+        return four, samples
 
     # -- cFlow.log_loss (M:1800-1848) -------------------------------------------------------------------
     def log_loss(self, xy):

@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the config's batch)")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="2: log_loss and sampling of a step on two CUDA streams (cFlow.log_loss_and_sample); 1: one after the other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline (+ training) only: skips the eval-only / "
@@ -269,9 +271,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(i):
+    def step_serial(i):
         model.log_loss(xs_d[i % NBUF])
         model(zs_d[i % NBUF], -1)
+
+    def step_device(i):
+        # the same two calls issued on two CUDA streams (cFlow.log_loss_and_sample): one pass's CTAs fill the SMs the
+        # other pass leaves idle at every kernel boundary
+        if args.streams == 2:
+            model.log_loss_and_sample(xs_d[i % NBUF], zs_d[i % NBUF])
+        else:
+            step_serial(i)
 
     host_out = {"loss": torch.empty(4).pin_memory(), "ps": torch.empty((3, (B + 3) & ~3)).pin_memory(),
                 "x": torch.empty((B, H, W, D)).pin_memory()}
@@ -280,13 +290,18 @@ def run_ours(args):
     def step_e2e(i):
         # host buffers in, host results out, through the public API
         dbuf["x"].copy_(xs_h[i % NBUF], non_blocking=True)
-        four = model.log_loss(dbuf["x"])
+        if args.streams == 2:
+            dbuf["z"].copy_(zs_h[i % NBUF], non_blocking=True)
+            four, s = model.log_loss_and_sample(dbuf["x"], dbuf["z"])
+        else:
+            four = model.log_loss(dbuf["x"])
         host_out["loss"].copy_(torch.stack(list(four)), non_blocking=True)
         host_out["ps"][0, :B].copy_(model.last_per_sample["ll_z"], non_blocking=True)
         host_out["ps"][1, :B].copy_(model.last_per_sample["ll_y"], non_blocking=True)
         host_out["ps"][2, :B].copy_(model.last_per_sample["logdet"], non_blocking=True)
-        dbuf["z"].copy_(zs_h[i % NBUF], non_blocking=True)
-        s = model(dbuf["z"], -1)
+        if args.streams != 2:
+            dbuf["z"].copy_(zs_h[i % NBUF], non_blocking=True)
+            s = model(dbuf["z"], -1)
         host_out["x"].copy_(s, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -312,6 +327,7 @@ def run_ours(args):
     ms_total = timed(step_device, K, Wm)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, K, 2)
+    ms_serial = timed(step_serial, K, 1) if args.streams == 2 else ms_total     # the two calls one after the other
     Bs = max(1, B // world)
     ms_eval = ms_samp = ms_unfused = ms_strong = float("nan")
     if not args.quick:
@@ -319,7 +335,7 @@ def run_ours(args):
         ms_samp = timed(lambda i: model(zs_d[i % NBUF], -1), K, 1)
         # the same step with every layer on the layer-per-kernel path (what the activation-resident launches replace)
         model.set_fusion(0)
-        ms_unfused = timed(step_device, K, 1)
+        ms_unfused = timed(step_serial, K, 1)
         model.set_fusion(1)
         # strong scaling: the config's batch as the GLOBAL batch, split over the ranks
         ms_strong = timed(lambda i: (model.log_loss(xs_d[i % NBUF][:Bs]), model(zs_d[i % NBUF][:Bs], -1)), K, 1)
@@ -457,6 +473,10 @@ def run_ours(args):
                        "weights": "trained-like random (SURVEY 8d W-rand; cFlow.randomize_weights, seed 0)",
                        "l2": "no explicit flush: each step streams the model's weights and the s/t-net activations of the "
                              f"full-resolution layers (> 126 MB L2 at this batch) and inputs rotate over {NBUF} distinct batches",
+                       "streams": f"{args.streams}: " + ("log_loss and sampling of a step issued on two CUDA streams "
+                                                         "(cFlow.log_loss_and_sample); the same kernels one call after the other: "
+                                                         "serial_images_per_s" if args.streams == 2 else "one call after the other"),
+                       "serial_images_per_s": imgs * K / (ms_serial * 1e-3),
                        "eval_images_per_s": None if args.quick else B * world * K / (ms_eval * 1e-3),
                        "sample_images_per_s": None if args.quick else B * world * K / (ms_samp * 1e-3),
                        "layer_per_kernel_path_images_per_s": None if args.quick else imgs * K / (ms_unfused * 1e-3),

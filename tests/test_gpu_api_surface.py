@@ -151,3 +151,28 @@ def test_call_forward_scalar_is_the_batch_mean_of_the_per_sample_logdets(dev, B)
     assert ps.shape == (B,) and ld.dim() == 0
     want = ps.double().mean().item()
     assert abs(float(ld) - want) <= 1e-6 * max(1.0, abs(want))
+
+
+def test_log_loss_and_sample_on_two_streams_equals_the_two_calls():
+    """cFlow.log_loss_and_sample issues the two independent halves of an evaluation + sampling step on two CUDA streams
+    (separate workspaces): same kernels, bit-identical results, repeated calls included."""
+    import torch
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import cFlow
+    dev = torch.device("cuda:0")
+    cfg = dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[1, 1, 1, 1],
+               num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4])
+    m = cFlow(**cfg, device=dev)
+    m.randomize_weights(seed=3)
+    g = torch.Generator().manual_seed(0)
+    for B in (33, 8):
+        x = torch.randn(B, 28, 28, 2, generator=g).to(dev)
+        z = torch.randn(B, 28, 28, 2, generator=g).to(dev)
+        want_four = [float(t) for t in m.log_loss(x)]
+        want_ld = m.last_per_sample['logdet'].clone()
+        want_s = m(z, -1).clone()
+        for _ in range(3):
+            four, s = m.log_loss_and_sample(x, z)
+            torch.cuda.synchronize()
+            assert [float(t) for t in four] == want_four
+            assert torch.equal(m.last_per_sample['logdet'], want_ld)
+            assert torch.equal(s, want_s)
