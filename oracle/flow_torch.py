@@ -52,6 +52,15 @@ def common_layers(y, gamma, beta, ln=True):
     return y
 
 
+#: How the `Lambda(lambda z: z[:, :, :, j * _d:j * _d + _d])` slices of F:402 bind `j` (oracle/tf_shim/README.md).
+#: False: every group reads its own slice (the lambda runs once, while the graph is built: TF 1.x graph-mode Keras; SURVEY
+#: quirk Q11; what the CUDA kernels implement).  True: tf.keras >= 2.4 re-runs the lambda on every model call, when the loop
+#: variable holds its final value, so EVERY group reads the last group's channels.  Both are pinned against the reference's
+#: own source (tests/golden/refsrc_*.npz); which one a real TensorFlow 2.7 produces must be decided on a TensorFlow box
+#: (tools/tf_dump_reference.py writes the probe).
+LAMBDA_LATE_BINDING = False
+
+
 def grouped_convolution(y, P, prefix, nb_channels, ksize, dilation, cardinality):
     """F:364-413, literal: one Conv2D per group over channel slice [j*_d, (j+1)*_d)."""
     if cardinality == 1:
@@ -60,7 +69,8 @@ def grouped_convolution(y, P, prefix, nb_channels, ksize, dilation, cardinality)
     _d = nb_channels // cardinality
     groups = []
     for j in range(cardinality):
-        grp = y[..., j * _d:j * _d + _d]
+        js = cardinality - 1 if LAMBDA_LATE_BINDING else j
+        grp = y[..., js * _d:js * _d + _d]
         groups.append(conv2d_same(grp, P[f'{prefix}.g{j}.kernel'], P[f'{prefix}.g{j}.bias'], dilation))
     return torch.cat(groups, dim=-1)
 

@@ -1,0 +1,119 @@
+"""Golden vectors from the reference's OWN source files, executed under the NumPy TensorFlow stand-in of oracle/tf_shim
+(README there): /root/reference/conv_cINN_make_model.py and conv_cINN_base_functions.py are imported unmodified, the reference
+`cFlow` is built, seeded weights are assigned to its Keras variables BY NAME through the product's name map
+(keras_interchange.keras_weight_names: this is also the test of that map against the reference's real construction order), and
+`call(+1)`, `call(-1)`, `log_loss` run eagerly in fp64.
+
+Writes tests/golden/refsrc_<case>.npz with: the config, the Keras-named fp32 weights, the inputs, and the outputs under both
+executions of the `Lambda` closure of F:402 (`*_trace_once`: every group reads its own slice; `*_replay`: late-bound `j`).
+Needs /root/reference, so it runs in the build container only; the fixtures travel.  TEST INFRASTRUCTURE.
+
+usage: python oracle/make_ref_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("CNF_REFERENCE_DIR", "/root/reference")
+
+CASES = {
+    # one squeeze, two residual blocks in the first coupling block, odd channel count (D = 3, x_d = 2)
+    'small_sq': dict(io_shape=[8, 8, 3], x_d=2, squeeze_factor_block_list=[1, 0], ResNeXt_block_list=[2, 1],
+                     num_kernels_list=[16, 8], cardinality_list=[2, 2]),
+    # the block pattern of BASELINE config 2 ([0, 1, 0, 0]) at 8x8x2 with narrow nets
+    'cfg2_pattern': dict(io_shape=[8, 8, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[1, 1, 1, 1],
+                         num_kernels_list=[16, 16, 8, 8], cardinality_list=[2, 2, 2, 2]),
+    # four groups: the Lambda question matters most here
+    'card4': dict(io_shape=[4, 4, 2], x_d=1, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
+                  num_kernels_list=[16], cardinality_list=[4]),
+}
+
+
+def load_reference():
+    """import the reference model module against the shim (np.int: NumPy < 1.24 alias the reference still uses, M:1532)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "tf_shim"))
+    sys.path.insert(0, REF)
+    if not hasattr(np, "int"):
+        np.int = int
+    import conv_cINN_make_model as M          # noqa: E402  (the reference's file)
+    from tensorflow.keras import layers as KL  # noqa: E402  (the shim)
+    return M, KL
+
+
+def run_case(name, cfg, M, KL, seed):
+    sys.path.insert(0, ROOT)
+    from arl_conditional_normalizing_flows_b200.keras_interchange import keras_weight_names
+    from oracle.flow_torch import FlowOracle
+    from oracle.weights import init_weights
+    import torch
+
+    KL.reset_state()                       # a fresh process as far as Keras' name counters are concerned
+    ref = M.cFlow(**cfg)
+    variables = {v.name: v for v in KL.all_variables()}
+
+    oracle = FlowOracle(**cfg, dtype=torch.float64)
+    W = init_weights(oracle.plan, 'rand', seed=seed)
+    table = keras_weight_names([{n: list(w) for n, w in lw.items()} for lw in W])
+    names = [k for k, *_ in table]
+    assert len(set(names)) == len(names)
+    assert set(names) == set(variables), (sorted(set(names) ^ set(variables))[:6], len(names), len(variables))
+    # Keras creation order == the order the name map walks
+    assert names == [v.name for v in KL.all_variables()], "creation order of the reference differs from the name map"
+    keras_w = {}
+    for k, ci, net, our in table:
+        a = np.asarray(W[ci][net][our], dtype=np.float32)
+        assert tuple(variables[k].shape) == a.shape, (k, variables[k].shape, a.shape)
+        variables[k].assign(a)
+        keras_w[k] = a
+
+    rng = np.random.default_rng(seed + 1)
+    H, Wd, D = cfg['io_shape']
+    xd = cfg['x_d']
+    B = 3
+    xy = rng.standard_normal((B, H, Wd, D)).astype(np.float32).astype(np.float64)
+    zy_in = rng.standard_normal((B, H, Wd, D)).astype(np.float32).astype(np.float64)
+    zy_in[..., xd:] = xy[..., xd:]
+
+    out = {}
+    for mode, replay in (('trace_once', False), ('replay', True)):
+        KL.LAMBDA_REPLAY = replay
+        zy, ld = ref(xy, 1)
+        four = [float(v) for v in ref.log_loss(xy)]
+        xs = ref(zy_in, -1)
+        back = ref(zy, -1)
+        out[mode] = dict(zy=np.asarray(zy), logdet_mean=float(ld), loss4=np.asarray(four), sample=np.asarray(xs),
+                         roundtrip=float(np.abs(np.asarray(back) - xy).max()))
+
+    # the oracle on the same weights and inputs, under both readings of the Lambda closure
+    import oracle.flow_torch as FT
+    oracle.set_weights(W)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max()))  # noqa: E731
+    report = {}
+    for mode, late in (('trace_once', False), ('replay', True)):
+        FT.LAMBDA_LATE_BINDING = late
+        four_o, ps = oracle.log_loss(xy)
+        xs_o = oracle.call(zy_in, -1)
+        t = out[mode]
+        report.update({f"{mode}:zy": rel(ps['zy'], t['zy']), f"{mode}:loss4": rel(four_o, t['loss4']),
+                       f"{mode}:sample": rel(xs_o, t['sample']),
+                       f"{mode}:logdet_mean": abs(float(np.mean(ps['logdet'])) - t['logdet_mean']) / abs(t['logdet_mean'])})
+    FT.LAMBDA_LATE_BINDING = False
+    t = out['trace_once']
+    report['replay_vs_trace_once'] = rel(out['replay']['zy'], t['zy'])
+    print(f"{name}: {len(names)} Keras variables; oracle vs reference source: " +
+          ", ".join(f"{k} {v:.2e}" for k, v in report.items()) +
+          f"; round trips {t['roundtrip']:.1e} / {out['replay']['roundtrip']:.1e}")
+    path = os.path.join(ROOT, "tests", "golden", f"refsrc_{name}.npz")
+    np.savez_compressed(path, cfg=json.dumps(cfg), xy=xy.astype(np.float32), zy_in=zy_in.astype(np.float32),
+                        weight_names=np.array(names), **keras_w,
+                        **{f"{mode}:{k}": np.asarray(v) for mode, d in out.items() for k, v in d.items()})
+    return report
+
+
+if __name__ == "__main__":
+    M, KL = load_reference()
+    for i, (name, cfg) in enumerate(CASES.items()):
+        run_case(name, cfg, M, KL, seed=10 + i)
