@@ -28,6 +28,8 @@ class GlorotUniform(Orthogonal):
 
 
 def get(identifier):
+    if isinstance(identifier, str) and identifier.lower() in ('ones', 'zeros'):
+        return Ones() if identifier.lower() == 'ones' else Zeros()
     if identifier is None or isinstance(identifier, str):
         return GlorotUniform()
     return identifier

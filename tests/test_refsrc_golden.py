@@ -128,3 +128,17 @@ def test_cuda_path_equals_the_reference_source(path):
     assert rel(zy, z['trace_once:zy']) <= 1e-4
     assert rel(xs, z['trace_once:sample']) <= 1e-4
     assert abs(ld - float(z['trace_once:logdet_mean'])) <= 1e-4 * abs(float(z['trace_once:logdet_mean']))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("CNF_REFERENCE_DIR", "/root/reference")),
+                    reason="the reference checkout only exists in the build container")
+def test_lambda_probe_tells_the_two_executions_apart():
+    """tools/tf_dump_reference.py probe (meant for a TensorFlow box) run against the stand-in's two settings"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "tf_dump_reference.py"), "probe", "--impl", "shim"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env=dict(os.environ, PYTHONPATH=root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("shim")]
+    assert lines[0].endswith("trace_once") and lines[1].endswith("replay"), out.stdout

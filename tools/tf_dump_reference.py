@@ -18,6 +18,14 @@ reference is "unpinned".  This script is the route out.  It has two halves:
      (M:1800-1848),  xy_sampled = model(zy_in, -1) (M:1774-1798)  and the per-sample log-dets of the first samples
      (batch-of-one calls: the reference only returns the batch mean, Q1).
 
+  3. on the same TensorFlow box, the one-second answer to the question oracle/tf_shim/README.md raises about F:402:
+         python tools/tf_dump_reference.py probe --reference /path/to/ARL_Conditional_Normalizing_Flows
+     builds the reference's grouped_convolution (two groups, all-ones kernels) as a functional Model, feeds an input whose
+     FIRST group slice is ones and whose second is zeros, and prints `trace_once` (group 0 read its own slice: what the oracle
+     default and the CUDA kernels implement) or `replay` (tf.keras re-ran the Lambda with the loop variable's final value:
+     every group read the last slice; oracle.flow_torch.LAMBDA_LATE_BINDING = True reproduces that).
+     `--impl shim` answers the same question for the two settings of the stand-in (oracle/tf_shim), as a test of the probe.
+
 tests/test_tf_golden.py consumes every tests/golden/tf_*.npz that exists: the oracle must reproduce it to 1e-5 (that pins
 the oracle) and the CUDA path to the north-star tolerance 1e-4.  `run --impl oracle` writes the same file format from the
 oracle instead of TensorFlow; it exists to test the harness and must never be committed as tf_*.npz.
@@ -96,6 +104,34 @@ def _run_tf(a, meta, xy, z, wz):
             f"tensorflow {tf.__version__}")
 
 
+def cmd_probe(a):
+    np.int = int
+    if a.impl == 'shim':
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "tf_shim"))
+    sys.path.insert(0, a.reference)
+    import tensorflow as tf
+    from tensorflow.keras import Model
+    from tensorflow.keras.layers import Input
+    import conv_cINN_base_functions as F      # the reference's own module, unmodified
+    verdicts = []
+    for replay in ((False, True) if a.impl == 'shim' else (None,)):
+        if replay is not None:
+            from tensorflow.keras import layers as KL
+            KL.LAMBDA_REPLAY = replay
+        inp = Input(shape=(4, 4, 4))
+        out = F.grouped_convolution(inp, 4, _strides=(1, 1), ksize=(1, 1), dilation=(1, 1), cardinality=2, init='ones')
+        model = Model(inputs=inp, outputs=out)
+        x = np.zeros((1, 4, 4, 4), np.float32)
+        x[..., :2] = 1.0                       # only the FIRST group's input slice is non-zero
+        y = np.asarray(model(tf.constant(x)))
+        g0, g1 = float(y[0, 0, 0, 0]), float(y[0, 0, 0, 2])     # an output channel of group 0 / of group 1
+        verdict = 'trace_once' if (g0, g1) == (2.0, 0.0) else 'replay' if (g0, g1) == (0.0, 0.0) else f'unexpected {g0} {g1}'
+        who = f"tensorflow {getattr(tf, '__version__', '?')}" if replay is None else f"shim, LAMBDA_REPLAY = {replay}"
+        print(f"{who}: group 0 -> {g0}, group 1 -> {g1}: {verdict}")
+        verdicts.append(verdict)
+    return verdicts
+
+
 def _run_oracle(meta, xy, z):
     import torch
     from oracle.flow_torch import FlowOracle
@@ -136,5 +172,8 @@ if __name__ == "__main__":
     r.add_argument('--case', required=True)
     r.add_argument('--out', required=True)
     r.add_argument('--impl', choices=['tf', 'oracle'], default='tf')
+    q = sub.add_parser('probe')
+    q.add_argument('--reference', default='/root/reference')
+    q.add_argument('--impl', choices=['tf', 'shim'], default='tf')
     args = ap.parse_args()
-    (cmd_export if args.cmd == 'export' else cmd_run)(args)
+    {'export': cmd_export, 'run': cmd_run, 'probe': cmd_probe}[args.cmd](args)
