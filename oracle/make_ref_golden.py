@@ -113,7 +113,52 @@ def run_case(name, cfg, M, KL, seed):
     return report
 
 
+def run_toy(KL, seed=20):
+    """TOYcINN_make_model.cINN_affine (T:105-506) under the shim against oracle/toy.py: 12 coupling layers with an explicit
+    mask order, Dense weights assigned in Keras creation order (per layer: the b-net's Dense layers, then the A-net's)."""
+    import TOYcINN_make_model as T            # the reference's file
+    sys.path.insert(0, ROOT)
+    from oracle.toy import ToyOracle, toy_init_weights
+    KL.reset_state()
+    n, width, depth = 12, 16, 2
+    order = [int(v) for v in np.random.default_rng(seed).permutation(n)]
+    ref = T.cINN_affine(3, 2, n, width, depth, None, mask_indices=order)
+    W = toy_init_weights(n, width, depth, seed=seed, scale=1.0)
+    variables = KL.all_variables()
+    flat, k = {}, 0
+    for j in range(n):
+        for net in ('b', 'A'):                 # T:52-66 builds the b-net first
+            for Wm, bv in W[j][net]:
+                for a in (Wm, bv):
+                    v = variables[k]
+                    assert tuple(v.shape) == a.shape, (v.name, v.shape, a.shape)
+                    v.assign(a)
+                    flat[v.name] = np.asarray(a, np.float32)
+                    k += 1
+    assert k == len(variables)
+    rng = np.random.default_rng(seed + 1)
+    B = 64
+    xy = np.concatenate([rng.standard_normal((B, 2)), np.where(rng.uniform(size=(B, 1)) < 0.5, -1.0, 1.0)], 1)
+    xy = xy.astype(np.float32).astype(np.float64)
+    zy_in = rng.standard_normal((B, 3)).astype(np.float32).astype(np.float64)
+    zy, ld = ref(xy, -1)
+    four = [float(v) for v in ref.log_loss(xy)]
+    xs, _ = ref(zy_in, 1)
+    o = ToyOracle(3, 2, n, W, mask_indices=order, dtype=np.float64)
+    zy_o, ld_o = o.call(xy, -1)
+    four_o, _ = o.log_loss(xy)
+    xs_o, _ = o.call(zy_in, 1)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max()))  # noqa: E731
+    print(f"toy: {len(variables)} Keras variables; oracle vs reference source: zy {rel(zy_o, zy):.2e}, logdet {rel(ld_o, ld):.2e}, "
+          f"loss4 {rel(four_o, four):.2e}, sample {rel(xs_o, xs):.2e}")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refsrc_toy.npz"), mask_indices=np.array(order), width=width,
+                        depth=depth, seed=seed, xy=xy.astype(np.float32), zy_in=zy_in.astype(np.float32), zy=np.asarray(zy),
+                        logdet=np.asarray(ld), loss4=np.asarray(four), sample=np.asarray(xs),
+                        weight_names=np.array([v.name for v in variables]))
+
+
 if __name__ == "__main__":
     M, KL = load_reference()
     for i, (name, cfg) in enumerate(CASES.items()):
         run_case(name, cfg, M, KL, seed=10 + i)
+    run_toy(KL)

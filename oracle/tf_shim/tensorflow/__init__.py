@@ -144,6 +144,14 @@ class _Math:
         return 1.0 / _a(x)
 
     @staticmethod
+    def log(x):
+        return _np.log(_a(x))
+
+    @staticmethod
+    def abs(x):      # noqa: A003
+        return _np.abs(_a(x))
+
+    @staticmethod
     def floor(x):
         return _np.floor(x)
 
@@ -176,6 +184,41 @@ class _NN:
 
 
 nn = _NN()
+
+
+class _LinearOperatorFullMatrix:
+    def __init__(self, matrix):
+        self.m = _a(matrix, DTYPE)
+
+    def matvec(self, x):
+        return _np.einsum('ij,...j->...i', self.m, _a(x, DTYPE))
+
+
+class _LinearOperatorDiag:
+    def __init__(self, diag):
+        self.d = _a(diag, DTYPE)
+
+    def matvec(self, x):
+        return self.d * _a(x, DTYPE)
+
+
+class _Linalg:
+    """tf.linalg: what TOYcINN_make_model.py calls (T:379-436)."""
+    LinearOperatorFullMatrix = _LinearOperatorFullMatrix
+    LinearOperatorDiag = _LinearOperatorDiag
+
+    @staticmethod
+    def inv(op):
+        assert isinstance(op, _LinearOperatorDiag)
+        return _LinearOperatorDiag(1.0 / op.d)
+
+    @staticmethod
+    def det(op):
+        assert isinstance(op, _LinearOperatorDiag)
+        return _np.prod(op.d, axis=-1)
+
+
+linalg = _Linalg()
 
 
 class GradientTape:      # cFlow.train_step is not exercised under the shim

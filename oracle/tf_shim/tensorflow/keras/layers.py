@@ -129,6 +129,7 @@ class Layer:
 
 
 def Input(shape, dtype=None, **kw):     # noqa: N802
+    shape = (shape,) if _np.isscalar(shape) else tuple(shape)       # Input(shape=3) is accepted by Keras (T:48)
     return KTensor(_np.zeros((1,) + tuple(int(s) for s in shape), dtype=_np.float64), node=None)
 
 
@@ -153,6 +154,8 @@ class Model(Layer):
             out = layer._run(vals)
             memo[id(t)] = out
             return out
+        if isinstance(self.outputs, (list, tuple)):
+            return [value(t) for t in self.outputs]
         return value(self.outputs)
 
 
@@ -183,6 +186,24 @@ class Conv2D(Layer):
 
 
 Convolution2D = Conv2D
+
+
+class Dense(Layer):
+    _base_name = 'dense'
+
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer='glorot_uniform', kernel_regularizer=None,
+                 **kwargs):
+        super().__init__(**kwargs)
+        assert activation is None
+        self.units, self.use_bias, self.kinit = int(units), use_bias, kernel_initializer
+
+    def build(self, input_shape):
+        self.kernel = self.add_weight('kernel', (int(input_shape[-1]), self.units), self.kinit)
+        self.bias = self.add_weight('bias', (self.units,), _init.Zeros()) if self.use_bias else None
+
+    def call(self, x):
+        y = _np.asarray(x, dtype=_np.float64) @ self.kernel.value
+        return y + self.bias.value if self.bias is not None else y
 
 
 class LayerNormalization(Layer):

@@ -22,7 +22,8 @@ import torch
 import oracle.flow_torch as FT
 from oracle.flow_torch import FlowOracle
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_*.npz"))
+                if not p.endswith("refsrc_toy.npz"))          # the conv model's cases; the toy model has its own test below
 TOL64 = 1e-12
 
 
@@ -142,3 +143,25 @@ def test_lambda_probe_tells_the_two_executions_apart():
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("shim")]
     assert lines[0].endswith("trace_once") and lines[1].endswith("replay"), out.stdout
+
+
+def test_toy_oracle_equals_the_reference_source():
+    """TOYcINN_make_model.cINN_affine (T:105-506) run under the stand-in (tests/golden/refsrc_toy.npz) against oracle/toy.py:
+    12 coupling layers in an explicit mask order, call(-1), call(+1) and log_loss; Dense variables in Keras creation order
+    (per coupling layer the b-net's layers, then the A-net's)."""
+    from oracle.toy import ToyOracle, toy_init_weights
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_toy.npz"))
+    order = [int(v) for v in z['mask_indices']]
+    n, width, depth, seed = len(order), int(z['width']), int(z['depth']), int(z['seed'])
+    W = toy_init_weights(n, width, depth, seed=seed, scale=1.0)
+    names = [str(v) for v in z['weight_names']]
+    per_layer = 2 * 2 * (depth + 2)                      # two nets x (kernel, bias) x Dense layers
+    assert len(names) == n * per_layer and names[0] == "dense/kernel:0" and names[1] == "dense/bias:0"
+    o = ToyOracle(3, 2, n, W, mask_indices=order, dtype=np.float64)
+    xy, zy_in = z['xy'].astype(np.float64), z['zy_in'].astype(np.float64)
+    zy, ld = o.call(xy, -1)
+    four, _ = o.log_loss(xy)
+    xs, _ = o.call(zy_in, 1)
+    assert rel(zy, z['zy']) <= TOL64 and rel(ld, z['logdet']) <= TOL64
+    assert rel(four, z['loss4']) <= TOL64 and rel(xs, z['sample']) <= TOL64
+    assert np.abs(zy - xy).max() > 0.1                    # the flow does something
