@@ -157,8 +157,41 @@ def run_toy(KL, seed=20):
                         weight_names=np.array([v.name for v in variables]))
 
 
+def run_data():
+    """the data-side helpers of conv_cINN_base_functions.py (down / up F:74-164, preprocess_dataset_class F:174-231,
+    preprocess_dataset_SR F:233-279, de_logitify F:287-318) under the shim against oracle/data_np.py"""
+    import tensorflow as tf
+    import conv_cINN_base_functions as F      # the reference's file
+    sys.path.insert(0, ROOT)
+    from oracle import data_np
+    rng = np.random.default_rng(30)
+    img = rng.uniform(0, 1, (3, 9, 10, 2)).astype(np.float32).astype(np.float64)      # odd height: the crop of F:94-97
+    hr = rng.uniform(0, 1, (2, 16, 16, 3)).astype(np.float32).astype(np.float64)
+    out = dict(img=img, hr=hr)
+    out['down'] = F.down(img)
+    out['down1'] = F.down(img[0])
+    out['up'] = F.up(img)
+    out['up1'] = F.up(img[0])
+    out['logits'] = np.stack(list(F.preprocess_dataset_class(tf.data.Dataset.from_tensor_slices(img), LOGITS=True, a=0.01)))
+    for mt in ('SR4,2', 'SR2,1'):
+        for res in (True, False):
+            out[f'sr:{mt}:{int(res)}'] = np.stack(list(F.preprocess_dataset_SR(tf.data.Dataset.from_tensor_slices(hr), mt, RESIDUAL=res)))
+    out['delogit'] = F.de_logitify(np.array(out['logits']), a=0.01)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max()))  # noqa: E731
+    errs = dict(down=rel(data_np.down(img), out['down']), down1=rel(data_np.down(img[0]), out['down1']),
+                up=rel(data_np.up(img), out['up']), up1=rel(data_np.up(img[0]), out['up1']),
+                logits=rel(data_np.preprocess_class_logits(img, 0.01), out['logits']),
+                delogit=rel(data_np.de_logitify(out['logits'], 0.01), out['delogit']))
+    for mt in ('SR4,2', 'SR2,1'):
+        for res in (True, False):
+            errs[f'sr:{mt}:{int(res)}'] = rel(data_np.preprocess_SR(hr, mt, RESIDUAL=res), out[f'sr:{mt}:{int(res)}'])
+    print("data helpers: oracle vs reference source: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refsrc_data.npz"), **{k: np.asarray(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     M, KL = load_reference()
+    run_data()
     for i, (name, cfg) in enumerate(CASES.items()):
         run_case(name, cfg, M, KL, seed=10 + i)
     run_toy(KL)

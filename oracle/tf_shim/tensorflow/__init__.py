@@ -77,6 +77,43 @@ def transpose(x, perm=None):
     return _np.transpose(_a(x), None if perm is None else tuple(int(p) for p in perm))
 
 
+def reshape(x, shape):             # noqa: A002
+    return _np.reshape(_a(x), tuple(int(s) for s in shape))
+
+
+def squeeze(x, axis=None):
+    return _np.squeeze(_a(x), axis=_axes(axis))
+
+
+def repeat(x, repeats, axis=None):
+    return _np.repeat(_a(x), repeats, axis=axis)
+
+
+class _ListDataset:
+    """tf.data.Dataset stand-in: an eager list of elements with map() (what preprocess_dataset_* use, F:174-279)."""
+
+    def __init__(self, elements):
+        self.elements = list(elements)
+
+    def map(self, fn, num_parallel_calls=None):   # noqa: A003
+        return _ListDataset(fn(_np.array(e, dtype=DTYPE)) for e in self.elements)
+
+    def __iter__(self):
+        return iter(self.elements)
+
+
+class _Data:
+    AUTOTUNE = -1
+
+    class Dataset:
+        @staticmethod
+        def from_tensor_slices(x):
+            return _ListDataset(_np.asarray(x))
+
+
+data = _Data()
+
+
 def ensure_shape(x, shape):        # noqa: A002
     got = _np.shape(x)
     want = list(shape)

@@ -23,7 +23,7 @@ import oracle.flow_torch as FT
 from oracle.flow_torch import FlowOracle
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_*.npz"))
-                if not p.endswith("refsrc_toy.npz"))          # the conv model's cases; the toy model has its own test below
+                if os.path.basename(p) not in ("refsrc_toy.npz", "refsrc_data.npz"))   # conv-model cases; toy / data: own tests below
 TOL64 = 1e-12
 
 
@@ -165,3 +165,22 @@ def test_toy_oracle_equals_the_reference_source():
     assert rel(zy, z['zy']) <= TOL64 and rel(ld, z['logdet']) <= TOL64
     assert rel(four, z['loss4']) <= TOL64 and rel(xs, z['sample']) <= TOL64
     assert np.abs(zy - xy).max() > 0.1                    # the flow does something
+
+
+def test_data_helpers_equal_the_reference_source():
+    """down / up (F:74-164, batched and single image, odd height cropped), preprocess_dataset_class with LOGITS (F:174-231),
+    preprocess_dataset_SR for both model types with and without RESIDUAL (F:233-279) and de_logitify (F:287-318), as the
+    reference's own functions compute them under the stand-in (tests/golden/refsrc_data.npz), against oracle/data_np.py --
+    which in turn is what the CUDA data kernels are held to bit for bit (tests/test_gpu_data.py)."""
+    from oracle import data_np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_data.npz"))
+    img, hr = z['img'], z['hr']
+    assert rel(data_np.down(img), z['down']) <= TOL64 and rel(data_np.down(img[0]), z['down1']) <= TOL64
+    assert data_np.down(img).shape == (3, 4, 5, 2)
+    assert rel(data_np.up(img), z['up']) <= TOL64 and rel(data_np.up(img[0]), z['up1']) <= TOL64
+    assert rel(data_np.preprocess_class_logits(img, 0.01), z['logits']) <= TOL64
+    assert rel(data_np.de_logitify(z['logits'], 0.01), z['delogit']) <= TOL64
+    assert rel(z['delogit'], img) <= 1e-9                                  # and the reference's pair is an inverse pair
+    for mt in ('SR4,2', 'SR2,1'):
+        for res in (True, False):
+            assert rel(data_np.preprocess_SR(hr, mt, RESIDUAL=res), z[f'sr:{mt}:{int(res)}']) <= TOL64
