@@ -189,8 +189,111 @@ def run_data():
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refsrc_data.npz"), **{k: np.asarray(v) for k, v in out.items()})
 
 
+PLANNER_CASES = {
+    'cfg2': dict(io_shape=[28, 28, 2], x_d=1, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+                 num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4]),
+    'cfg3': dict(io_shape=[32, 32, 4], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[3] * 4,
+                 num_kernels_list=[64, 64, 32, 32], cardinality_list=[8, 8, 4, 4]),
+    'cfg4': dict(io_shape=[64, 64, 6], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[1] * 4,
+                 num_kernels_list=[64, 64, 32, 32], cardinality_list=[4, 4, 2, 2]),
+    'cfg5': dict(io_shape=[128, 128, 4], x_d=3, squeeze_factor_block_list=[0, 1, 0, 0], ResNeXt_block_list=[1] * 4,
+                 num_kernels_list=[64, 64, 32, 32], cardinality_list=[2, 2, 2, 2]),
+    'sq2': dict(io_shape=[8, 8, 3], x_d=2, squeeze_factor_block_list=[1, 1], ResNeXt_block_list=[2, 1],
+                num_kernels_list=[16, 8], cardinality_list=[2, 2]),
+}
+
+
+def run_planner(M, KL):
+    """cFlow.__init__ (M:1431-1695) of the reference for the BASELINE configs (R = 1 on the two large ones: the planner does
+    not depend on it): every derived attribute the constructor computes, next to oracle/planner.py"""
+    sys.path.insert(0, ROOT)
+    from oracle.planner import plan_flow
+    out = {}
+    for name, cfg in PLANNER_CASES.items():
+        KL.reset_state()
+        ref = M.cFlow(**cfg)
+        layers = []
+        for L in ref.layers_list:
+            kind = type(L).__name__
+            if kind == 'coupling_layer':
+                layers.append(dict(type='coupling', mask=int(L.which_mask), mask_complement=int(L.which_mask_complement),
+                                   nk=int(L.num_kernels), cardinality=int(L.cardinality), R=int(L.num_res_blocks),
+                                   dilations=[int(d) for d in L.which_dilations],
+                                   in_shape=[int(L.input_height), int(L.input_width), int(L.input_depth)],
+                                   compressed=[int(L.compressed_height), int(L.compressed_width), int(L.compressed_depth)],
+                                   n_variables_A=len([w for lay in _layers_of(L.model_A) for w in lay.weights]),
+                                   out_A=[int(v) for v in L.model_A.outputs.shape[1:]]))
+            elif kind == 'squeeze_layer':
+                layers.append(dict(type='squeeze'))
+            else:
+                layers.append(dict(type='factor', num_prev_factors=int(L.num_prev_factors)))
+        rec = dict(cfg=cfg, scale_list=[int(v) for v in ref.scale_list],
+                   num_prev_factors_list=[int(v) for v in ref.num_prev_factors_list],
+                   io_shape_list=[[int(v) for v in r] for r in ref.io_shape_list],
+                   dilations_list=[{k: [int(d) for d in v] for k, v in d.items()} for d in ref.dilations_list],
+                   layers=layers, n_squeeze_factor_layers=len(ref.squeeze_factor_layers_list),
+                   n_variables=len(KL.all_variables()))
+        p = plan_flow(cfg['io_shape'], cfg['x_d'], cfg['squeeze_factor_block_list'], cfg['ResNeXt_block_list'],
+                      cfg['num_kernels_list'], cfg['cardinality_list'])
+        assert rec['scale_list'] == p['scale_list'] and rec['num_prev_factors_list'] == p['num_prev_factors_list'], name
+        assert rec['io_shape_list'] == p['io_shape_list'], name
+        assert [L['type'] for L in layers] == [L['type'] for L in p['layers']], name
+        out[name] = rec
+        print(f"planner {name}: {len(layers)} layers, {rec['n_variables']} Keras variables, scales {rec['scale_list']}, "
+              f"dilations {[d['channelwise'] for d in rec['dilations_list']]}")
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "refsrc_planner.json"), "w"), indent=1)
+
+
+def _layers_of(model):
+    """the layers of a functional shim model, each once"""
+    seen, order = set(), []
+
+    def walk(t):
+        if t.node is None:
+            return
+        layer, ins = t.node
+        for v in (ins if isinstance(ins, (list, tuple)) else [ins]):
+            walk(v)
+        if id(layer) not in seen:
+            seen.add(id(layer))
+            order.append(layer)
+    for t in (model.outputs if isinstance(model.outputs, (list, tuple)) else [model.outputs]):
+        walk(t)
+    return order
+
+
+def run_masks(M, KL):
+    """coupling_layer.mask / decompress_mask (M:500-1073) of the reference, all four masks, compressed and not, even and odd
+    depths, against the literal transcription in oracle/masks_np.py (bit exact: pure index permutations)"""
+    sys.path.insert(0, ROOT)
+    from oracle import masks_np
+    import tensorflow as tf
+    rng = np.random.default_rng(40)
+    out, worst = {}, 0.0
+    for (H, W, D) in ((4, 4, 2), (4, 6, 3), (6, 4, 4), (2, 2, 5)):
+        uv = rng.standard_normal((2, H, W, D)).astype(np.float32).astype(np.float64)
+        out[f'uv:{H}x{W}x{D}'] = uv
+        for m in range(4):
+            KL.reset_state()
+            L = M.coupling_layer([H, W, D], m, 1, 2, 8, 3, tf.keras.initializers.Orthogonal(gain=0.1), LAYER_NORM=True,
+                                 which_dilations=[1])
+            full = np.asarray(L.mask(uv, m, False))
+            comp = np.asarray(L.mask(uv, m, True))
+            back = np.asarray(L.decompress_mask(comp, m, (2, H, W, D)))
+            out[f'full:{H}x{W}x{D}:{m}'], out[f'comp:{H}x{W}x{D}:{m}'], out[f'back:{H}x{W}x{D}:{m}'] = full, comp, back
+            assert np.array_equal(masks_np.mask(uv, m, False), full), (H, W, D, m)
+            assert np.array_equal(masks_np.mask(uv, m, True), comp), (H, W, D, m)
+            assert np.array_equal(masks_np.decompress_mask(comp, m, (2, H, W, D)), back), (H, W, D, m)
+            assert np.array_equal(back, full)                      # decompress(compress) = the masked tensor
+            worst = max(worst, float(np.abs(back - full).max()))
+    print(f"masks: {len(out)} arrays, oracle/masks_np.py bit-identical to the reference's mask / decompress_mask")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refsrc_masks.npz"), **out)
+
+
 if __name__ == "__main__":
     M, KL = load_reference()
+    run_masks(M, KL)
+    run_planner(M, KL)
     run_data()
     for i, (name, cfg) in enumerate(CASES.items()):
         run_case(name, cfg, M, KL, seed=10 + i)

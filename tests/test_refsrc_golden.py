@@ -23,7 +23,7 @@ import oracle.flow_torch as FT
 from oracle.flow_torch import FlowOracle
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_*.npz"))
-                if os.path.basename(p) not in ("refsrc_toy.npz", "refsrc_data.npz"))   # conv-model cases; toy / data: own tests below
+                if os.path.basename(p) not in ("refsrc_toy.npz", "refsrc_data.npz", "refsrc_masks.npz"))   # conv-model cases
 TOL64 = 1e-12
 
 
@@ -184,3 +184,66 @@ def test_data_helpers_equal_the_reference_source():
     for mt in ('SR4,2', 'SR2,1'):
         for res in (True, False):
             assert rel(data_np.preprocess_SR(hr, mt, RESIDUAL=res), z[f'sr:{mt}:{int(res)}']) <= TOL64
+
+
+def test_masks_equal_the_reference_source_bit_for_bit():
+    """coupling_layer.mask / decompress_mask of the reference (M:500-1073; all four masks, compressed and uncompressed, even
+    and odd depths) as executed under the stand-in (tests/golden/refsrc_masks.npz) against oracle/masks_np.py, to which the CUDA
+    mask kernels and the folded addressing are held bit for bit (tests/test_gpu_parity.py)."""
+    from oracle import masks_np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_masks.npz"))
+    shapes = [k[3:] for k in z.files if k.startswith("uv:")]
+    assert len(shapes) == 4
+    for shp in shapes:
+        uv = z[f"uv:{shp}"]
+        for m in range(4):
+            assert np.array_equal(masks_np.mask(uv, m, False), z[f"full:{shp}:{m}"])
+            comp = masks_np.mask(uv, m, True)
+            assert np.array_equal(comp, z[f"comp:{shp}:{m}"])
+            assert np.array_equal(masks_np.decompress_mask(comp, m, uv.shape), z[f"back:{shp}:{m}"])
+
+
+def _planner_cases():
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_planner.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+@pytest.mark.parametrize("name", sorted(_planner_cases()))
+def test_planners_equal_the_reference_constructor(name):
+    """cFlow.__init__ of the reference (M:1431-1695) run under the stand-in for BASELINE configs 2-5 and a two-squeeze case
+    (tests/golden/refsrc_planner.json): scale / factor bookkeeping, per-block shapes, auto-derived dilations, layer order,
+    per-layer mask / kernels / cardinality / compressed shape and the number of Keras variables -- against BOTH the oracle
+    planner and the product's C planner (csrc/plan.cpp through cFlow on the CPU)."""
+    from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import cFlow
+    from arl_conditional_normalizing_flows_b200.keras_interchange import keras_weight_names
+    from oracle.planner import plan_flow
+    rec = _planner_cases()[name]
+    cfg = rec['cfg']
+    p = plan_flow(cfg['io_shape'], cfg['x_d'], cfg['squeeze_factor_block_list'], cfg['ResNeXt_block_list'],
+                  cfg['num_kernels_list'], cfg['cardinality_list'])
+    m = cFlow(**cfg, device="cpu")
+    for got_scale, got_npf, got_shapes, got_dil in (
+            (p['scale_list'], p['num_prev_factors_list'], p['io_shape_list'], p['dilations_list']),
+            (list(m.scale_list), list(m.num_prev_factors_list), m.io_shape_list.tolist(), m.dilations_list)):
+        assert [int(v) for v in got_scale] == rec['scale_list']
+        assert [int(v) for v in got_npf] == rec['num_prev_factors_list']
+        assert [[int(v) for v in r] for r in got_shapes] == rec['io_shape_list']
+        assert [{k: [int(d) for d in v] for k, v in d.items()} for d in got_dil] == rec['dilations_list']
+    assert [L['type'] for L in p['layers']] == [L['type'] for L in rec['layers']]
+    assert len(m.squeeze_factor_layers_list) == rec['n_squeeze_factor_layers']
+    ref_c = [L for L in rec['layers'] if L['type'] == 'coupling']
+    ora_c = [L for L in p['layers'] if L['type'] == 'coupling']
+    assert len(ref_c) == len(ora_c) == len(m.coupling_layers)
+    for R, L, layer in zip(ref_c, ora_c, m.coupling_layers):
+        i = layer._info
+        assert (R['mask'], R['mask_complement'], R['nk'], R['cardinality'], R['R']) == \
+               (L['mask'], L['mask_complement'], L['nk'], L['cardinality'], L['R']) == \
+               (i.mask, i.mask_complement, i.nk, i.cardinality, i.R)
+        assert R['dilations'] == [int(d) for d in L['dilations']] == [i.dilation[j] for j in range(i.n_branches)]
+        assert R['compressed'] == [L['h'], L['w'], L['c1']] == [i.h, i.w, i.c1]
+        assert R['out_A'] == [L['h'], L['w'], L['c2']] == [i.h, i.w, i.c2]
+    for L in rec['layers']:
+        if L['type'] == 'factor':
+            assert L['num_prev_factors'] in rec['num_prev_factors_list']
+    W = m.get_weights()
+    assert len(keras_weight_names([{n: list(w) for n, w in lw.items()} for lw in W])) == rec['n_variables']
