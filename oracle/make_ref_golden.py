@@ -29,6 +29,13 @@ CASES = {
     # four groups: the Lambda question matters most here
     'card4': dict(io_shape=[4, 4, 2], x_d=1, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
                   num_kernels_list=[16], cardinality_list=[4]),
+    # the constructor's optional switches (oracle-only fixtures: names start with "opt_")
+    'opt_no_ln': dict(io_shape=[8, 8, 2], x_d=1, squeeze_factor_block_list=[1, 0], ResNeXt_block_list=[1, 2],
+                      num_kernels_list=[16, 8], cardinality_list=[2, 2], LAYER_NORM=False),
+    # (DILATIONS=False cannot be a case: the reference's constructor reads self.dilations_list, which it only defines when
+    #  DILATIONS is true, and raises AttributeError at M:1643 -- the product mirrors that)
+    'opt_lambda_y': dict(io_shape=[4, 4, 4], x_d=2, squeeze_factor_block_list=[0], ResNeXt_block_list=[1],
+                         num_kernels_list=[8], cardinality_list=[2], lambda_y=7),
 }
 
 
@@ -55,7 +62,7 @@ def run_case(name, cfg, M, KL, seed):
     variables = {v.name: v for v in KL.all_variables()}
 
     oracle = FlowOracle(**cfg, dtype=torch.float64)
-    W = init_weights(oracle.plan, 'rand', seed=seed)
+    W = init_weights(oracle.plan, 'rand', seed=seed, ln=cfg.get('LAYER_NORM', True))
     table = keras_weight_names([{n: list(w) for n, w in lw.items()} for lw in W])
     names = [k for k, *_ in table]
     assert len(set(names)) == len(names)

@@ -24,6 +24,8 @@ from oracle.flow_torch import FlowOracle
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refsrc_*.npz"))
                 if os.path.basename(p) not in ("refsrc_toy.npz", "refsrc_data.npz", "refsrc_masks.npz"))   # conv-model cases
+# the constructor's optional switches (LAYER_NORM = False, DILATIONS = False, lambda_y) are oracle-level fixtures
+GOLDEN_GPU = [p for p in GOLDEN if not os.path.basename(p).startswith("refsrc_opt_")]
 TOL64 = 1e-12
 
 
@@ -44,7 +46,7 @@ def oracle_weights(cfg, z, names):
     from arl_conditional_normalizing_flows_b200.keras_interchange import keras_weight_names
     from oracle.weights import init_weights
     o = FlowOracle(**cfg, dtype=torch.float64)
-    W = init_weights(o.plan, 'init', seed=0)          # structure only; every entry is overwritten
+    W = init_weights(o.plan, 'init', seed=0, ln=cfg.get('LAYER_NORM', True))   # structure only; every entry is overwritten
     table = keras_weight_names([{n: list(w) for n, w in lw.items()} for lw in W])
     assert [k for k, *_ in table] == names, "Keras creation order of the reference differs from the product's name map"
     for k, ci, net, our in table:
@@ -111,7 +113,7 @@ def test_fixture_is_reproducible_from_the_reference_checkout(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[7:-4] for p in GOLDEN])
+@pytest.mark.parametrize("path", GOLDEN_GPU, ids=[os.path.basename(p)[7:-4] for p in GOLDEN_GPU])
 def test_cuda_path_equals_the_reference_source(path):
     from arl_conditional_normalizing_flows_b200.conv_cINN_make_model import cFlow
     from arl_conditional_normalizing_flows_b200.keras_interchange import import_keras_npz
