@@ -50,7 +50,7 @@ def load_reference():
     return M, KL
 
 
-def run_case(name, cfg, M, KL, seed):
+def run_case(name, cfg, M, KL, seed, out_dir=None):
     sys.path.insert(0, ROOT)
     from arl_conditional_normalizing_flows_b200.keras_interchange import keras_weight_names
     from oracle.flow_torch import FlowOracle
@@ -113,7 +113,7 @@ def run_case(name, cfg, M, KL, seed):
     print(f"{name}: {len(names)} Keras variables; oracle vs reference source: " +
           ", ".join(f"{k} {v:.2e}" for k, v in report.items()) +
           f"; round trips {t['roundtrip']:.1e} / {out['replay']['roundtrip']:.1e}")
-    path = os.path.join(ROOT, "tests", "golden", f"refsrc_{name}.npz")
+    path = os.path.join(out_dir or os.path.join(ROOT, "tests", "golden"), f"refsrc_{name}.npz")
     np.savez_compressed(path, cfg=json.dumps(cfg), xy=xy.astype(np.float32), zy_in=zy_in.astype(np.float32),
                         weight_names=np.array(names), **keras_w,
                         **{f"{mode}:{k}": np.asarray(v) for mode, d in out.items() for k, v in d.items()})

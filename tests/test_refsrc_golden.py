@@ -91,25 +91,22 @@ def test_the_two_readings_of_the_lambda_closure_differ():
 @pytest.mark.skipif(not os.path.isdir(os.environ.get("CNF_REFERENCE_DIR", "/root/reference")),
                     reason="the reference checkout only exists in the build container")
 def test_fixture_is_reproducible_from_the_reference_checkout(tmp_path):
-    """re-run the reference's source under the shim (smallest case) and compare with the committed fixture"""
+    """re-run the reference's source under the shim (smallest case, into a scratch directory) and compare with the committed
+    fixture"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import oracle.make_ref_golden as G; "
-            "M, KL = G.load_reference(); r = G.run_case('card4', G.CASES['card4'], M, KL, seed=12); "
-            "print('REPORT', json.dumps(r))" % root)
-    before = open(os.path.join(root, "tests", "golden", "refsrc_card4.npz"), "rb").read()
-    try:
-        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
-        assert out.returncode == 0, out.stderr[-2000:]
-        z_new = np.load(os.path.join(root, "tests", "golden", "refsrc_card4.npz"))
-        import io
-        z_old = np.load(io.BytesIO(before))
-        for k in z_old.files:
-            if z_old[k].dtype.kind in "fc":
-                np.testing.assert_allclose(z_new[k], z_old[k], rtol=1e-12, atol=1e-14)
-    finally:
-        open(os.path.join(root, "tests", "golden", "refsrc_card4.npz"), "wb").write(before)
+            "M, KL = G.load_reference(); G.run_case('card4', G.CASES['card4'], M, KL, seed=12, out_dir=%r)"
+            % (root, str(tmp_path)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    z_new = np.load(os.path.join(str(tmp_path), "refsrc_card4.npz"))
+    z_old = np.load(os.path.join(root, "tests", "golden", "refsrc_card4.npz"))
+    assert sorted(z_new.files) == sorted(z_old.files)
+    for k in z_old.files:
+        if z_old[k].dtype.kind in "fc":
+            np.testing.assert_allclose(z_new[k], z_old[k], rtol=1e-12, atol=1e-14)
 
 
 @pytest.mark.gpu
