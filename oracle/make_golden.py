@@ -2,7 +2,8 @@
 
     python -m oracle.make_golden
 
-PARITY UNPINNED: the reference itself (TensorFlow) cannot run here, so these vectors are outputs of the
+These vectors are the ORACLE'S OWN outputs (regression fixtures); the vectors that pin the oracle to the reference's source
+are tests/golden/refsrc_* (oracle/make_ref_golden.py).  The reference itself (TensorFlow) cannot run here, so these are outputs of the
 restatement, committed so that (i) the oracle cannot drift silently and (ii) the GPU box, which has no
 /root/reference, checks the CUDA path against fixed numbers.  Each file stores the config, the full
 weight set, inputs and fp64 outputs of cFlow.call(+1), log_loss and cFlow.call(-1).

@@ -1,7 +1,8 @@
 """Pin parity at the TensorFlow boundary: dump golden outputs of the UNMODIFIED reference (TensorFlow) for a seeded case.
 
-Nothing in this image can run TensorFlow, so the oracle in oracle/ is a restatement whose parity with the
-reference is "unpinned".  This script is the route out.  It has two halves:
+Nothing in this image can run TensorFlow: the oracle in oracle/ is pinned to the reference's SOURCE (run under the
+NumPy stand-in of oracle/tf_shim, tests/golden/refsrc_*) but not to TensorFlow's own kernels.  This script is the route from
+there to fixtures written by a real TensorFlow.  It has three parts:
 
   1. anywhere this repo is checked out (no TF needed):
          python tools/tf_dump_reference.py export --config cfg2 --batch 8 --out /tmp/case_cfg2
