@@ -91,8 +91,10 @@ def run_case(name, cfg, M, KL, seed, out_dir=None):
         four = [float(v) for v in ref.log_loss(xy)]
         xs = ref(zy_in, -1)
         back = ref(zy, -1)
-        out[mode] = dict(zy=np.asarray(zy), logdet_mean=float(ld), loss4=np.asarray(four), sample=np.asarray(xs),
-                         roundtrip=float(np.abs(np.asarray(back) - xy).max()))
+        # the reference only returns the batch MEAN of the log-dets (M:1325, quirk Q1): per-sample values from batch-of-one calls
+        ld_ps = [float(ref(xy[i:i + 1], 1)[1]) for i in range(B)]
+        out[mode] = dict(zy=np.asarray(zy), logdet_mean=float(ld), logdet_ps=np.asarray(ld_ps), loss4=np.asarray(four),
+                         sample=np.asarray(xs), roundtrip=float(np.abs(np.asarray(back) - xy).max()))
 
     # the oracle on the same weights and inputs, under both readings of the Lambda closure
     import oracle.flow_torch as FT
@@ -106,7 +108,8 @@ def run_case(name, cfg, M, KL, seed, out_dir=None):
         t = out[mode]
         report.update({f"{mode}:zy": rel(ps['zy'], t['zy']), f"{mode}:loss4": rel(four_o, t['loss4']),
                        f"{mode}:sample": rel(xs_o, t['sample']),
-                       f"{mode}:logdet_mean": abs(float(np.mean(ps['logdet'])) - t['logdet_mean']) / abs(t['logdet_mean'])})
+                       f"{mode}:logdet_mean": abs(float(np.mean(ps['logdet'])) - t['logdet_mean']) / abs(t['logdet_mean']),
+                       f"{mode}:logdet_ps": rel(ps['logdet'], t['logdet_ps'])})
     FT.LAMBDA_LATE_BINDING = False
     t = out['trace_once']
     report['replay_vs_trace_once'] = rel(out['replay']['zy'], t['zy'])

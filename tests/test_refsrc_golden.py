@@ -78,6 +78,8 @@ def test_oracle_equals_the_reference_source(path, mode):
     assert rel(four, z[f'{mode}:loss4']) <= TOL64
     assert rel(xs, z[f'{mode}:sample']) <= TOL64
     assert abs(float(np.mean(ps['logdet'])) - float(z[f'{mode}:logdet_mean'])) <= TOL64 * abs(float(z[f'{mode}:logdet_mean']))
+    # per-sample log-dets: the reference returns only their batch mean (quirk Q1), so the fixture holds batch-of-one calls
+    assert rel(ps['logdet'], z[f'{mode}:logdet_ps']) <= TOL64
     assert np.abs(back - xy).max() <= 1e-9            # and the restated inverse undoes the restated forward
 
 
